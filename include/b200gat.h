@@ -1,0 +1,143 @@
+/* b200gat.h -- C ABI of libb200gat.so: the B200 (sm_100a) GAT training hot path.
+ *
+ * The reference (Axionis47/PlotPointe-GAT-Recommendation) is pure Python and has no FFI of its own;
+ * the interface it offers for this path is two torch modules and five loss lines.  Each entry point
+ * below names the reference lines it replaces.  A Python/ctypes binding (the one this repo ships in
+ * plotpointe-gat-recommendation_b200/_lib.py, and the one a reference maintainer would add -- see
+ * INTEGRATION.md) passes raw device pointers, sizes and a cudaStream_t; there are no torch types in
+ * any signature.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer unless it says "host"; buffers are caller-owned;
+ *   - all float tensors are fp32, row-major, 16-byte aligned; index outputs are int32;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); every call is asynchronous;
+ *   - return value: 0 = ok, <0 = error (B200GAT_ERR_*); b200gat_last_error() returns the message of
+ *     the last failure on the calling host thread;
+ *   - there is no CPU path: with no CUDA device every launch fails with B200GAT_ERR_CUDA.
+ */
+#ifndef B200GAT_H_
+#define B200GAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GAT_ABI_VERSION 1
+
+#define B200GAT_ERR_ARG (-1)
+#define B200GAT_ERR_CUDA (-2)
+#define B200GAT_ERR_UNSUPPORTED (-3)
+#define B200GAT_ERR_WORKSPACE (-4)
+
+/* softmax dialect of the edge kernels */
+#define B200GAT_POLICY_CUSTOM 0 /* SimpleGATLayer: clamp[-10,10], no max, denom+1e-9 (train_gat_custom.py:80-88) */
+#define B200GAT_POLICY_PYG 1    /* PyG GATConv: max-subtracted, denom+1e-16, head mean + bias (train_gat_pyg.py:77,87) */
+
+#define B200GAT_LOSS_BPR 0 /* train_gat_custom.py:354-355 */
+#define B200GAT_LOSS_BCE 1 /* train_gat_custom.py:356-359 */
+
+const char* b200gat_last_error(void);
+int b200gat_abi_version(void);
+
+/* ---- (1) COO -> CSR/CSC -------------------------------------------------------------------------
+ * Replaces the edge ordering that the reference's per-edge scatter ops imply
+ * (denom.scatter_add_ / out.index_add_ over edge_index, scripts/train_gat_custom.py:85-92; the list
+ * itself comes from build_edge_index, :166-175).  CSR = stable sort by destination (edge_index row
+ * 1), CSC = stable sort by source (row 0); duplicates kept; bit-exact with
+ * `edge_index[1].argsort(stable=True)`.
+ *   edge_index : int64 [2, n_edges] (row 0 = src, row 1 = dst)
+ *   rowptr,colptr : int32 [n_nodes+1]     col : src ids in CSR order     row : dst ids in CSC order
+ *   perm, perm_csc : original edge ids in CSR / CSC order
+ *   csr2csc : CSC position of the edge at each CSR position
+ *   n_bad : device int32, number of edges with an endpoint outside [0, n_nodes) (caller checks == 0)
+ */
+int b200gat_graph_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes /*host*/);
+int b200gat_build_graph(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t* rowptr, int32_t* col,
+                        int32_t* perm, int32_t* colptr, int32_t* row, int32_t* perm_csc, int32_t* csr2csc,
+                        int32_t* n_bad, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (2) projection + attention logits ----------------------------------------------------------
+ * h = x W^T (self.lin(x), train_gat_custom.py:77; GATConv.lin) and the per-node halves of the edge
+ * logit, s[:, 0:H] = (h * a_src).sum(-1), s[:, H:2H] = (h * a_dst).sum(-1) (:79).
+ *   x [n_rows, in_features]; W [heads*channels, in_features]; a_src, a_dst [heads, channels]
+ *   h [n_rows, heads*channels]; s [n_rows, 2*heads]
+ * precision: B200GAT_GEMM_FP32 = CUDA-core FFMA; B200GAT_GEMM_TF32X3 = tcgen05 tensor cores with a
+ * 3-term TF32 split (fp32-accurate); B200GAT_GEMM_BF16 = tcgen05 bf16 inputs, fp32 accumulation.
+ */
+#define B200GAT_GEMM_FP32 0
+#define B200GAT_GEMM_TF32X3 1
+#define B200GAT_GEMM_BF16 2
+int b200gat_project_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                        int in_features, int heads, int channels, float* h, float* s, void* stream);
+
+/* Backward of (2).  `dh` holds the aggregation part on entry and is overwritten with the full
+ * gradient of h (adds ds_src*a_src + ds_dst*a_dst); ds = [ds_src | ds_dst] [n_rows, 2*heads].
+ * Outputs: dx [n_rows, in_features] (may be NULL), dW [heads*channels, in_features], da_src, da_dst. */
+int b200gat_dense_workspace_bytes(int heads, int channels, int in_features, size_t* bytes /*host*/);
+int b200gat_project_bwd_f32(const float* x, const float* W, const float* a_src, const float* a_dst, float* dh,
+                            const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx,
+                            float* dW, float* da_src, float* da_dst, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* out[c] = sum_n a[n, c] in a fixed order (GATConv bias gradient). workspace >= 296*channels floats. */
+int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, float* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- (3) fused edge forward ---------------------------------------------------------------------
+ * Replaces train_gat_custom.py:79-92 (logit, LeakyReLU, clamp, exp, scatter_add denominator,
+ * normalise, dropout, index_add aggregate) / GATConv's propagate at train_gat_pyg.py:87.
+ * One warp per destination row `row_offset + r`, r in [0, n_rows).
+ *   h [*, heads*channels], s [*, 2*heads] : indexed by global node id
+ *   rowptr [n_rows+1] (already offset to the first local row), col/perm : CSR arrays
+ *   bias [channels] or NULL; out [n_rows, channels] (head mean + bias)
+ *   out_heads [n_rows, heads, channels] or NULL (per-head outputs, needed by the backward if heads>1)
+ *   rowstat [n_rows, heads, 2] = (running max m (0 for CUSTOM), 1/(denominator+eps)) or NULL
+ *   p_drop/seed : attention dropout (0 = off); the mask is a function of (seed, original edge id,
+ *   head) only.
+ */
+int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* rowptr, const int32_t* col,
+                         const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels, int policy,
+                         float negative_slope, const float* bias, float* out, float* out_heads, float* rowstat,
+                         float p_drop, uint64_t seed, void* stream);
+
+/* ---- (4) fused edge backward --------------------------------------------------------------------
+ * Replaces autograd's replay of the lines above (loss.backward(), train_gat_custom.py:361).
+ * node_prep : nodestat[r,h] = (s_dst, m, 1/D, t), t = (1/H) dout[r,:].out_heads[r,h,:]
+ *             (for heads==1 pass out as out_heads, and bias to subtract it if it was added)
+ * edge_bwd  : warp per SOURCE row over the CSC: dh[r,:,:] = sum_i alpha_ij dout_i / H (no atomics),
+ *             de[q,h] = d loss / d logit for CSC position q, ds_src[r*ld_ds + h] = sum_q de
+ * ds_dst    : ds_dst[r*ld_ds + h] = sum over the in-edges of r (CSR order) of de[csr2csc[e], h]
+ */
+int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
+                          const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
+                          float* nodestat, void* stream);
+int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
+                         const int32_t* colptr, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
+                         int64_t row_offset, int heads, int channels, int policy, float negative_slope, float* dh,
+                         float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream);
+int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int heads,
+                       float* ds_dst, int ld_ds, void* stream);
+
+/* ---- (5) fused ranking loss ---------------------------------------------------------------------
+ * Replaces train_gat_custom.py:350-359: pos/neg dot products of gathered rows of Z, BPR
+ * -log(sigmoid(pos-neg)+1e-8).mean() or BCE-with-logits, and (bwd) the duplicate-row index_put.
+ *   z [n_users+n_items, channels]; u, i, j int64 [n_triples] (i, j are item ids, not node ids)
+ *   loss : device float[1]; an out-of-range triple makes it NaN.
+ *   The forward leaves per-triple coefficients and node-sorted incidence lists in `workspace`; pass the
+ *   same workspace to the backward.  grad_out : device float[1].  dz [n_users+n_items, channels],
+ *   every row written (rows without triples = 0); no atomics, bitwise reproducible.
+ */
+int b200gat_loss_workspace_bytes(int64_t n_nodes, int64_t n_triples, size_t* bytes /*host*/);
+int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
+                              const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind, int need_backward,
+                              float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
+                              const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
+                              const float* grad_out, float* dz, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GAT_H_ */

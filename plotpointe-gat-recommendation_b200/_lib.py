@@ -1,0 +1,112 @@
+"""ctypes binding of libb200gat.so (the C ABI declared in include/b200gat.h).
+
+PyTorch is used for device memory and streams only: every call below hands raw device pointers, sizes
+and the current CUDA stream to the library.  There is no CPU fallback -- if the shared library is
+missing this module raises at import, and every wrapper rejects non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gat.so")
+
+POLICY_CUSTOM, POLICY_PYG = 0, 1
+LOSS_BPR, LOSS_BCE = 0, 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: the CUDA library has not been built. Run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` (or plotpointe-gat-recommendation_b200/csrc/build.sh). "
+        "There is no CPU fallback for this package.")
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_P = c_void_p
+_SIGS = {
+    "b200gat_last_error": (ctypes.c_char_p, []),
+    "b200gat_abi_version": (c_int, []),
+    "b200gat_graph_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
+    "b200gat_build_graph": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "b200gat_project_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "b200gat_dense_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "b200gat_project_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                                        c_size_t, _P]),
+    "b200gat_colsum_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "b200gat_edge_fwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P, _P, _P,
+                                     c_float, c_uint64, _P]),
+    "b200gat_node_prep_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P]),
+    "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P,
+                                     _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_ds_dst_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P]),
+    "b200gat_loss_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
+    "b200gat_rank_loss_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, c_int, c_int, _P, _P,
+                                          c_size_t, _P]),
+    "b200gat_rank_loss_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, _P, _P, c_size_t,
+                                          _P]),
+}
+EXPORTS = tuple(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(_lib, _name)      # AttributeError here = header/library mismatch: fail at import
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+launch_count = 0   # number of C-ABI calls that launched device work (bench.py reads this)
+
+
+def last_error() -> str:
+    return _lib.b200gat_last_error().decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t, offset_elems: int = 0):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("b200gat: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("b200gat: expected a contiguous tensor")
+    return c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"b200gat: {name} must be float32, got {t.dtype}")
+    return t
+
+
+def call(name: str, *args) -> None:
+    global launch_count
+    launch_count += 1
+    _check(getattr(_lib, name)(*args), name)
+
+
+def graph_workspace_bytes(n_nodes: int, n_edges: int) -> int:
+    out = c_size_t(0)
+    _check(_lib.b200gat_graph_workspace_bytes(n_nodes, n_edges, ctypes.byref(out)), "graph_workspace_bytes")
+    return out.value
+
+
+def dense_workspace_bytes(heads: int, channels: int, in_features: int) -> int:
+    out = c_size_t(0)
+    _check(_lib.b200gat_dense_workspace_bytes(heads, channels, in_features, ctypes.byref(out)), "dense_workspace_bytes")
+    return out.value
+
+
+def loss_workspace_bytes(n_nodes: int, n_triples: int) -> int:
+    out = c_size_t(0)
+    _check(_lib.b200gat_loss_workspace_bytes(n_nodes, n_triples, ctypes.byref(out)), "loss_workspace_bytes")
+    return out.value

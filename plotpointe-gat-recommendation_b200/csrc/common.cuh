@@ -1,0 +1,94 @@
+// Shared helpers for the b200gat CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200gat {
+
+// ---- error plumbing -------------------------------------------------------------------------
+// Every extern "C" entry point returns 0 on success or a negative code; the message of the last
+// failure on this host thread is kept for b200gat_last_error().
+enum : int { kOk = 0, kErrArg = -1, kErrCuda = -2, kErrUnsupported = -3, kErrWorkspace = -4 };
+
+void set_error(const char* fmt, ...);
+
+#define B200GAT_CHECK_ARG(cond, ...)                    \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      ::b200gat::set_error(__VA_ARGS__);                \
+      return ::b200gat::kErrArg;                        \
+    }                                                   \
+  } while (0)
+
+#define B200GAT_CUDA(call)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ::b200gat::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return ::b200gat::kErrCuda;                                                            \
+    }                                                                                        \
+  } while (0)
+
+#define B200GAT_LAUNCH_CHECK() B200GAT_CUDA(cudaGetLastError())
+
+// ---- device helpers -------------------------------------------------------------------------
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// 128-bit read-only gather load (feature rows are read many times: keep them in L1/L2).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 128-bit load / store for data touched once (do not pollute L1)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float4 fma4(float a, float4 b, float4 c) {
+  c.x = fmaf(a, b.x, c.x);
+  c.y = fmaf(a, b.y, c.y);
+  c.z = fmaf(a, b.z, c.z);
+  c.w = fmaf(a, b.w, c.w);
+  return c;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- shared host-side building blocks (graph.cu) -------------------------------------------------
+// Stable LSD radix sort of (key, iota) pairs by int32 key in [0, key_range); vals_out = the stable
+// argsort.  workspace: sort_workspace_bytes(n).
+size_t sort_workspace_bytes(int64_t n);
+int sort_pairs_stable(const int32_t* keys, int64_t n, int64_t key_range, int32_t* keys_out, int32_t* vals_out,
+                      void* workspace, cudaStream_t st);
+// ptr[v] = first position in `sorted` with key >= v, for v in [0, n_nodes]
+int node_ptr_from_sorted(const int32_t* sorted, int64_t n, int64_t n_nodes, int32_t* ptr, cudaStream_t st);
+
+}  // namespace b200gat

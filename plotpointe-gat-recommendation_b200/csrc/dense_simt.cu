@@ -1,0 +1,257 @@
+// fp32 CUDA-core dense kernels around the projection h = x W^T (scripts/train_gat_custom.py:77):
+// a strided tiled SGEMM (NT / NN / TN-with-split reduction), the attention-logit row dots
+// ((h*a).sum(-1), train_gat_custom.py:79), and the small parameter-gradient finalisers.
+// This is the strict-fp32 path (true FFMA accumulation); the tensor-core path lives in
+// gemm_tcgen05.cu and is validated against this one.
+#include "common.cuh"
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+
+// C[m,n] (+)= sum_k A(m,k) * B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
+// blockIdx.z selects a K-slab [z*k_slab, min(K,(z+1)*k_slab)) written to C + z*c_slab_stride.
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+
+template <bool A_KMAJOR /*sak==1*/, bool B_NMAJOR /*sbn==1*/>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
+                                                    const float* __restrict__ B, int64_t sbk, int64_t sbn,
+                                                    float* __restrict__ Cm, int64_t ldc, int M, int N, int64_t K,
+                                                    int64_t k_slab, int64_t c_slab_stride,
+                                                    const float* __restrict__ bias /*[N] or null*/) {
+  __shared__ float As[kBK][kBM + 4];
+  __shared__ float Bs[kBK][kBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 micro-tile
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int64_t kbeg = blockIdx.z * k_slab;
+  const int64_t kend = min(K, kbeg + k_slab);
+  float acc[4][4] = {};
+  for (int64_t k0 = kbeg; k0 < kend; k0 += kBK) {
+    // A tile: 64 x 16
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * 256;
+      int mm, kk;
+      if (A_KMAJOR) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+      const int gm = m0 + mm;
+      const int64_t gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < kend) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * 256;
+      int nn, kk;
+      if (B_NMAJOR) { nn = idx & 63; kk = idx >> 6; } else { kk = idx & 15; nn = idx >> 4; }
+      const int gn = n0 + nn;
+      const int64_t gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < kend) ? __ldg(B + gk * sbk + gn * sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Cz = Cm + blockIdx.z * c_slab_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) Cz[(int64_t)gm * ldc + gn] = acc[i][j] + (bias ? bias[gn] : 0.f);
+    }
+  }
+}
+
+// out[i] = sum_z part[z*stride + i], fixed order (deterministic split-K reduction)
+__global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs, int64_t stride, int64_t n,
+                                    float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int z = 0; z < n_slabs; ++z) a += part[z * stride + i];
+  out[i] = a;
+}
+
+static int launch_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                        int64_t ldc, int M, int N, int64_t K, int n_slabs, int64_t k_slab, int64_t c_slab_stride,
+                        const float* bias, cudaStream_t st) {
+  dim3 grid(ceil_div(N, kBN), ceil_div(M, kBM), n_slabs);
+  const bool ak = sak == 1, bn = sbn == 1;
+  if (ak && bn) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else if (ak && !bn) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else if (!ak && bn) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// s[n, 0:H] = (h[n,hh,:] . a_src[hh,:]),  s[n, H:2H] = (h[n,hh,:] . a_dst[hh,:])   (warp per row)
+__global__ void __launch_bounds__(128) logits_kernel(const float* __restrict__ h, const float* __restrict__ a_src,
+                                                     const float* __restrict__ a_dst, int64_t n_rows, int H, int C,
+                                                     float* __restrict__ s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  for (int hh = 0; hh < H; ++hh) {
+    float ps = 0.f, pd = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = ldg4(h + (r * H + hh) * C + c);
+      ps += dot4(v, ldg4(a_src + hh * C + c));
+      pd += dot4(v, ldg4(a_dst + hh * C + c));
+    }
+    ps = warp_sum(ps);
+    pd = warp_sum(pd);
+    if (lane == 0) {
+      s[r * (2 * H) + hh] = ps;
+      s[r * (2 * H) + H + hh] = pd;
+    }
+  }
+}
+
+// dh[n,hh,c] += ds_src[n,hh]*a_src[hh,c] + ds_dst[n,hh]*a_dst[hh,c]   (gradient of the two row dots)
+__global__ void add_logit_grad_kernel(float* __restrict__ dh, const float* __restrict__ ds, const float* __restrict__ a_src,
+                                      const float* __restrict__ a_dst, int64_t n_rows, int H, int C) {
+  const int64_t HC4 = (int64_t)H * C / 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_rows * HC4;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / HC4;
+    const int off = (int)(idx - r * HC4) * 4;
+    const int hh = off / C;
+    const float gs = ds[r * (2 * H) + hh], gd = ds[r * (2 * H) + H + hh];
+    float4 v = *reinterpret_cast<float4*>(dh + r * H * C + off);
+    const float4 as = ldg4(a_src + off), ad = ldg4(a_dst + off);
+    v.x += gs * as.x + gd * ad.x;
+    v.y += gs * as.y + gd * ad.y;
+    v.z += gs * as.z + gd * ad.z;
+    v.w += gs * as.w + gd * ad.w;
+    *reinterpret_cast<float4*>(dh + r * H * C + off) = v;
+  }
+}
+
+// da_src[hh,c] = W[hh*C+c,:] . v[hh,:],  da_dst[hh,c] = W[hh*C+c,:] . v[H+hh,:]
+//   where v = [ds_src | ds_dst]^T x   (== h^T ds since h = x W^T)
+__global__ void att_grad_kernel(const float* __restrict__ W, const float* __restrict__ v, int H, int C, int F,
+                                float* __restrict__ da_src, float* __restrict__ da_dst) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // hh*C + c
+  if (row >= H * C) return;
+  const int hh = row / C;
+  float ps = 0.f, pd = 0.f;
+  for (int k = lane; k < F; k += 32) {
+    const float w = W[(int64_t)row * F + k];
+    ps += w * v[(int64_t)hh * F + k];
+    pd += w * v[(int64_t)(H + hh) * F + k];
+  }
+  ps = warp_sum(ps);
+  pd = warp_sum(pd);
+  if (lane == 0) { da_src[row] = ps; da_dst[row] = pd; }
+}
+
+// column sums of a [n, C] matrix with a fixed reduction tree: slabs of rows -> partial[slab, C] -> out[C]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ a, int64_t n, int C, int64_t rows_per_slab,
+                                                             float* __restrict__ part) {
+  const int64_t r0 = blockIdx.x * rows_per_slab, r1 = min(n, r0 + rows_per_slab);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += a[r * C + c];
+    part[(int64_t)blockIdx.x * C + c] = acc;
+  }
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+static const int kSlabs = 2 * kNumSMs;  // split count for reductions over the node dimension
+
+extern "C" int b200gat_dense_workspace_bytes(int heads, int channels, int in_features, size_t* bytes) {
+  B200GAT_CHECK_ARG(bytes, "null");
+  const size_t hc = (size_t)heads * channels;
+  *bytes = ((size_t)kSlabs * (hc + 2 * heads) * in_features + (size_t)kSlabs * channels + 2 * heads * in_features) * sizeof(float) + 1024;
+  return kOk;
+}
+
+// h = x W^T ; s = [h.a_src | h.a_dst]
+extern "C" int b200gat_project_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                                   int in_features, int heads, int channels, float* h, float* s, void* stream) {
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && h && s, "null pointer");
+  B200GAT_CHECK_ARG(channels % 4 == 0 && in_features > 0, "bad dims");
+  if (n_rows == 0) return kOk;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HC = heads * channels;
+  B200GAT_CHECK_ARG(n_rows < 2147483647LL, "n_rows too large");
+  int rc = launch_sgemm(x, in_features, 1, W, 1, in_features, h, HC, (int)n_rows, HC, in_features, 1, in_features, 0,
+                        nullptr, st);
+  if (rc) return rc;
+  logits_kernel<<<ceil_div(n_rows * 32, 128), 128, 0, st>>>(h, a_src, a_dst, n_rows, heads, channels, s);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// Given dh (aggregation part, overwritten with the full dh) and ds = [ds_src|ds_dst]:
+//   dx = dh W ; dW = dh^T x ; da_src, da_dst
+extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const float* a_src, const float* a_dst,
+                                       float* dh, const float* ds, int64_t n_rows, int in_features, int heads,
+                                       int channels, float* dx /*nullable*/, float* dW, float* da_src, float* da_dst,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && dh && ds && dW && da_src && da_dst && workspace, "null pointer");
+  size_t need;
+  b200gat_dense_workspace_bytes(heads, channels, in_features, &need);
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HC = heads * channels, F = in_features, H2 = 2 * heads;
+  float* part = (float*)workspace;                       // [kSlabs, HC + 2H, F]
+  float* v = part + (size_t)kSlabs * (HC + H2) * F + (size_t)kSlabs * channels;  // [2H, F]
+  if (n_rows == 0) {
+    B200GAT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * HC * F, st));
+    B200GAT_CUDA(cudaMemsetAsync(da_src, 0, sizeof(float) * HC, st));
+    B200GAT_CUDA(cudaMemsetAsync(da_dst, 0, sizeof(float) * HC, st));
+    return kOk;
+  }
+  add_logit_grad_kernel<<<kNumSMs * 8, 256, 0, st>>>(dh, ds, a_src, a_dst, n_rows, heads, channels);
+  B200GAT_LAUNCH_CHECK();
+  int rc;
+  if (dx) {  // dx[n,f] = sum_m dh[n,m] W[m,f]
+    rc = launch_sgemm(dh, HC, 1, W, F, 1, dx, F, (int)n_rows, F, HC, 1, HC, 0, nullptr, st);
+    if (rc) return rc;
+  }
+  const int64_t k_slab = (n_rows + kSlabs - 1) / kSlabs;
+  const int n_slabs = (int)((n_rows + k_slab - 1) / k_slab);
+  // dW[m,f] = sum_n dh[n,m] x[n,f]
+  rc = launch_sgemm(dh, 1, HC, x, F, 1, part, F, HC, F, n_rows, n_slabs, k_slab, (int64_t)HC * F, nullptr, st);
+  if (rc) return rc;
+  reduce_slabs_kernel<<<ceil_div((int64_t)HC * F, 256), 256, 0, st>>>(part, n_slabs, (int64_t)HC * F, (int64_t)HC * F, dW);
+  // v[q,f] = sum_n ds[n,q] x[n,f]
+  float* part_v = part + (size_t)kSlabs * HC * F;
+  rc = launch_sgemm(ds, 1, H2, x, F, 1, part_v, F, H2, F, n_rows, n_slabs, k_slab, (int64_t)H2 * F, nullptr, st);
+  if (rc) return rc;
+  reduce_slabs_kernel<<<ceil_div((int64_t)H2 * F, 256), 256, 0, st>>>(part_v, n_slabs, (int64_t)H2 * F, (int64_t)H2 * F, v);
+  att_grad_kernel<<<ceil_div((int64_t)HC * 32, 128), 128, 0, st>>>(W, v, heads, channels, F, da_src, da_dst);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// dbias[c] = sum_n dout[n,c]
+extern "C" int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(a && out && workspace, "null pointer");
+  B200GAT_CHECK_ARG(workspace_bytes >= (size_t)kSlabs * channels * sizeof(float), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows == 0) { B200GAT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, st)); return kOk; }
+  const int64_t rps = (n_rows + kSlabs - 1) / kSlabs;
+  const int n_slabs = (int)((n_rows + rps - 1) / rps);
+  colsum_partial_kernel<<<n_slabs, 256, 0, st>>>(a, n_rows, channels, rps, (float*)workspace);
+  reduce_slabs_kernel<<<ceil_div(channels, 256), 256, 0, st>>>((const float*)workspace, n_slabs, channels, channels, out);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

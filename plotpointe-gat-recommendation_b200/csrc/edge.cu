@@ -1,0 +1,458 @@
+// Fused GAT edge kernels: one forward launch and one backward (CSC) launch per layer.
+//
+// Forward  (replaces scripts/train_gat_custom.py:79-92 and the PyG GATConv message passing called
+//          at scripts/train_gat_pyg.py:87): warp per destination row over the CSR built in
+//          graph.cu; logits from the per-node scalars s_src/s_dst; LeakyReLU; segment softmax with
+//          warp shuffles (custom dialect: clamp[-10,10], no max, +1e-9; PyG dialect: online max,
+//          +1e-16); 128-bit gathers of h[src]; weighted aggregation; head mean + bias.  No E-sized
+//          float tensor is ever written.
+// Backward (replaces autograd's replay of the same lines, train_gat_custom.py:361): warp per SOURCE
+//          row over the CSC; gathers dout[dst] once per edge, recomputes alpha from per-node
+//          scalars, accumulates dh[src] in registers (no atomics), emits the logit gradient
+//          de per edge (E*H floats, the only E-sized scratch) and ds_src; a scalar CSR pass then
+//          reduces de per destination into ds_dst.
+//
+// Row width is H*C floats with C a multiple of 128 (lane l owns channels [4l,4l+4) of every
+// 128-wide chunk), H in {1,2,4}.
+#include "common.cuh"
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+
+constexpr int kCustom = B200GAT_POLICY_CUSTOM;
+constexpr int kPyG = B200GAT_POLICY_PYG;
+
+// ---- counter-based RNG for attention dropout (Philox-4x32-10) -----------------------------------
+// keyed on (seed, original edge id, head) so the forward (CSR order) and backward (CSC order)
+// passes regenerate the same mask without storing it.
+__device__ __forceinline__ uint32_t philox_uniform_bits(uint64_t seed, uint32_t edge_id, uint32_t head) {
+  uint32_t c0 = edge_id, c1 = head, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+// keep-scale: 1/(1-p) with probability 1-p, else 0
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t edge_id, uint32_t head, float p, float inv_keep) {
+  float u = (philox_uniform_bits(seed, edge_id, head) >> 8) * (1.0f / 16777216.0f);  // [0,1)
+  return u >= p ? inv_keep : 0.0f;
+}
+
+template <int POLICY>
+__device__ __forceinline__ float activate(float z0, float neg_slope) {
+  float z = z0 > 0.f ? z0 : z0 * neg_slope;
+  if (POLICY == kCustom) z = fminf(fmaxf(z, -10.f), 10.f);  // train_gat_custom.py:82
+  return z;
+}
+
+template <int H, int CV>
+struct Unroll {
+  static constexpr int value = (H * CV >= 8) ? 1 : (H * CV >= 4 ? 2 : (H * CV >= 2 ? 4 : 8));
+};
+
+// --------------------------------------------------------------------------------------------
+// forward
+// --------------------------------------------------------------------------------------------
+template <int POLICY, int H, int CV, bool DROPOUT>
+__global__ void __launch_bounds__(128) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+                                                       const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ col,
+                                                       const int32_t* __restrict__ perm, int n_rows, int row_offset,
+                                                       float neg_slope, const float* __restrict__ bias,
+                                                       float* __restrict__ out, float* __restrict__ out_heads,
+                                                       float2* __restrict__ rowstat, float p_drop, uint64_t seed) {
+  constexpr int C = CV * 128;
+  constexpr int HC = H * C;
+  constexpr int U = Unroll<H, CV>::value;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= n_rows) return;
+  const int beg = rowptr[r], end = rowptr[r + 1];
+  const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
+
+  float sd[H], m[H], l[H];
+  float4 acc[H][CV];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    sd[hh] = s[(size_t)(row_offset + r) * (2 * H) + H + hh];
+    m[hh] = POLICY == kPyG ? -INFINITY : 0.f;
+    l[hh] = 0.f;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    int c = valid ? col[e] : 0;
+    float p[H];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      float z = -INFINITY;
+      if (valid) z = activate<POLICY>(s[(size_t)c * (2 * H) + hh] + sd[hh], neg_slope);
+      if (POLICY == kPyG) {
+        const float nm = fmaxf(m[hh], warp_max(z));
+        if (nm != m[hh]) {  // warp-uniform
+          const float scale = expf(m[hh] - nm);
+          l[hh] *= scale;
+#pragma unroll
+          for (int cv = 0; cv < CV; ++cv) {
+            acc[hh][cv].x *= scale; acc[hh][cv].y *= scale; acc[hh][cv].z *= scale; acc[hh][cv].w *= scale;
+          }
+          m[hh] = nm;
+        }
+        p[hh] = valid ? expf(z - nm) : 0.f;
+      } else {
+        p[hh] = valid ? expf(z) : 0.f;
+      }
+      l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
+      if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)perm[e], hh, p_drop, inv_keep);
+    }
+    // zero-weight tail lanes re-read lane 0's row so they add no new cache lines
+    const int c0 = __shfl_sync(kFull, c, 0);
+    if (!valid) c = c0;
+    const int cnt = min(32, end - base);
+    for (int k = 0; k < cnt; k += U) {
+      float4 v[U][H][CV];
+      float pk[U][H];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ck = __shfl_sync(kFull, c, (k + u) & 31);
+        const float* hp = h + (size_t)ck * HC + lane * 4;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+          pk[u][hh] = __shfl_sync(kFull, p[hh], (k + u) & 31);
+#pragma unroll
+          for (int cv = 0; cv < CV; ++cv) v[u][hh][cv] = ldg4(hp + hh * C + cv * 128);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh)
+#pragma unroll
+          for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk[u][hh], v[u][hh][cv], acc[hh][cv]);
+    }
+  }
+
+  float inv[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    const float lt = warp_sum(l[hh]);
+    inv[hh] = 1.f / (lt + (POLICY == kCustom ? 1e-9f : 1e-16f));
+    if (lane == 0 && rowstat) rowstat[(size_t)r * H + hh] = make_float2(beg < end ? m[hh] : 0.f, inv[hh]);
+  }
+#pragma unroll
+  for (int cv = 0; cv < CV; ++cv) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      float4 a = acc[hh][cv];
+      a.x *= inv[hh]; a.y *= inv[hh]; a.z *= inv[hh]; a.w *= inv[hh];
+      if (out_heads) st_stream4(out_heads + (size_t)r * HC + hh * C + cv * 128 + lane * 4, a);
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
+    if (bias) {
+      const float4 b = ldg4(bias + cv * 128 + lane * 4);
+      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward, step 0: per-destination scalars  nodestat[i,h] = (s_dst, m, 1/D, t)
+//   t[i,h] = (1/H) * dout[i,:] . out_h[i,h,:]   (= sum_k alpha_ik dalpha_ik)
+// --------------------------------------------------------------------------------------------
+template <int H, int CV>
+__global__ void __launch_bounds__(128) node_prep_kernel(const float* __restrict__ dout,       // [n_rows, C]
+                                                        const float* __restrict__ out_heads,  // [n_rows, H, C]
+                                                        const float* __restrict__ bias,       // subtracted (H==1, PyG)
+                                                        const float* __restrict__ s, const float2* __restrict__ rowstat,
+                                                        int n_rows, int row_offset, float4* __restrict__ nodestat) {
+  constexpr int C = CV * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= n_rows) return;
+  float t[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) t[hh] = 0.f;
+#pragma unroll
+  for (int cv = 0; cv < CV; ++cv) {
+    const float4 g = ld_stream4(dout + (size_t)r * C + cv * 128 + lane * 4);
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      float4 o = ld_stream4(out_heads + ((size_t)r * H + hh) * C + cv * 128 + lane * 4);
+      if (bias) {
+        const float4 b = ldg4(bias + cv * 128 + lane * 4);
+        o.x -= b.x; o.y -= b.y; o.z -= b.z; o.w -= b.w;
+      }
+      t[hh] += dot4(g, o);
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    const float tt = warp_sum(t[hh]) * (1.f / H);
+    if (lane == 0) {
+      const float2 rs = rowstat[(size_t)r * H + hh];
+      nodestat[(size_t)r * H + hh] = make_float4(s[(size_t)(row_offset + r) * (2 * H) + H + hh], rs.x, rs.y, tt);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward, step 1: CSC pass (warp per source row)
+// --------------------------------------------------------------------------------------------
+template <int POLICY, int H, int CV, bool DROPOUT>
+__global__ void __launch_bounds__(128) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+                                                       const float* __restrict__ dout,
+                                                       const float4* __restrict__ nodestat,
+                                                       const int32_t* __restrict__ colptr,
+                                                       const int32_t* __restrict__ row,
+                                                       const int32_t* __restrict__ perm_csc, int n_rows, int row_offset,
+                                                       float neg_slope, float* __restrict__ dh,
+                                                       float* __restrict__ de, float* __restrict__ ds_src,
+                                                       int ld_ds, float p_drop, uint64_t seed) {
+  constexpr int C = CV * 128;
+  constexpr int HC = H * C;
+  constexpr int U = Unroll<1, CV>::value >= 4 ? 4 : Unroll<1, CV>::value;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= n_rows) return;
+  const int beg = colptr[r], end = colptr[r + 1];
+  const size_t j = (size_t)row_offset + r;
+  const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
+  constexpr float invH = 1.f / H;
+
+  float4 hj[H][CV], acc[H][CV];
+  float ssj[H], dss[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    ssj[hh] = s[j * (2 * H) + hh];
+    dss[hh] = 0.f;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) {
+      hj[hh][cv] = (beg < end) ? ldg4(h + j * HC + hh * C + cv * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  for (int base = beg; base < end; base += 32) {
+    const int q = base + lane;
+    const bool valid = q < end;
+    int i = valid ? row[q] : 0;
+    float alpha[H], agg[H], gsc[H], tt[H], ks[H], my_de[H];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      alpha[hh] = agg[hh] = gsc[hh] = tt[hh] = my_de[hh] = 0.f;
+      ks[hh] = 1.f;
+      if (valid) {
+        const float4 st = __ldg(nodestat + (size_t)i * H + hh);  // (s_dst, m, 1/D, t)
+        const float z0 = ssj[hh] + st.x;
+        const float zl = z0 > 0.f ? z0 : z0 * neg_slope;
+        float zc = zl, pass = 1.f;
+        if (POLICY == kCustom) {
+          zc = fminf(fmaxf(zl, -10.f), 10.f);
+          pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;  // clamp passes gradient only inside [-10,10]
+        }
+        alpha[hh] = expf(zc - st.y) * st.z;
+        gsc[hh] = (z0 > 0.f ? 1.f : neg_slope) * pass;
+        tt[hh] = st.w;
+        if (DROPOUT) ks[hh] = dropout_scale(seed, (uint32_t)perm_csc[q], hh, p_drop, inv_keep);
+        agg[hh] = alpha[hh] * ks[hh] * invH;
+      }
+    }
+    const int i0 = __shfl_sync(kFull, i, 0);
+    if (!valid) i = i0;
+    const int cnt = min(32, end - base);
+    for (int k = 0; k < cnt; k += U) {
+      float4 g[U][CV];
+      int kk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        kk[u] = (k + u) & 31;
+        const int ik = __shfl_sync(kFull, i, kk[u]);
+#pragma unroll
+        for (int cv = 0; cv < CV; ++cv) g[u][cv] = ldg4(dout + (size_t)ik * C + cv * 128 + lane * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+          const float a = __shfl_sync(kFull, agg[hh], kk[u]);
+          float d = 0.f;
+#pragma unroll
+          for (int cv = 0; cv < CV; ++cv) {
+            acc[hh][cv] = fma4(a, g[u][cv], acc[hh][cv]);
+            d += dot4(hj[hh][cv], g[u][cv]);
+          }
+          d = warp_sum(d) * invH;  // d(out)/d(alpha'_ij) for this head
+          if (lane == kk[u]) my_de[hh] = alpha[hh] * (d * ks[hh] - tt[hh]) * gsc[hh];
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {
+        de[(size_t)q * H + hh] = my_de[hh];
+        dss[hh] += my_de[hh];
+      }
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    const float t = warp_sum(dss[hh]);
+    if (lane == 0) ds_src[(size_t)r * ld_ds + hh] = t;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv)
+      *reinterpret_cast<float4*>(dh + (size_t)r * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward, step 2: ds_dst[i,h] = sum over in-edges of de (CSR order, via the CSR->CSC map)
+// --------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(128) ds_dst_kernel(const float* __restrict__ de, const int32_t* __restrict__ rowptr,
+                                                     const int32_t* __restrict__ csr2csc, int n_rows,
+                                                     float* __restrict__ ds_dst, int ld_ds) {
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= n_rows) return;
+  const int beg = rowptr[r], end = rowptr[r + 1];
+  float a[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) a[hh] = 0.f;
+  for (int e = beg + lane; e < end; e += 32) {
+    const size_t q = (size_t)csr2csc[e];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) a[hh] += de[q * H + hh];
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    const float t = warp_sum(a[hh]);
+    if (lane == 0) ds_dst[(size_t)r * ld_ds + hh] = t;
+  }
+}
+
+// ---- dispatch helpers ---------------------------------------------------------------------------
+#define B200GAT_DISPATCH_HC(H_, CV_, ...)                                        \
+  if (H_ == 1 && CV_ == 1) { constexpr int kH = 1, kCV = 1; __VA_ARGS__; }        \
+  else if (H_ == 2 && CV_ == 1) { constexpr int kH = 2, kCV = 1; __VA_ARGS__; }   \
+  else if (H_ == 4 && CV_ == 1) { constexpr int kH = 4, kCV = 1; __VA_ARGS__; }   \
+  else if (H_ == 1 && CV_ == 2) { constexpr int kH = 1, kCV = 2; __VA_ARGS__; }   \
+  else if (H_ == 4 && CV_ == 2) { constexpr int kH = 4, kCV = 2; __VA_ARGS__; }   \
+  else { set_error("unsupported heads=%d channels=%d (heads in {1,2,4} x C=128, or heads in {1,4} x C=256)", H_, CV_ * 128); return kErrUnsupported; }
+
+static int check_shape(int heads, int channels) {
+  if (channels % 128 != 0 || channels <= 0) {
+    set_error("out_channels=%d must be a positive multiple of 128 (128-bit lane gathers)", channels);
+    return kErrUnsupported;
+  }
+  (void)heads;
+  return kOk;
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* rowptr, const int32_t* col,
+                                    const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels,
+                                    int policy, float negative_slope, const float* bias, float* out, float* out_heads,
+                                    float* rowstat, float p_drop, uint64_t seed, void* stream) {
+  B200GAT_CHECK_ARG(h && s && rowptr && out, "null pointer");
+  B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
+  B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
+  B200GAT_CHECK_ARG(p_drop == 0.f || perm, "dropout needs perm");
+  int rc = check_shape(heads, channels);
+  if (rc) return rc;
+  if (n_rows == 0) return kOk;
+  const int cv = channels / 128;
+  const int threads = 128;
+  const int grid = ceil_div(n_rows * 32, threads);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool drop = p_drop > 0.f;
+#define LAUNCH_FWD(P, D)                                                                                          \
+  edge_fwd_kernel<P, kH, kCV, D><<<grid, threads, 0, st>>>(h, s, rowptr, col, perm, (int)n_rows, (int)row_offset, \
+                                                           negative_slope, bias, out, out_heads, (float2*)rowstat,  \
+                                                           p_drop, seed)
+  B200GAT_DISPATCH_HC(heads, cv, {
+    if (policy == kCustom) { if (drop) LAUNCH_FWD(kCustom, true); else LAUNCH_FWD(kCustom, false); }
+    else { if (drop) LAUNCH_FWD(kPyG, true); else LAUNCH_FWD(kPyG, false); }
+  })
+#undef LAUNCH_FWD
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
+                                     const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
+                                     float* nodestat, void* stream) {
+  B200GAT_CHECK_ARG(dout && out_heads && s && rowstat && nodestat, "null pointer");
+  int rc = check_shape(heads, channels);
+  if (rc) return rc;
+  if (n_rows == 0) return kOk;
+  const int cv = channels / 128;
+  const int grid = ceil_div(n_rows * 32, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  B200GAT_DISPATCH_HC(heads, cv, {
+    node_prep_kernel<kH, kCV><<<grid, 128, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
+                                                   (int)row_offset, (float4*)nodestat);
+  })
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
+                                    const int32_t* colptr, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
+                                    int64_t row_offset, int heads, int channels, int policy, float negative_slope,
+                                    float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
+                                    void* stream) {
+  B200GAT_CHECK_ARG(h && s && dout && nodestat && colptr && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
+  B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
+  B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
+  B200GAT_CHECK_ARG(p_drop == 0.f || perm_csc, "dropout needs perm_csc");
+  int rc = check_shape(heads, channels);
+  if (rc) return rc;
+  if (n_rows == 0) return kOk;
+  const int cv = channels / 128;
+  const int grid = ceil_div(n_rows * 32, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool drop = p_drop > 0.f;
+#define LAUNCH_BWD(P, D)                                                                                             \
+  edge_bwd_kernel<P, kH, kCV, D><<<grid, 128, 0, st>>>(h, s, dout, (const float4*)nodestat, colptr, row, perm_csc,  \
+                                                       (int)n_rows, (int)row_offset, negative_slope, dh, de, ds_src, \
+                                                       ld_ds, p_drop, seed)
+  B200GAT_DISPATCH_HC(heads, cv, {
+    if (policy == kCustom) { if (drop) LAUNCH_BWD(kCustom, true); else LAUNCH_BWD(kCustom, false); }
+    else { if (drop) LAUNCH_BWD(kPyG, true); else LAUNCH_BWD(kPyG, false); }
+  })
+#undef LAUNCH_BWD
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows,
+                                  int heads, float* ds_dst, int ld_ds, void* stream) {
+  B200GAT_CHECK_ARG(rowptr && ds_dst && ld_ds >= heads, "null pointer / bad ld");
+  if (n_rows == 0) return kOk;
+  const int grid = ceil_div(n_rows * 32, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (heads == 1) ds_dst_kernel<1><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 2) ds_dst_kernel<2><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 4) ds_dst_kernel<4><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else { set_error("unsupported heads=%d", heads); return kErrUnsupported; }
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

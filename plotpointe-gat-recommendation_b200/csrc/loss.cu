@@ -1,0 +1,219 @@
+// Fused ranking loss over sampled (u, i, j) triples: positive/negative dot products, BPR or BCE,
+// mean -- replaces scripts/train_gat_custom.py:350-359 (three S x C gathers, two S x C products and
+// the reductions) and its autograd backward (an index_put with duplicate rows).
+//
+// forward : warp per triple; per-triple gradient coefficients are kept (2S floats); block partial
+//           sums are reduced in a fixed order -> deterministic loss.
+// backward: the 3S (node, triple) incidences are stably sorted by node once per triple set
+//           (radix sort from graph.cu); a warp per node then accumulates its incidences in that
+//           order -> dZ[N, C] without atomics, every row written exactly once.
+#include "common.cuh"
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+
+constexpr int kBpr = B200GAT_LOSS_BPR;
+constexpr int kBce = B200GAT_LOSS_BCE;
+
+__device__ __forceinline__ float softplusf(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
+__device__ __forceinline__ float sigmoidf_(float a) { return 1.f / (1.f + expf(-a)); }
+
+template <int LOSS>
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ z, int C, int64_t n_users, int64_t n_items,
+                                                       const int64_t* __restrict__ u, const int64_t* __restrict__ i,
+                                                       const int64_t* __restrict__ j, int64_t S,
+                                                       float* __restrict__ coef /*[2S]: d/dpos, d/dneg*/,
+                                                       double* __restrict__ partial, int32_t* __restrict__ n_bad) {
+  __shared__ float wsum[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t t = blockIdx.x * 8LL + w;
+  float term = 0.f;
+  if (t < S) {
+    int64_t uu = u[t], ii = i[t], jj = j[t];
+    const bool ok = uu >= 0 && uu < n_users && ii >= 0 && ii < n_items && jj >= 0 && jj < n_items;
+    if (!ok) { uu = 0; ii = 0; jj = 0; if (lane == 0) atomicAdd(n_bad, 1); }
+    const float* zu = z + uu * C;
+    const float* zi = z + (n_users + ii) * C;
+    const float* zj = z + (n_users + jj) * C;
+    float pos = 0.f, neg = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 a = ldg4(zu + c);
+      pos += dot4(a, ldg4(zi + c));
+      neg += dot4(a, ldg4(zj + c));
+    }
+    pos = warp_sum(pos);
+    neg = warp_sum(neg);
+    float gp, gn;
+    if (LOSS == kBpr) {  // -log(sigmoid(pos-neg) + 1e-8), train_gat_custom.py:355
+      const float sg = sigmoidf_(pos - neg);
+      term = -logf(sg + 1e-8f);
+      gp = -(sg * (1.f - sg)) / (sg + 1e-8f);
+      gn = -gp;
+    } else {  // BCE-with-logits on [pos -> 1, neg -> 0], train_gat_custom.py:357-359
+      term = softplusf(-pos) + softplusf(neg);
+      gp = -sigmoidf_(-pos);
+      gn = sigmoidf_(neg);
+    }
+    if (lane == 0) { coef[t] = gp; coef[S + t] = gn; }
+  }
+  if (lane == 0) wsum[w] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += (double)wsum[k];
+    partial[blockIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ partial, int n, double scale,
+                                                            const int32_t* __restrict__ n_bad, float* __restrict__ loss) {
+  __shared__ double sm[256];
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) a += partial[k];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  // an out-of-range triple index poisons the loss instead of silently reading another row
+  if (threadIdx.x == 0) loss[0] = *n_bad ? __int_as_float(0x7fc00000) : (float)(sm[0] * scale);
+}
+
+__global__ void incidence_keys_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ i,
+                                      const int64_t* __restrict__ j, int64_t S, int64_t n_users, int64_t n_items,
+                                      int32_t* __restrict__ keys) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < S; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t uu = u[t], ii = i[t], jj = j[t];
+    if (uu < 0 || uu >= n_users) uu = 0;
+    if (ii < 0 || ii >= n_items) ii = 0;
+    if (jj < 0 || jj >= n_items) jj = 0;
+    keys[t] = (int32_t)uu;
+    keys[S + t] = (int32_t)(n_users + ii);
+    keys[2 * S + t] = (int32_t)(n_users + jj);
+  }
+}
+
+__global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__ z, int C, int64_t n_nodes, int64_t n_users,
+                                                       const int64_t* __restrict__ u, const int64_t* __restrict__ i,
+                                                       const int64_t* __restrict__ j, int64_t S,
+                                                       const float* __restrict__ coef, const int32_t* __restrict__ ptr,
+                                                       const int32_t* __restrict__ ids, const float* __restrict__ grad_out,
+                                                       float scale, float* __restrict__ dz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_nodes) return;
+  const int beg = ptr[n], end = ptr[n + 1];
+  const float g = grad_out[0] * scale;
+  const int64_t n_items = n_nodes - n_users;
+  auto safe = [](int64_t v, int64_t lim) { return (v < 0 || v >= lim) ? (int64_t)0 : v; };
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = beg; q < end; ++q) {
+      const int id = ids[q];
+      const int role = id / (int)S;
+      const int64_t t = id - (int64_t)role * S;
+      if (role == 0) {
+        acc = fma4(coef[t], ldg4(z + (n_users + safe(i[t], n_items)) * C + c), acc);
+        acc = fma4(coef[S + t], ldg4(z + (n_users + safe(j[t], n_items)) * C + c), acc);
+      } else {
+        acc = fma4(coef[(role - 1) * S + t], ldg4(z + safe(u[t], n_users) * C + c), acc);
+      }
+    }
+    acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
+    *reinterpret_cast<float4*>(dz + n * C + c) = acc;
+  }
+}
+
+static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" int b200gat_loss_workspace_bytes(int64_t n_nodes, int64_t n_triples, size_t* bytes) {
+  B200GAT_CHECK_ARG(bytes && n_triples >= 0 && n_nodes >= 0, "bad args");
+  B200GAT_CHECK_ARG(3 * n_triples < 2147483647LL && n_nodes < 2147483647LL, "sizes must be < 2^31");
+  const int64_t S = n_triples;
+  *bytes = al(2 * S * 4 + 4) /*coef*/ + al((size_t)(S / 8 + 2) * 8) /*partials*/ + 3 * al(3 * S * 4 + 4) /*keys, sorted, ids*/ +
+           al((n_nodes + 1) * 4) /*ptr*/ + al(sort_workspace_bytes(3 * S)) + 256 /*n_bad*/;
+  return kOk;
+}
+
+namespace {
+struct LossWs {
+  float* coef; double* partial; int32_t *keys, *sorted, *ids, *ptr; void* sort_ws; int32_t* n_bad;
+};
+LossWs carve(void* ws, int64_t n_nodes, int64_t S) {
+  char* p = (char*)ws;
+  auto take = [&](size_t b) { char* q = p; p += al(b); return (void*)q; };
+  LossWs w;
+  w.coef = (float*)take(2 * S * 4 + 4);
+  w.partial = (double*)take((size_t)(S / 8 + 2) * 8);
+  w.keys = (int32_t*)take(3 * S * 4 + 4);
+  w.sorted = (int32_t*)take(3 * S * 4 + 4);
+  w.ids = (int32_t*)take(3 * S * 4 + 4);
+  w.ptr = (int32_t*)take((n_nodes + 1) * 4);
+  w.sort_ws = take(sort_workspace_bytes(3 * S));
+  w.n_bad = (int32_t*)take(4);
+  return w;
+}
+}  // namespace
+
+// loss[0] = mean over triples.  Leaves coef + the node-sorted incidence lists in `workspace` for the backward.
+extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
+                                         const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
+                                         int need_backward, float* loss, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  B200GAT_CHECK_ARG(z && loss && workspace, "null pointer");
+  B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
+  B200GAT_CHECK_ARG(channels % 4 == 0, "channels must be a multiple of 4");
+  B200GAT_CHECK_ARG(n_triples > 0 && u && i && j, "empty triple set");
+  size_t need;
+  int rc = b200gat_loss_workspace_bytes(n_users + n_items, n_triples, &need);
+  if (rc) return rc;
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t S = n_triples, N = n_users + n_items;
+  LossWs w = carve(workspace, N, S);
+  B200GAT_CUDA(cudaMemsetAsync(w.n_bad, 0, 4, st));
+  const int blocks = ceil_div(S, 8);
+  if (loss_kind == kBpr) {
+    loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 1.0 / (double)S, w.n_bad, loss);
+  } else {
+    loss_fwd_kernel<kBce><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 0.5 / (double)S, w.n_bad, loss);
+  }
+  B200GAT_LAUNCH_CHECK();
+  if (need_backward) {
+    incidence_keys_kernel<<<min(ceil_div(S, 256), kNumSMs * 8), 256, 0, st>>>(u, i, j, S, n_users, n_items, w.keys);
+    B200GAT_LAUNCH_CHECK();
+    rc = sort_pairs_stable(w.keys, 3 * S, N, w.sorted, w.ids, w.sort_ws, st);
+    if (rc) return rc;
+    rc = node_ptr_from_sorted(w.sorted, 3 * S, N, w.ptr, st);
+    if (rc) return rc;
+  }
+  return kOk;
+}
+
+extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
+                                         const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
+                                         const float* grad_out, float* dz, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  B200GAT_CHECK_ARG(z && grad_out && dz && workspace && u && i && j, "null pointer");
+  B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
+  size_t need;
+  int rc = b200gat_loss_workspace_bytes(n_users + n_items, n_triples, &need);
+  if (rc) return rc;
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t S = n_triples, N = n_users + n_items;
+  LossWs w = carve(workspace, N, S);
+  const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
+  loss_bwd_kernel<<<ceil_div(N * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids, grad_out,
+                                                        scale, dz);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

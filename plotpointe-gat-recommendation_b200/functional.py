@@ -1,0 +1,149 @@
+"""torch.autograd ops over the C ABI: one GAT layer (both dialects) and the ranking loss."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .graph import GraphStructure
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+class GATLayerFunction(torch.autograd.Function):
+    """y = GAT(x; W, a_src, a_dst[, bias]) over ``graph``.
+
+    policy CUSTOM = SimpleGATLayer.forward (scripts/train_gat_custom.py:75-93), policy PYG =
+    GATConv(heads=H, concat=False, add_self_loops=False) (scripts/train_gat_pyg.py:77,87).
+    Saved for backward: x, h, the per-node scalars (s, rowstat) and the output -- no E-sized float tensor.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, a_src, a_dst, bias, graph: GraphStructure, heads: int, channels: int, policy: int,
+                negative_slope: float, p_drop: float, seed: int):
+        if not x.is_cuda:
+            raise RuntimeError("b200gat GAT layer: x must be a CUDA tensor (there is no CPU fallback)")
+        x = _lib._f32(x, "x").contiguous()
+        weight = _lib._f32(weight, "weight").contiguous()
+        a_s = _lib._f32(a_src, "a_src").contiguous().view(heads, channels)
+        a_d = _lib._f32(a_dst, "a_dst").contiguous().view(heads, channels)
+        n, f_in = x.shape
+        if n != graph.n_nodes:
+            raise RuntimeError(f"x has {n} rows but the graph has {graph.n_nodes} nodes")
+        if weight.shape != (heads * channels, f_in):
+            raise RuntimeError(f"weight must be [{heads * channels}, {f_in}], got {tuple(weight.shape)}")
+        need_grad = any(ctx.needs_input_grad[:5])
+        with torch.cuda.device(x.device):
+            st = _lib.stream()
+            h = _empty((n, heads * channels), x)
+            s = _empty((n, 2 * heads), x)
+            _lib.call("b200gat_project_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), n, f_in, heads,
+                      channels, _lib.ptr(h), _lib.ptr(s), st)
+            out = _empty((n, channels), x)
+            rowstat = _empty((n, heads, 2), x) if need_grad else None
+            out_heads = _empty((n, heads, channels), x) if (need_grad and heads > 1) else None
+            b = None if bias is None else _lib._f32(bias, "bias").contiguous()
+            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                      _lib.ptr(graph.perm), n, 0, heads, channels, policy, negative_slope, _lib.ptr(b), _lib.ptr(out),
+                      _lib.ptr(out_heads), _lib.ptr(rowstat), p_drop, seed, st)
+        if need_grad:
+            ctx.save_for_backward(x, weight, a_s, a_d, b, h, s, rowstat, out if heads == 1 else out_heads)
+            ctx.graph = graph
+            ctx.cfg = (heads, channels, policy, negative_slope, p_drop, seed)
+            ctx.att_shape = (a_src.shape, a_dst.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, a_s, a_d, b, h, s, rowstat, out_h = ctx.saved_tensors
+        heads, channels, policy, negative_slope, p_drop, seed = ctx.cfg
+        g = ctx.graph
+        n, f_in = x.shape
+        dout = dout.contiguous()
+        with torch.cuda.device(x.device):
+            st = _lib.stream()
+            nodestat = _empty((n, heads, 4), x)
+            _lib.call("b200gat_node_prep_f32", _lib.ptr(dout), _lib.ptr(out_h), _lib.ptr(b if heads == 1 else None),
+                      _lib.ptr(s), _lib.ptr(rowstat), n, 0, heads, channels, _lib.ptr(nodestat), st)
+            dh = _empty((n, heads * channels), x)
+            de = _empty((max(g.n_edges, 1), heads), x)
+            ds = _empty((n, 2 * heads), x)
+            _lib.call("b200gat_edge_bwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(dout), _lib.ptr(nodestat),
+                      _lib.ptr(g.colptr), _lib.ptr(g.row), _lib.ptr(g.perm_csc), n, 0, heads, channels, policy,
+                      negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
+            _lib.call("b200gat_ds_dst_f32", _lib.ptr(de), _lib.ptr(g.rowptr), _lib.ptr(g.csr2csc), n, heads,
+                      _lib.ptr(ds, heads), 2 * heads, st)
+            del de
+            ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            dx = _empty((n, f_in), x) if ctx.needs_input_grad[0] else None
+            dw = torch.empty_like(weight)
+            da_s = torch.empty_like(a_s)
+            da_d = torch.empty_like(a_d)
+            _lib.call("b200gat_project_bwd_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(dh),
+                      _lib.ptr(ds), n, f_in, heads, channels, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(da_s), _lib.ptr(da_d),
+                      _lib.ptr(ws), ws_bytes, st)
+            dbias = None
+            if b is not None and ctx.needs_input_grad[4]:
+                dbias = torch.empty_like(b)
+                _lib.call("b200gat_colsum_f32", _lib.ptr(dout), n, channels, _lib.ptr(dbias), _lib.ptr(ws), ws_bytes, st)
+        sa, sd = ctx.att_shape
+        return dx, dw, da_s.view(sa), da_d.view(sd), dbias, None, None, None, None, None, None, None
+
+
+def gat_layer(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, negative_slope=0.2, p_drop=0.0, seed=0):
+    return GATLayerFunction.apply(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, float(negative_slope),
+                                  float(p_drop), int(seed))
+
+
+class RankLossFunction(torch.autograd.Function):
+    """Fused pos/neg dot products + BPR / BCE mean (scripts/train_gat_custom.py:350-359)."""
+
+    @staticmethod
+    def forward(ctx, z, n_users: int, u, i, j, kind: int):
+        if not z.is_cuda:
+            raise RuntimeError("b200gat ranking loss: z must be a CUDA tensor (there is no CPU fallback)")
+        z = _lib._f32(z, "z").contiguous()
+        n, c = z.shape
+        n_items = n - n_users
+        idx = []
+        for name, t in (("u", u), ("i", i), ("j", j)):
+            if t.dtype != torch.int64 or t.dim() != 1 or t.shape != u.shape:
+                raise RuntimeError(f"{name} must be an int64 vector of the common length")
+            idx.append(t.to(z.device).contiguous())
+        s = int(u.shape[0])
+        need = ctx.needs_input_grad[0]
+        ws_bytes = _lib.loss_workspace_bytes(n, s)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        loss = _empty((1,), z)
+        with torch.cuda.device(z.device):
+            _lib.call("b200gat_rank_loss_fwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(idx[0]), _lib.ptr(idx[1]),
+                      _lib.ptr(idx[2]), s, kind, int(need), _lib.ptr(loss), _lib.ptr(ws), ws_bytes, _lib.stream())
+        if need:
+            ctx.save_for_backward(z, idx[0], idx[1], idx[2], ws)
+            ctx.meta = (n_users, n_items, c, s, kind, ws_bytes)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z, u, i, j, ws = ctx.saved_tensors
+        n_users, n_items, c, s, kind, ws_bytes = ctx.meta
+        go = grad_out.to(torch.float32).reshape(1).contiguous()
+        dz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _lib.call("b200gat_rank_loss_bwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), s,
+                      kind, _lib.ptr(go), _lib.ptr(dz), _lib.ptr(ws), ws_bytes, _lib.stream())
+        return dz, None, None, None, None, None
+
+
+def bpr_loss(z: torch.Tensor, n_users: int, u: torch.Tensor, i: torch.Tensor, j: torch.Tensor) -> torch.Tensor:
+    """``-log(sigmoid(pos - neg) + 1e-8).mean()`` with pos/neg as at scripts/train_gat_custom.py:350-355."""
+    return RankLossFunction.apply(z, int(n_users), u, i, j, _lib.LOSS_BPR)
+
+
+def bce_loss(z: torch.Tensor, n_users: int, u: torch.Tensor, i: torch.Tensor, j: torch.Tensor) -> torch.Tensor:
+    """BCE-with-logits over cat[pos, neg] vs cat[1, 0] (scripts/train_gat_custom.py:356-359)."""
+    return RankLossFunction.apply(z, int(n_users), u, i, j, _lib.LOSS_BCE)

@@ -1,0 +1,57 @@
+"""Synthetic graphs of the reference's shape: User-Item interactions in the reference's interleaved
+edge order (scripts/train_gat_custom.py:166-175) followed by a directed Item-Item k-NN block
+(graphs/build_ii_knn.py:103-111: row = item, col = neighbour)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+
+CONFIGS = {
+    # name: (n_users, n_items, n_interactions, k)
+    "cfg1": (10_000, 20_000, 200_000, 20),
+    "amazon": (192_403, 498_196, 1_689_116, 20),
+    "tiny": (300, 500, 4_000, 8),
+}
+
+
+def make_graph(n_users: int, n_items: int, n_inter: int, k: int = 20, seed: int = 42, item_zipf: float = 0.9,
+               item_shift: float = 40.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (edge_index int64 [2, 2*n_inter + k*n_items] on the host, item_feats fp32 [n_items, 128]).
+
+    Users get one interaction each plus a geometric-ish remainder (mean n_inter/n_users); items are drawn from a
+    shifted power law so item in-degree is heavy-tailed (std >> mean, as the reference's graph stats report);
+    duplicate (u, i) pairs are kept.  Each item gets k distinct random neighbours (exact cosine kNN is O(n_items^2)
+    and only used for small graphs, see oracle.build_ii_knn)."""
+    rng = np.random.default_rng(seed)
+    extra = n_inter - n_users
+    assert extra >= 0
+    w = rng.exponential(1.0, size=n_users)
+    deg = 1 + rng.multinomial(extra, w / w.sum())
+    users = np.repeat(np.arange(n_users, dtype=np.int64), deg)
+    ranks = np.arange(1, n_items + 1, dtype=np.float64)
+    pop = 1.0 / (ranks + item_shift) ** item_zipf
+    pop /= pop.sum()
+    item_of_rank = rng.permutation(n_items)
+    items = item_of_rank[rng.choice(n_items, size=n_inter, p=pop)].astype(np.int64) + n_users
+    ui = np.empty((2, 2 * n_inter), dtype=np.int64)
+    ui[0, 0::2], ui[1, 0::2] = users, items
+    ui[0, 1::2], ui[1, 1::2] = items, users
+    # k distinct neighbours != self: offsets in [1, n_items) without replacement per row (vectorised via argpartition
+    # of random keys would be O(n_items^2); draw k offsets and de-duplicate by sorting + bumping instead)
+    off = np.sort(rng.integers(1, n_items - k + 1, size=(n_items, k)), axis=1) + np.arange(k)[None, :]
+    rows = np.repeat(np.arange(n_items, dtype=np.int64), k)
+    cols = (rows + off.reshape(-1)) % n_items
+    ii = np.stack([rows + n_users, cols + n_users])
+    edge_index = torch.from_numpy(np.concatenate([ui, ii], axis=1))
+    feats = rng.standard_normal((n_items, 128)).astype(np.float32)
+    feats /= np.linalg.norm(feats, axis=1, keepdims=True)
+    return edge_index, torch.from_numpy(feats)
+
+
+def make_triples(n_users: int, n_items: int, n_triples: int, seed: int = 42):
+    rng = np.random.default_rng(seed + 1)
+    return (torch.from_numpy(rng.integers(0, n_users, size=n_triples)),
+            torch.from_numpy(rng.integers(0, n_items, size=n_triples)),
+            torch.from_numpy(rng.integers(0, n_items, size=n_triples)))

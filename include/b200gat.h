@@ -41,6 +41,8 @@ extern "C" {
 
 const char* b200gat_last_error(void);
 int b200gat_abi_version(void);
+/* number of kernels launched through this library by the calling process (monotonic) */
+int64_t b200gat_launch_count(void);
 
 /* ---- (1) COO -> CSR/CSC -------------------------------------------------------------------------
  * Replaces the edge ordering that the reference's per-edge scatter ops imply

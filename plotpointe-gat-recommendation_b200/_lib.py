@@ -30,6 +30,7 @@ _P = c_void_p
 _SIGS = {
     "b200gat_last_error": (ctypes.c_char_p, []),
     "b200gat_abi_version": (c_int, []),
+    "b200gat_launch_count": (c_int64, []),
     "b200gat_graph_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_build_graph": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200gat_project_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
@@ -55,7 +56,9 @@ for _name, (_res, _args) in _SIGS.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-launch_count = 0   # number of C-ABI calls that launched device work (bench.py reads this)
+# kernels launched by each entry point (used for bench.py's gpu_launches claim; graph/loss sort passes are
+# counted by the library itself, see b200gat_launch_count)
+timing = None      # bench.py sets this to a dict: entry point -> list of (start_event, end_event)
 
 
 def last_error() -> str:
@@ -89,9 +92,19 @@ def _f32(t, name):
 
 
 def call(name: str, *args) -> None:
-    global launch_count
-    launch_count += 1
+    if timing is None:
+        _check(getattr(_lib, name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     _check(getattr(_lib, name)(*args), name)
+    b.record()
+    timing.setdefault(name, []).append((a, b))
+
+
+def launch_count() -> int:
+    """Total number of kernels this process has launched through the library."""
+    return int(_lib.b200gat_launch_count())
 
 
 def graph_workspace_bytes(n_nodes: int, n_edges: int) -> int:

@@ -12,6 +12,7 @@ namespace b200gat {
 enum : int { kOk = 0, kErrArg = -1, kErrCuda = -2, kErrUnsupported = -3, kErrWorkspace = -4 };
 
 void set_error(const char* fmt, ...);
+void count_launch();  // bumps the process-wide kernel launch counter (b200gat_launch_count)
 
 #define B200GAT_CHECK_ARG(cond, ...)                    \
   do {                                                  \

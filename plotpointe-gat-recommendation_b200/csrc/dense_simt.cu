@@ -87,10 +87,10 @@ static int launch_sgemm(const float* A, int64_t sam, int64_t sak, const float* B
                         const float* bias, cudaStream_t st) {
   dim3 grid(ceil_div(N, kBN), ceil_div(M, kBM), n_slabs);
   const bool ak = sak == 1, bn = sbn == 1;
-  if (ak && bn) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
-  else if (ak && !bn) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
-  else if (!ak && bn) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
-  else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  if (ak && bn) count_launch(), sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else if (ak && !bn) count_launch(), sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else if (!ak && bn) count_launch(), sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
+  else count_launch(), sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -193,7 +193,7 @@ extern "C" int b200gat_project_f32(const float* x, const float* W, const float* 
   int rc = launch_sgemm(x, in_features, 1, W, 1, in_features, h, HC, (int)n_rows, HC, in_features, 1, in_features, 0,
                         nullptr, st);
   if (rc) return rc;
-  logits_kernel<<<ceil_div(n_rows * 32, 128), 128, 0, st>>>(h, a_src, a_dst, n_rows, heads, channels, s);
+  count_launch(), logits_kernel<<<ceil_div(n_rows * 32, 128), 128, 0, st>>>(h, a_src, a_dst, n_rows, heads, channels, s);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -218,7 +218,7 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
     B200GAT_CUDA(cudaMemsetAsync(da_dst, 0, sizeof(float) * HC, st));
     return kOk;
   }
-  add_logit_grad_kernel<<<kNumSMs * 8, 256, 0, st>>>(dh, ds, a_src, a_dst, n_rows, heads, channels);
+  count_launch(), add_logit_grad_kernel<<<kNumSMs * 8, 256, 0, st>>>(dh, ds, a_src, a_dst, n_rows, heads, channels);
   B200GAT_LAUNCH_CHECK();
   int rc;
   if (dx) {  // dx[n,f] = sum_m dh[n,m] W[m,f]
@@ -230,13 +230,13 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   // dW[m,f] = sum_n dh[n,m] x[n,f]
   rc = launch_sgemm(dh, 1, HC, x, F, 1, part, F, HC, F, n_rows, n_slabs, k_slab, (int64_t)HC * F, nullptr, st);
   if (rc) return rc;
-  reduce_slabs_kernel<<<ceil_div((int64_t)HC * F, 256), 256, 0, st>>>(part, n_slabs, (int64_t)HC * F, (int64_t)HC * F, dW);
+  count_launch(), reduce_slabs_kernel<<<ceil_div((int64_t)HC * F, 256), 256, 0, st>>>(part, n_slabs, (int64_t)HC * F, (int64_t)HC * F, dW);
   // v[q,f] = sum_n ds[n,q] x[n,f]
   float* part_v = part + (size_t)kSlabs * HC * F;
   rc = launch_sgemm(ds, 1, H2, x, F, 1, part_v, F, H2, F, n_rows, n_slabs, k_slab, (int64_t)H2 * F, nullptr, st);
   if (rc) return rc;
-  reduce_slabs_kernel<<<ceil_div((int64_t)H2 * F, 256), 256, 0, st>>>(part_v, n_slabs, (int64_t)H2 * F, (int64_t)H2 * F, v);
-  att_grad_kernel<<<ceil_div((int64_t)HC * 32, 128), 128, 0, st>>>(W, v, heads, channels, F, da_src, da_dst);
+  count_launch(), reduce_slabs_kernel<<<ceil_div((int64_t)H2 * F, 256), 256, 0, st>>>(part_v, n_slabs, (int64_t)H2 * F, (int64_t)H2 * F, v);
+  count_launch(), att_grad_kernel<<<ceil_div((int64_t)HC * 32, 128), 128, 0, st>>>(W, v, heads, channels, F, da_src, da_dst);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -250,8 +250,8 @@ extern "C" int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, 
   if (n_rows == 0) { B200GAT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, st)); return kOk; }
   const int64_t rps = (n_rows + kSlabs - 1) / kSlabs;
   const int n_slabs = (int)((n_rows + rps - 1) / rps);
-  colsum_partial_kernel<<<n_slabs, 256, 0, st>>>(a, n_rows, channels, rps, (float*)workspace);
-  reduce_slabs_kernel<<<ceil_div(channels, 256), 256, 0, st>>>((const float*)workspace, n_slabs, channels, channels, out);
+  count_launch(), colsum_partial_kernel<<<n_slabs, 256, 0, st>>>(a, n_rows, channels, rps, (float*)workspace);
+  count_launch(), reduce_slabs_kernel<<<ceil_div(channels, 256), 256, 0, st>>>((const float*)workspace, n_slabs, channels, channels, out);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

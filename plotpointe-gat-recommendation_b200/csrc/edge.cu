@@ -384,7 +384,7 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = p_drop > 0.f;
 #define LAUNCH_FWD(P, D)                                                                                          \
-  edge_fwd_kernel<P, kH, kCV, D><<<grid, threads, 0, st>>>(h, s, rowptr, col, perm, (int)n_rows, (int)row_offset, \
+  count_launch(), edge_fwd_kernel<P, kH, kCV, D><<<grid, threads, 0, st>>>(h, s, rowptr, col, perm, (int)n_rows, (int)row_offset, \
                                                            negative_slope, bias, out, out_heads, (float2*)rowstat,  \
                                                            p_drop, seed)
   B200GAT_DISPATCH_HC(heads, cv, {
@@ -407,7 +407,7 @@ extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, 
   const int grid = ceil_div(n_rows * 32, 128);
   cudaStream_t st = (cudaStream_t)stream;
   B200GAT_DISPATCH_HC(heads, cv, {
-    node_prep_kernel<kH, kCV><<<grid, 128, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
+    count_launch(), node_prep_kernel<kH, kCV><<<grid, 128, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
                                                    (int)row_offset, (float4*)nodestat);
   })
   B200GAT_LAUNCH_CHECK();
@@ -431,7 +431,7 @@ extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = p_drop > 0.f;
 #define LAUNCH_BWD(P, D)                                                                                             \
-  edge_bwd_kernel<P, kH, kCV, D><<<grid, 128, 0, st>>>(h, s, dout, (const float4*)nodestat, colptr, row, perm_csc,  \
+  count_launch(), edge_bwd_kernel<P, kH, kCV, D><<<grid, 128, 0, st>>>(h, s, dout, (const float4*)nodestat, colptr, row, perm_csc,  \
                                                        (int)n_rows, (int)row_offset, negative_slope, dh, de, ds_src, \
                                                        ld_ds, p_drop, seed)
   B200GAT_DISPATCH_HC(heads, cv, {
@@ -449,9 +449,9 @@ extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const 
   if (n_rows == 0) return kOk;
   const int grid = ceil_div(n_rows * 32, 128);
   cudaStream_t st = (cudaStream_t)stream;
-  if (heads == 1) ds_dst_kernel<1><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
-  else if (heads == 2) ds_dst_kernel<2><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
-  else if (heads == 4) ds_dst_kernel<4><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  if (heads == 1) count_launch(), ds_dst_kernel<1><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 2) count_launch(), ds_dst_kernel<2><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 4) count_launch(), ds_dst_kernel<4><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
   else { set_error("unsupported heads=%d", heads); return kErrUnsupported; }
   B200GAT_LAUNCH_CHECK();
   return kOk;

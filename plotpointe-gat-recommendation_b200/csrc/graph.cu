@@ -121,9 +121,9 @@ static size_t scan_ws_ints(int64_t n) { return (size_t)ceil_div(n, kScanTile) + 
 static int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* ws, cudaStream_t st) {
   if (n == 0) return kOk;
   int tiles = ceil_div(n, kScanTile);
-  scan_tile_sums_kernel<<<tiles, kScanThreads, 0, st>>>(in, n, ws);
-  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(ws, tiles);
-  scan_apply_kernel<<<tiles, kScanThreads, 0, st>>>(in, n, ws, out);
+  count_launch(), scan_tile_sums_kernel<<<tiles, kScanThreads, 0, st>>>(in, n, ws);
+  count_launch(), scan_sums_kernel<<<1, kScanThreads, 0, st>>>(ws, tiles);
+  count_launch(), scan_apply_kernel<<<tiles, kScanThreads, 0, st>>>(in, n, ws, out);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -237,10 +237,10 @@ static int radix_sort_by_key(const int32_t* keys, int64_t n, int64_t n_nodes, in
     bool last = p == passes - 1;
     int32_t* ko = last ? keys_out : ((p & 1) ? ws.k1 : ws.k0);
     int32_t* vo = last ? vals_out : ((p & 1) ? ws.v1 : ws.v0);
-    radix_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, n, 8 * p, n_tiles, ws.table);
+    count_launch(), radix_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, n, 8 * p, n_tiles, ws.table);
     int rc = exclusive_scan_i32(ws.table, ws.table, (int64_t)kRadix * n_tiles, ws.scan, st);
     if (rc) return rc;
-    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, vin, n, 8 * p, n_tiles, ws.table, ko, vo);
+    count_launch(), radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, vin, n, 8 * p, n_tiles, ws.table, ko, vo);
     B200GAT_LAUNCH_CHECK();
     kin = ko;
     vin = vo;
@@ -295,7 +295,7 @@ int sort_pairs_stable(const int32_t* keys, int64_t n, int64_t key_range, int32_t
 }
 
 int node_ptr_from_sorted(const int32_t* sorted, int64_t n, int64_t n_nodes, int32_t* ptr, cudaStream_t st) {
-  lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, 256), 256, 0, st>>>(sorted, n, n_nodes, ptr);
+  count_launch(), lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, 256), 256, 0, st>>>(sorted, n, n_nodes, ptr);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -347,24 +347,24 @@ extern "C" int b200gat_build_graph(const int64_t* edge_index, int64_t n_edges, i
   B200GAT_CUDA(cudaMemsetAsync(n_bad_out, 0, sizeof(int32_t), st));
   const int T = 256;
   int grid = n_edges ? min(ceil_div(n_edges, T), kNumSMs * 8) : 1;
-  if (n_edges) narrow_validate_kernel<<<grid, T, 0, st>>>(edge_index, n_edges, n_nodes, src32, dst32, n_bad_out);
+  if (n_edges) count_launch(), narrow_validate_kernel<<<grid, T, 0, st>>>(edge_index, n_edges, n_nodes, src32, dst32, n_bad_out);
   B200GAT_LAUNCH_CHECK();
 
   // CSR: stable by destination
   rc = radix_sort_by_key(dst32, n_edges, n_nodes, sorted, perm, ws, st);
   if (rc) return rc;
-  lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, T), T, 0, st>>>(sorted, n_edges, n_nodes, rowptr);
-  if (n_edges) gather_i32_kernel<<<grid, T, 0, st>>>(src32, perm, n_edges, col);
+  count_launch(), lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, T), T, 0, st>>>(sorted, n_edges, n_nodes, rowptr);
+  if (n_edges) count_launch(), gather_i32_kernel<<<grid, T, 0, st>>>(src32, perm, n_edges, col);
   B200GAT_LAUNCH_CHECK();
 
   // CSC: stable by source
   rc = radix_sort_by_key(src32, n_edges, n_nodes, sorted, perm_csc, ws, st);
   if (rc) return rc;
-  lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, T), T, 0, st>>>(sorted, n_edges, n_nodes, colptr);
+  count_launch(), lower_bound_ptr_kernel<<<ceil_div(n_nodes + 1, T), T, 0, st>>>(sorted, n_edges, n_nodes, colptr);
   if (n_edges) {
-    gather_i32_kernel<<<grid, T, 0, st>>>(dst32, perm_csc, n_edges, row);
-    invert_perm_kernel<<<grid, T, 0, st>>>(perm_csc, n_edges, inv);      // inv[edge id] = CSC position
-    gather_i32_kernel<<<grid, T, 0, st>>>(inv, perm, n_edges, csr2csc);   // CSR position -> CSC position
+    count_launch(), gather_i32_kernel<<<grid, T, 0, st>>>(dst32, perm_csc, n_edges, row);
+    count_launch(), invert_perm_kernel<<<grid, T, 0, st>>>(perm_csc, n_edges, inv);      // inv[edge id] = CSC position
+    count_launch(), gather_i32_kernel<<<grid, T, 0, st>>>(inv, perm, n_edges, csr2csc);   // CSR position -> CSC position
   }
   B200GAT_LAUNCH_CHECK();
   return kOk;

@@ -180,15 +180,15 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
   B200GAT_CUDA(cudaMemsetAsync(w.n_bad, 0, 4, st));
   const int blocks = ceil_div(S, 8);
   if (loss_kind == kBpr) {
-    loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
-    loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 1.0 / (double)S, w.n_bad, loss);
+    count_launch(), loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    count_launch(), loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 1.0 / (double)S, w.n_bad, loss);
   } else {
-    loss_fwd_kernel<kBce><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
-    loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 0.5 / (double)S, w.n_bad, loss);
+    count_launch(), loss_fwd_kernel<kBce><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    count_launch(), loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 0.5 / (double)S, w.n_bad, loss);
   }
   B200GAT_LAUNCH_CHECK();
   if (need_backward) {
-    incidence_keys_kernel<<<min(ceil_div(S, 256), kNumSMs * 8), 256, 0, st>>>(u, i, j, S, n_users, n_items, w.keys);
+    count_launch(), incidence_keys_kernel<<<min(ceil_div(S, 256), kNumSMs * 8), 256, 0, st>>>(u, i, j, S, n_users, n_items, w.keys);
     B200GAT_LAUNCH_CHECK();
     rc = sort_pairs_stable(w.keys, 3 * S, N, w.sorted, w.ids, w.sort_ws, st);
     if (rc) return rc;
@@ -212,7 +212,7 @@ extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_
   const int64_t S = n_triples, N = n_users + n_items;
   LossWs w = carve(workspace, N, S);
   const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
-  loss_bwd_kernel<<<ceil_div(N * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids, grad_out,
+  count_launch(), loss_bwd_kernel<<<ceil_div(N * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids, grad_out,
                                                         scale, dz);
   B200GAT_LAUNCH_CHECK();
   return kOk;

@@ -266,10 +266,14 @@ def test_attention_dropout_statistics_and_gradient(dev):
     layer.eval()
     y_eval = layer(x, ei)
     layer.train()
-    ys = torch.stack([layer(x, ei) for _ in range(64)])
+    with torch.no_grad():
+        ys = torch.stack([layer(x, ei) for _ in range(256)])
     assert not torch.equal(ys[0], ys[1])
-    rel = (ys.mean(0) - y_eval).norm() / y_eval.norm()
-    assert rel < 0.05, rel                      # E[dropout(alpha)] = alpha
+    # E[dropout(alpha)] = alpha.  With independent h rows the per-sample relative noise is sqrt(p/(1-p)) = 0.577,
+    # so the mean of 256 samples sits near 0.577/16 = 0.036: well below 0.06 if unbiased, well above 0.01 if the
+    # mask really varies between calls.
+    rel = ((ys.mean(0) - y_eval).norm() / y_eval.norm()).item()
+    assert 0.01 < rel < 0.06, rel
     # finite-difference check of the backward with a frozen seed
     from b200gat import _lib
     from b200gat.functional import gat_layer

@@ -128,8 +128,10 @@ int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* cs
  *   z [n_users+n_items, channels]; u, i, j int64 [n_triples] (i, j are item ids, not node ids)
  *   loss : device float[1]; an out-of-range triple makes it NaN.
  *   The forward leaves per-triple coefficients and node-sorted incidence lists in `workspace`; pass the
- *   same workspace to the backward.  grad_out : device float[1].  dz [n_users+n_items, channels],
- *   every row written (rows without triples = 0); no atomics, bitwise reproducible.
+ *   same workspace to the backward.  grad_out : device float[1].  The backward writes the gradient
+ *   rows of nodes [node_begin, node_begin+node_count) into dz [node_count, channels] (a row shard;
+ *   0 / n_users+n_items = everything); every row written (rows without triples = 0); no atomics,
+ *   bitwise reproducible.
  */
 int b200gat_loss_workspace_bytes(int64_t n_nodes, int64_t n_triples, size_t* bytes /*host*/);
 int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
@@ -137,7 +139,8 @@ int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, 
                               float* loss, void* workspace, size_t workspace_bytes, void* stream);
 int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
                               const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
-                              const float* grad_out, float* dz, void* workspace, size_t workspace_bytes, void* stream);
+                              const float* grad_out, int64_t node_begin, int64_t node_count, float* dz,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ j, int64_t S,
                                                        const float* __restrict__ coef, const int32_t* __restrict__ ptr,
                                                        const int32_t* __restrict__ ids, const float* __restrict__ grad_out,
-                                                       float scale, float* __restrict__ dz) {
+                                                       float scale, int64_t node_begin, int64_t node_count,
+                                                       float* __restrict__ dz /*[node_count, C]*/) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (n >= n_nodes) return;
+  const int64_t local = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (local >= node_count) return;
+  const int64_t n = node_begin + local;
   const int beg = ptr[n], end = ptr[n + 1];
   const float g = grad_out[0] * scale;
   const int64_t n_items = n_nodes - n_users;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
       }
     }
     acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
-    *reinterpret_cast<float4*>(dz + n * C + c) = acc;
+    *reinterpret_cast<float4*>(dz + local * C + c) = acc;
   }
 }
 
@@ -200,8 +202,8 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
 
 extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
                                          const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
-                                         const float* grad_out, float* dz, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         const float* grad_out, int64_t node_begin, int64_t node_count, float* dz,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
   B200GAT_CHECK_ARG(z && grad_out && dz && workspace && u && i && j, "null pointer");
   B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
   size_t need;
@@ -210,10 +212,12 @@ extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t S = n_triples, N = n_users + n_items;
+  B200GAT_CHECK_ARG(node_begin >= 0 && node_count >= 0 && node_begin + node_count <= N, "bad node range");
+  if (node_count == 0) return kOk;
   LossWs w = carve(workspace, N, S);
   const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
-  count_launch(), loss_bwd_kernel<<<ceil_div(N * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids, grad_out,
-                                                        scale, dz);
+  count_launch(), loss_bwd_kernel<<<ceil_div(node_count * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids,
+                                                                 grad_out, scale, node_begin, node_count, dz);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

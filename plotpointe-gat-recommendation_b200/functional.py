@@ -135,7 +135,7 @@ class RankLossFunction(torch.autograd.Function):
         dz = torch.empty_like(z)
         with torch.cuda.device(z.device):
             _lib.call("b200gat_rank_loss_bwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), s,
-                      kind, _lib.ptr(go), _lib.ptr(dz), _lib.ptr(ws), ws_bytes, _lib.stream())
+                      kind, _lib.ptr(go), 0, n_users + n_items, _lib.ptr(dz), _lib.ptr(ws), ws_bytes, _lib.stream())
         return dz, None, None, None, None, None
 
 

@@ -1,0 +1,337 @@
+"""Row-sharded full-graph GAT training over P GPUs of one node (one process per GPU, torch.distributed/NCCL).
+
+The node space [0, N) is cut into P contiguous blocks balanced by in+out edge count.  Rank p owns the rows of its
+block: their input features, their destination rows in the forward (CSR slice) and their source rows in the
+backward (CSC slice).  Per layer the exchange steps are:
+
+  forward : all-gather of the projected rows [h | s]   (N x (H*C + 2H) floats)      -> fused edge forward on local rows
+  backward: all-gather of dout rows and of the per-destination scalars (N x (C + 4H)) -> fused edge backward on local
+            source rows (no atomics, no reduce-scatter); all-reduce of the ds_dst partial sums (N x H) and of the
+            parameter gradients (< 100 KB)
+  loss    : all-gather of the last layer's rows; every rank evaluates the (tiny) triple set and keeps the gradient
+            rows of its own block.
+
+The collectives go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the
+single-GPU path.  The plan (block bounds, per-rank edge selections) is plain torch and also runs on CPU tensors, which
+is how the gloo tests exercise it.
+"""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import time
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------------ the plan
+@dataclass
+class ShardPlan:
+    bounds: List[int]            # P+1 node boundaries
+    rank: int
+    world: int
+    fwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose destination is in the local block
+    bwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose source is in the local block
+
+    @property
+    def lo(self):
+        return self.bounds[self.rank]
+
+    @property
+    def hi(self):
+        return self.bounds[self.rank + 1]
+
+
+def partition_bounds(edge_index: torch.Tensor, n_nodes: int, world: int) -> List[int]:
+    """Contiguous node blocks with (approximately) equal in-edge + out-edge counts.  Deterministic, so every rank
+    computes the same bounds from the same edge list."""
+    w = torch.bincount(edge_index[0], minlength=n_nodes) + torch.bincount(edge_index[1], minlength=n_nodes)
+    w = w.to(torch.float64) + 1e-3                      # isolated nodes still cost a row
+    cum = torch.cumsum(w, 0)
+    total = float(cum[-1])
+    targets = torch.tensor([total * k / world for k in range(1, world)], dtype=torch.float64, device=cum.device)
+    cuts = torch.searchsorted(cum, targets).tolist() if world > 1 else []
+    bounds = [0] + [min(int(c) + 1, n_nodes) for c in cuts] + [n_nodes]
+    for k in range(1, len(bounds)):                     # monotone, no empty interior blocks when N >= P
+        bounds[k] = max(bounds[k], bounds[k - 1])
+    return bounds
+
+
+def make_plan(edge_index: torch.Tensor, n_nodes: int, rank: int, world: int) -> ShardPlan:
+    bounds = partition_bounds(edge_index, n_nodes, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    src, dst = edge_index[0], edge_index[1]
+    fwd_sel = torch.nonzero((dst >= lo) & (dst < hi)).flatten()
+    bwd_sel = torch.nonzero((src >= lo) & (src < hi)).flatten()
+    return ShardPlan(bounds, rank, world, fwd_sel, bwd_sel)
+
+
+def all_gather_rows(local: torch.Tensor, bounds: List[int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Concatenate the ranks' row blocks (block k has bounds[k+1]-bounds[k] rows) into one [N, ...] tensor."""
+    world = len(bounds) - 1
+    n = bounds[-1]
+    if out is None:
+        out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out.copy_(local)
+        return out
+    pieces = [out[bounds[k]:bounds[k + 1]] for k in range(world)]
+    sizes = {p.shape[0] for p in pieces}
+    if len(sizes) == 1:
+        dist.all_gather_into_tensor(out, local.contiguous())
+    else:
+        # uneven blocks: one broadcast per owner, straight into its slice of the output (works on NCCL and gloo)
+        rank = dist.get_rank()
+        pieces[rank].copy_(local)
+        handles = [dist.broadcast(pieces[k], src=k, async_op=True) for k in range(world) if pieces[k].numel()]
+        for h in handles:
+            h.wait()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ trainer
+class ShardedGAT:
+    """Manual forward/backward of the 2-model family (custom / PyG dialect) over a row-sharded graph.
+
+    Parameters are created with the same initialisers and in the same order as the single-GPU modules under the
+    same ``torch.manual_seed``, so a sharded run starts from the identical state; ``user_emb`` rows are owned by the
+    rank that owns the node, everything else is replicated and its gradient all-reduced."""
+
+    def __init__(self, kind: str, n_users: int, n_items: int, item_feats: torch.Tensor, edge_index: torch.Tensor,
+                 hidden: int = 128, layers: int = 2, heads: int = 1, attn_dropout: float = 0.1, seed: int = 42,
+                 lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None):
+        from . import _lib
+        from .graph import build_graph
+        from .modules import CustomGAT, PyGGAT
+        self._lib = _lib
+        self.kind = kind
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.nu, self.ni, self.n = n_users, n_items, n_users + n_items
+        self.hidden, self.heads, self.n_layers = hidden, (1 if kind == "custom" else heads), layers
+        self.p_drop = attn_dropout
+        self.training = True
+        self.policy = _lib.POLICY_CUSTOM if kind == "custom" else _lib.POLICY_PYG
+
+        ei = edge_index.to(self.dev)
+        self.plan = make_plan(ei, self.n, self.rank, self.world)
+        lo, hi = self.plan.lo, self.plan.hi
+        self.n_loc = hi - lo
+        self.g_fwd = build_graph(ei[:, self.plan.fwd_sel].contiguous(), self.n)
+        self.g_bwd = build_graph(ei[:, self.plan.bwd_sel].contiguous(), self.n)
+        # dropout masks are keyed on the ORIGINAL edge id so that the rank that owns an edge's destination (forward)
+        # and the rank that owns its source (backward) regenerate the same bit
+        self.perm_fwd = self.plan.fwd_sel[self.g_fwd.perm.long()].to(torch.int32).contiguous()
+        self.perm_bwd = self.plan.bwd_sel[self.g_bwd.perm_csc.long()].to(torch.int32).contiguous()
+        self.e_total = int(ei.shape[1])
+        del ei
+
+        torch.manual_seed(seed)
+        full = (CustomGAT(n_users, n_items, item_feats.shape[1], hidden, layers) if kind == "custom"
+                else PyGGAT(n_users, n_items, item_feats.shape[1], hidden, layers, heads, attn_dropout))
+        self.u_lo, self.u_hi = min(lo, n_users), min(hi, n_users)              # user rows in the block
+        self.i_lo, self.i_hi = max(lo, n_users) - n_users, max(hi, n_users) - n_users   # item rows in the block
+        P = torch.nn.Parameter
+        self.user_emb = P(full.user_emb.weight.detach()[self.u_lo:self.u_hi].clone().to(self.dev))
+        self.item_proj = full.item_proj.to(self.dev)
+        self.feats_loc = item_feats[self.i_lo:self.i_hi].to(self.dev).contiguous()
+        self.W, self.a_src, self.a_dst, self.bias = [], [], [], []
+        for l in range(layers):
+            lay = full.layers[l] if kind == "custom" else full.convs[l]
+            self.W.append(P(lay.lin.weight.detach().clone().to(self.dev)))
+            a_s, a_d = (lay.a_src, lay.a_dst) if kind == "custom" else (lay.att_src, lay.att_dst)
+            self.a_src.append(P(a_s.detach().clone().to(self.dev).view(self.heads, hidden)))
+            self.a_dst.append(P(a_d.detach().clone().to(self.dev).view(self.heads, hidden)))
+            self.bias.append(None if kind == "custom" else P(lay.bias.detach().clone().to(self.dev)))
+        del full
+        self.replicated = list(self.item_proj.parameters()) + self.W + self.a_src + self.a_dst + [b for b in self.bias if b is not None]
+        self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay)
+        self.step_no = 0
+        self.seed = seed
+        self.comm_ms: List[float] = []
+
+    # -------------------------------------------------------------------------------------------- helpers
+    def _empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def _layer_seed(self, layer: int) -> int:
+        return (self.seed * 1_000_003 + self.step_no * 101 + layer) & (2 ** 62 - 1)
+
+    # -------------------------------------------------------------------------------------------- forward
+    def forward(self) -> torch.Tensor:
+        """Returns the local rows of Z; keeps what the backward needs in ``self.saved``."""
+        L, H, C, lib = self._lib, self.heads, self.hidden, self._lib
+        st = lib.stream()
+        with torch.enable_grad():
+            x0 = torch.cat([self.user_emb, self.item_proj(self.feats_loc)], dim=0)
+        self.x0 = x0
+        x = x0.detach()
+        self.saved = []
+        p = self.p_drop if self.training else 0.0
+        bounds = self.plan.bounds
+        for l in range(self.n_layers):
+            f_in = x.shape[1]
+            h_loc, s_loc = self._empty(self.n_loc, H * C), self._empty(self.n_loc, 2 * H)
+            lib.call("b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+                     self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), st)
+            h_full = all_gather_rows(h_loc, bounds)
+            s_full = all_gather_rows(s_loc, bounds)
+            out = self._empty(self.n_loc, C)
+            rowstat = self._empty(self.n_loc, H, 2)
+            out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
+            seed = self._layer_seed(l)
+            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(self.g_fwd.rowptr, self.plan.lo),
+                     lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.n_loc, self.plan.lo, H, C, self.policy, 0.2,
+                     lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
+            self.saved.append((x, h_full, s_full, rowstat, out if H == 1 else out_heads, p, seed))
+            x = out
+        return x
+
+    def loss_and_backward(self, z_loc: torch.Tensor, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
+        lib, H, C = self._lib, self.heads, self.hidden
+        st = lib.stream()
+        bounds = self.plan.bounds
+        z_full = all_gather_rows(z_loc, bounds)
+        s_tr = int(u.shape[0])
+        ws_bytes = lib.loss_workspace_bytes(self.n, s_tr)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
+        loss = self._empty(1)
+        kind = lib.LOSS_BPR if loss_kind == "bpr" else lib.LOSS_BCE
+        lib.call("b200gat_rank_loss_fwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
+                 kind, 1, lib.ptr(loss), lib.ptr(ws), ws_bytes, st)
+        one = torch.ones(1, dtype=torch.float32, device=self.dev)
+        dout = self._empty(self.n_loc, C)
+        lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
+                 kind, lib.ptr(one), self.plan.lo, self.n_loc, lib.ptr(dout), lib.ptr(ws), ws_bytes, st)
+        del z_full
+        grads = {}
+        for l in reversed(range(self.n_layers)):
+            x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
+            f_in = x.shape[1]
+            nodestat = self._empty(self.n_loc, H, 4)
+            lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
+                     lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), st)
+            dout_full = all_gather_rows(dout, bounds)
+            nodestat_full = all_gather_rows(nodestat, bounds)
+            dh = self._empty(self.n_loc, H * C)
+            de = self._empty(max(self.g_bwd.n_edges, 1), H)
+            ds = self._empty(self.n_loc, 2 * H)
+            lib.call("b200gat_edge_bwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(dout_full), lib.ptr(nodestat_full),
+                     lib.ptr(self.g_bwd.colptr, self.plan.lo), lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.n_loc,
+                     self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh), lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
+            ds_dst = self._empty(self.n, H)                                  # partial sums over this rank's edges
+            lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n, H,
+                     lib.ptr(ds_dst), H, st)
+            if self.world > 1:
+                dist.all_reduce(ds_dst)
+            ds[:, H:] = ds_dst[self.plan.lo:self.plan.hi]
+            del de, dout_full, nodestat_full
+            dwb = lib.dense_workspace_bytes(H, C, f_in)
+            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
+            dx = self._empty(self.n_loc, f_in)
+            dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
+            lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+                     lib.ptr(dh), lib.ptr(ds), self.n_loc, f_in, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
+                     lib.ptr(dws), dwb, st)
+            grads[self.W[l]], grads[self.a_src[l]], grads[self.a_dst[l]] = dW, da_s, da_d
+            if self.bias[l] is not None:
+                db = torch.empty_like(self.bias[l])
+                lib.call("b200gat_colsum_f32", lib.ptr(dout), self.n_loc, C, lib.ptr(db), lib.ptr(dws), dwb, st)
+                grads[self.bias[l]] = db
+            dout = dx
+        # input features: user rows take their gradient rows directly, item_proj through torch autograd
+        for p_ in [self.user_emb] + list(self.item_proj.parameters()):
+            p_.grad = None
+        self.x0.backward(dout)
+        for p_, g in grads.items():
+            p_.grad = g
+        if self.world > 1:
+            flat = torch.cat([p_.grad.reshape(-1) for p_ in self.replicated])
+            dist.all_reduce(flat)
+            off = 0
+            for p_ in self.replicated:
+                k = p_.numel()
+                p_.grad = flat[off:off + k].view_as(p_)
+                off += k
+        self.saved = []
+        return loss.view(())
+
+    def train_step(self, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
+        z = self.forward()
+        loss = self.loss_and_backward(z, u, i, j, loss_kind)
+        self.opt.step()
+        self.step_no += 1
+        return loss
+
+    @torch.no_grad()
+    def export_item_embeddings(self) -> torch.Tensor:
+        """Config 4: forward-only, returns Z[n_users:] gathered on every rank (tools/export_item_embeddings.py:140-142)."""
+        was, self.training = self.training, False
+        z = all_gather_rows(self.forward(), self.plan.bounds)
+        self.training = was
+        self.saved = []
+        return z[self.nu:]
+
+
+# ------------------------------------------------------------------------------------------------------ bench (N > 1)
+def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
+    """bench.py's N>1 leg: strong scaling of the same workload, max-over-ranks device time."""
+    from . import _lib, synth
+    import bench as B
+    nu, ni, n_inter, k = synth.CONFIGS[args.workload]
+    ei, feats = synth.make_graph(nu, ni, n_inter, k)
+    e = int(ei.shape[1])
+    tr = ShardedGAT("pyg", nu, ni, feats, ei, hidden=B.HIDDEN, layers=B.LAYERS, heads=B.HEADS, attn_dropout=0.1, device=dev)
+    u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
+    hu, hi, hj = (t.pin_memory() for t in (u, i, j))
+    du, di, dj = (t.to(dev) for t in (u, i, j))
+    for _ in range(args.warmup):
+        tr.train_step(du, di, dj)
+    sampler = B.ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(args.steps):
+        loss = tr.train_step(du, di, dj)
+    ev[1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = _lib.launch_count() - launches0
+    t_e2e = []
+    for _ in range(max(args.steps, 3)):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        uu, ii, jj = (t.to(dev, non_blocking=True) for t in (hu, hi, hj))
+        lv = tr.train_step(uu, ii, jj).item()
+        t_e2e.append((time.perf_counter() - t0) * 1e3)
+    e2e = torch.tensor([statistics.median(t_e2e)], device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step, e2e_ms = float(ms), float(e2e)
+    if rank == 0:
+        print(json.dumps({
+            "metric": B.METRIC, "value": e * B.LAYERS / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{B.LAYERS}, d={B.HIDDEN}, heads={B.HEADS}, BPR on "
+                                   f"{B.S_TRIPLES} triples, train mode, Adam step; {e} edges", "n_nodes": nu + ni, "n_edges": e,
+                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs, NCCL all-gather per layer",
+                       "block_bounds": tr.plan.bounds,
+                       "l2": "per-step working set exceeds the 126 MB L2"},
+            "e2e": {"value": e * B.LAYERS / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(3 * B.S_TRIPLES * 8), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches) * world, "clocks": clocks, "epoch_time_ms": ms_step, "loss": lv}))
+    dist.barrier()
+    dist.destroy_process_group()

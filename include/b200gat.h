@@ -66,17 +66,21 @@ int b200gat_build_graph(const int64_t* edge_index, int64_t n_edges, int64_t n_no
  * logit, s[:, 0:H] = (h * a_src).sum(-1), s[:, H:2H] = (h * a_dst).sum(-1) (:79).
  *   x [n_rows, in_features]; W [heads*channels, in_features]; a_src, a_dst [heads, channels]
  *   h [n_rows, heads*channels]; s [n_rows, 2*heads]
- * precision: B200GAT_GEMM_FP32 = CUDA-core FFMA; B200GAT_GEMM_TF32X3 = tcgen05 tensor cores with a
- * 3-term TF32 split (fp32-accurate); B200GAT_GEMM_BF16 = tcgen05 bf16 inputs, fp32 accumulation.
+ * precision: B200GAT_GEMM_FP32 = CUDA-core FFMA; B200GAT_GEMM_TF32X3 = tcgen05 tensor cores, every
+ * fp32 operand split into tf32 hi + lo and three UMMAs per K step (fp32-accurate, error ~2^-22).
+ * The tensor-core path needs in_features == channels == 128; other shapes use the FP32 kernels.
  */
 #define B200GAT_GEMM_FP32 0
 #define B200GAT_GEMM_TF32X3 1
-#define B200GAT_GEMM_BF16 2
+int b200gat_set_gemm_mode(int mode); /* process-wide; default B200GAT_GEMM_TF32X3 where the shape allows it */
+int b200gat_get_gemm_mode(void);
 int b200gat_project_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
-                        int in_features, int heads, int channels, float* h, float* s, void* stream);
+                        int in_features, int heads, int channels, float* h, float* s, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
-/* Backward of (2).  `dh` holds the aggregation part on entry and is overwritten with the full
+/* Backward of (2).  `dh` holds the aggregation part on entry and may be overwritten with the full
  * gradient of h (adds ds_src*a_src + ds_dst*a_dst); ds = [ds_src | ds_dst] [n_rows, 2*heads].
+ * workspace (both directions): b200gat_dense_workspace_bytes.
  * Outputs: dx [n_rows, in_features] (may be NULL), dW [heads*channels, in_features], da_src, da_dst. */
 int b200gat_dense_workspace_bytes(int heads, int channels, int in_features, size_t* bytes /*host*/);
 int b200gat_project_bwd_f32(const float* x, const float* W, const float* a_src, const float* a_dst, float* dh,

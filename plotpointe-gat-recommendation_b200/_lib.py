@@ -33,7 +33,9 @@ _SIGS = {
     "b200gat_launch_count": (c_int64, []),
     "b200gat_graph_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_build_graph": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "b200gat_project_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "b200gat_set_gemm_mode": (c_int, [c_int]),
+    "b200gat_get_gemm_mode": (c_int, []),
+    "b200gat_project_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "b200gat_dense_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "b200gat_project_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P,
                                         c_size_t, _P]),
@@ -100,6 +102,18 @@ def call(name: str, *args) -> None:
     _check(getattr(_lib, name)(*args), name)
     b.record()
     timing.setdefault(name, []).append((a, b))
+
+
+GEMM_FP32, GEMM_TF32X3 = 0, 1
+
+
+def set_gemm_mode(mode: int) -> None:
+    """GEMM_TF32X3 (default): tcgen05 tensor cores with the 3-term TF32 split; GEMM_FP32: CUDA-core FFMA."""
+    _check(_lib.b200gat_set_gemm_mode(mode), "set_gemm_mode")
+
+
+def get_gemm_mode() -> int:
+    return int(_lib.b200gat_get_gemm_mode())
 
 
 def launch_count() -> int:

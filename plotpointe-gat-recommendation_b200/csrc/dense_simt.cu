@@ -174,20 +174,39 @@ using namespace b200gat;
 
 static const int kSlabs = 2 * kNumSMs;  // split count for reductions over the node dimension
 
+namespace b200gat {  // gemm_tc.cu
+bool tc_supported(int in_features, int heads, int channels);
+size_t tc_workspace_bytes(int heads);
+int tc_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int heads,
+                   float* h, float* s, void* workspace, cudaStream_t st);
+int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
+                   int64_t n_rows, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st);
+}  // namespace b200gat
+
+static size_t simt_workspace_bytes(int heads, int channels, int in_features) {
+  const size_t hc = (size_t)heads * channels;
+  return ((size_t)kSlabs * (hc + 2 * heads) * in_features + (size_t)kSlabs * channels + 2 * heads * in_features) * sizeof(float) + 1024;
+}
+
 extern "C" int b200gat_dense_workspace_bytes(int heads, int channels, int in_features, size_t* bytes) {
   B200GAT_CHECK_ARG(bytes, "null");
-  const size_t hc = (size_t)heads * channels;
-  *bytes = ((size_t)kSlabs * (hc + 2 * heads) * in_features + (size_t)kSlabs * channels + 2 * heads * in_features) * sizeof(float) + 1024;
+  const size_t a = simt_workspace_bytes(heads, channels, in_features), b = tc_workspace_bytes(heads);
+  *bytes = a > b ? a : b;
   return kOk;
 }
 
 // h = x W^T ; s = [h.a_src | h.a_dst]
 extern "C" int b200gat_project_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
-                                   int in_features, int heads, int channels, float* h, float* s, void* stream) {
+                                   int in_features, int heads, int channels, float* h, float* s, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   B200GAT_CHECK_ARG(x && W && a_src && a_dst && h && s, "null pointer");
   B200GAT_CHECK_ARG(channels % 4 == 0 && in_features > 0, "bad dims");
   if (n_rows == 0) return kOk;
   cudaStream_t st = (cudaStream_t)stream;
+  if (tc_supported(in_features, heads, channels)) {
+    B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(heads), "workspace too small for the tensor-core path");
+    return tc_project_fwd(x, W, a_src, a_dst, n_rows, heads, h, s, workspace, st);
+  }
   const int HC = heads * channels;
   B200GAT_CHECK_ARG(n_rows < 2147483647LL, "n_rows too large");
   int rc = launch_sgemm(x, in_features, 1, W, 1, in_features, h, HC, (int)n_rows, HC, in_features, 1, in_features, 0,
@@ -210,6 +229,8 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const int HC = heads * channels, F = in_features, H2 = 2 * heads;
+  if (n_rows > 0 && heads == 1 && tc_supported(in_features, heads, channels))
+    return tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, dx, dW, da_src, da_dst, workspace, st);
   float* part = (float*)workspace;                       // [kSlabs, HC + 2H, F]
   float* v = part + (size_t)kSlabs * (HC + H2) * F + (size_t)kSlabs * channels;  // [2H, F]
   if (n_rows == 0) {

@@ -40,8 +40,10 @@ class GATLayerFunction(torch.autograd.Function):
             st = _lib.stream()
             h = _empty((n, heads * channels), x)
             s = _empty((n, 2 * heads), x)
+            ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             _lib.call("b200gat_project_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), n, f_in, heads,
-                      channels, _lib.ptr(h), _lib.ptr(s), st)
+                      channels, _lib.ptr(h), _lib.ptr(s), _lib.ptr(ws), ws_bytes, st)
             out = _empty((n, channels), x)
             rowstat = _empty((n, heads, 2), x) if need_grad else None
             out_heads = _empty((n, heads, channels), x) if (need_grad and heads > 1) else None

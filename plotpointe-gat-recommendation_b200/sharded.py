@@ -177,8 +177,10 @@ class ShardedGAT:
         for l in range(self.n_layers):
             f_in = x.shape[1]
             h_loc, s_loc = self._empty(self.n_loc, H * C), self._empty(self.n_loc, 2 * H)
+            dwb = lib.dense_workspace_bytes(H, C, f_in)
+            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             lib.call("b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
-                     self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), st)
+                     self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), lib.ptr(dws), dwb, st)
             h_full = all_gather_rows(h_loc, bounds)
             s_full = all_gather_rows(s_loc, bounds)
             out = self._empty(self.n_loc, C)

@@ -114,9 +114,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 
 // ---- descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128B swizzle, version 1 (Blackwell). Offsets in bytes.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the form MN-major
+// tf32 operands need)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout_type = 2) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout_type << 61);
 }
 // instruction descriptor: D=f32, A=B=tf32, dense
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
@@ -385,9 +387,13 @@ struct DwParams {
   float* part_v;     // [grid][2*128]
 };
 
-// MN-major staging: 16-byte chunk c4 (0..31) of node row r (0..31): 8-row K groups x 32-float MN blocks, 1 KB atoms
+// MN-major tf32 staging (SWIZZLE_128B_BASE32B): atoms of 4 K rows x 128 B (32 floats along MN); inside an atom
+// the 32-byte chunk index is XORed with the row index (Swizzle<2,5,2>).  Atoms are laid out K-group major:
+// offset = ((r/4)*4 + mn_block) * 512, so LBO (next MN block) = 512 B and SBO (next 4 K rows) = 2048 B.
+// Returns the byte offset of 16-byte chunk c4 (0..31) of node row r (0..31).
 __device__ __forceinline__ uint32_t mn_off(int r, int c4) {
-  return (uint32_t)(((r >> 3) * 4 + (c4 >> 3)) * 1024 + (r & 7) * 128 + ((((c4 & 7) ^ r) & 7) << 4));
+  const int j = c4 & 7;
+  return (uint32_t)(((r >> 2) * 4 + (c4 >> 3)) * 512 + (r & 3) * 128 + ((((j >> 1) ^ r) & 3) << 5) + ((j & 1) << 4));
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
@@ -487,8 +493,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
 #pragma unroll
         for (int kg = 0; kg < kDwRows / kUmmaK; ++kg) {
           const uint32_t ko = kg * 4096;
-          const uint64_t dah = make_desc(a_hi + ko, 1024, 4096), dal = make_desc(a_lo + ko, 1024, 4096);
-          const uint64_t dbh = make_desc(b_hi + ko, 1024, 4096), dbl = make_desc(b_lo + ko, 1024, 4096);
+          const uint64_t dah = make_desc(a_hi + ko, 512, 2048, 1), dal = make_desc(a_lo + ko, 512, 2048, 1);
+          const uint64_t dbh = make_desc(b_hi + ko, 512, 2048, 1), dbl = make_desc(b_lo + ko, 512, 2048, 1);
           umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
           umma_tf32(tmem_base, dal, dbh, idesc, 1);
           umma_tf32(tmem_base, dah, dbl, idesc, 1);

@@ -105,6 +105,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // 1D bulk copy global -> shared through the TMA unit, completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -373,6 +388,11 @@ constexpr int kDwRows = 32;                                 // node rows per sta
 constexpr int kDwOperandBytes = 2 * kDwRows * 512;          // hi + lo of one operand (32 KB)
 constexpr int kDwStageBytes = 2 * kDwOperandBytes;          // A + B (64 KB)
 constexpr int kDwStages = 3;
+// The tensor core truncates when it adds into the fp32 accumulator, so a long accumulation chain drifts
+// (measured 1.4e-5 relative over 2000 rows).  Every kDwGroup stages (256 node rows, 96 UMMAs) the running tile is
+// therefore "promoted": the epilogue warps add it into a second TMEM tile with round-to-nearest FADDs while the
+// MMA warp continues into the other running tile.  TMEM columns: [0,128) running A, [128,256) running B, [256,384) sum.
+constexpr int kDwGroup = 8;
 constexpr int kDwSmem = 1024 + kDwStages * kDwStageBytes + kDwEpiWarps * 32 * 128 + 2 * kTileN * 4 + 256;
 
 struct DwParams {
@@ -404,24 +424,29 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
   const uint32_t sEpi = sStage + kDwStages * kDwStageBytes;
   float* att = reinterpret_cast<float*>(sm + kDwStages * kDwStageBytes + kDwEpiWarps * 32 * 128);
   const uint32_t sBar = sEpi + kDwEpiWarps * 32 * 128 + 2 * kTileN * 4;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 32, bar_tfull = sBar + 64;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 80);
+  const uint32_t bar_full = sBar, bar_empty = sBar + 32, bar_tfull = sBar + 64, bar_tempty = sBar + 80, bar_done = sBar + 96;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 112);
   float* vred = reinterpret_cast<float*>(sm);   // reused after the main loop: [8 warps][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
   const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_cta);
   const int n_stages_total = r_begin < r_end ? (int)((r_end - r_begin + kDwRows - 1) / kDwRows) : 0;
+  const int n_groups = (n_stages_total + kDwGroup - 1) / kDwGroup;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDwStages; ++i) {
       mbar_init(bar_full + 8 * i, kDwProducerWarps * 32);
       mbar_init(bar_empty + 8 * i, 1);
     }
-    mbar_init(bar_tfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, kDwEpiWarps * 32);
+    }
+    mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == kDwProducerWarps + kDwEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 128);
+  if (warp == kDwProducerWarps + kDwEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   for (int i = threadIdx.x; i < 2 * kTileN; i += kDwThreads) att[i] = i < kTileN ? p.att_src[i] : p.att_dst[i - kTileN];
   tc_fence_before();
   __syncthreads();
@@ -478,7 +503,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
     }
     // park the side sums; reduced after the block barrier below
     // (the MMA pipeline may still be reading the stages: wait until the accumulator is published)
-    mbar_wait(bar_tfull, 0);
+    mbar_wait(bar_done, 0);
     *reinterpret_cast<float4*>(vred + (warp * 2 + 0) * kTileN + c4 * 4) = vs;
     *reinterpret_cast<float4*>(vred + (warp * 2 + 1) * kTileN + c4 * 4) = vd;
   } else if (warp == kDwProducerWarps + kDwEpiWarps) {
@@ -486,6 +511,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
       constexpr uint32_t idesc = make_idesc(kTileM, kTileN, 1, 1);
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < n_stages_total; ++it) {
+        const int grp = it / kDwGroup, buf = grp & 1, in_grp = it - grp * kDwGroup;
+        if (in_grp == 0) {  // the promotion of this buffer's previous group must have drained it
+          mbar_wait(bar_tempty + 8 * buf, ((grp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t d = tmem_base + buf * kTileN;
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t a_hi = sStage + stage * kDwStageBytes, a_lo = a_hi + kDwRows * 512;
@@ -495,26 +526,55 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
           const uint32_t ko = kg * 4096;
           const uint64_t dah = make_desc(a_hi + ko, 512, 2048, 1), dal = make_desc(a_lo + ko, 512, 2048, 1);
           const uint64_t dbh = make_desc(b_hi + ko, 512, 2048, 1), dbl = make_desc(b_lo + ko, 512, 2048, 1);
-          umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
-          umma_tf32(tmem_base, dal, dbh, idesc, 1);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1);
+          umma_tf32(d, dah, dbh, idesc, (in_grp | kg) != 0);
+          umma_tf32(d, dal, dbh, idesc, 1);
+          umma_tf32(d, dah, dbl, idesc, 1);
         }
         umma_commit(bar_empty + 8 * stage);
+        if (in_grp == kDwGroup - 1 || it == n_stages_total - 1) umma_commit(bar_tfull + 8 * buf);
         if (++stage == kDwStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(bar_tfull);
+      umma_commit(bar_done);   // every UMMA has finished reading shared memory
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     uint8_t* stg = sm + kDwStages * kDwStageBytes + (warp - kDwProducerWarps) * 32 * 128;
     float* out = p.part_dw + (size_t)blockIdx.x * kTileM * kTileN;
-    mbar_wait(bar_tfull, 0);
-    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // promote all groups but the last into the sum tile
+    for (int grp = 0; grp + 1 < n_groups; ++grp) {
+      const int buf = grp & 1;
+      mbar_wait(bar_tfull + 8 * buf, (grp >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < kTileN / 32; ++c) {
+        float v[32], acc[32];
+        tmem_ld32(lane_base + buf * kTileN + c * 32, v);
+        if (grp > 0) {
+          tmem_ld32(lane_base + 2 * kTileN + c * 32, acc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += acc[j];
+        }
+        tmem_st32(lane_base + 2 * kTileN + c * 32, v);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+    if (n_groups > 0) {
+      const int grp = n_groups - 1;
+      mbar_wait(bar_tfull + 8 * (grp & 1), (grp >> 1) & 1);
+      tc_fence_after();
+    }
     for (int c = 0; c < kTileN / 32; ++c) {
       float v[32];
-      if (n_stages_total > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      if (n_groups > 0) {
+        tmem_ld32(lane_base + ((n_groups - 1) & 1) * kTileN + c * 32, v);
+        if (n_groups > 1) {
+          float acc[32];
+          tmem_ld32(lane_base + 2 * kTileN + c * 32, acc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += acc[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -542,7 +602,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
     for (int w = 0; w < kDwProducerWarps; ++w) a += vred[(w * 2 + threadIdx.x / kTileN) * kTileN + threadIdx.x % kTileN];
     p.part_v[(size_t)blockIdx.x * 2 * kTileN + threadIdx.x] = a;
   }
-  if (warp == kDwProducerWarps + kDwEpiWarps) tmem_dealloc(tmem_base, 128);
+  if (warp == kDwProducerWarps + kDwEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
 // out[i] = sum_z part[z*stride + i]

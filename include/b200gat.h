@@ -61,6 +61,14 @@ int b200gat_build_graph(const int64_t* edge_index, int64_t n_edges, int64_t n_no
                         int32_t* perm, int32_t* colptr, int32_t* row, int32_t* perm_csc, int32_t* csr2csc,
                         int32_t* n_bad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Row schedule for the edge kernels: sched[k] = (row, ptr[row], ptr[row+1], 0) (int32 x4) for the k-th row of
+ * `ptr` (a CSR rowptr or CSC colptr slice, n_rows+1 entries) in descending-degree order.  The persistent warps
+ * of (3)/(4) walk it round-robin: hubs start first and every warp gets the same degree mix.
+ * degree_bound: any value > the largest degree (e.g. n_edges+1). */
+int b200gat_schedule_workspace_bytes(int64_t n_rows, size_t* bytes /*host*/);
+int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_t degree_bound, int32_t* sched, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- (2) projection + attention logits ----------------------------------------------------------
  * h = x W^T (self.lin(x), train_gat_custom.py:77; GATConv.lin) and the per-node halves of the edge
  * logit, s[:, 0:H] = (h * a_src).sum(-1), s[:, H:2H] = (h * a_dst).sum(-1) (:79).
@@ -94,16 +102,16 @@ int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, float* out,
 /* ---- (3) fused edge forward ---------------------------------------------------------------------
  * Replaces train_gat_custom.py:79-92 (logit, LeakyReLU, clamp, exp, scatter_add denominator,
  * normalise, dropout, index_add aggregate) / GATConv's propagate at train_gat_pyg.py:87.
- * One warp per destination row `row_offset + r`, r in [0, n_rows).
+ * Persistent warps, one destination row at a time; local row r is global node `row_offset + r`.
  *   h [*, heads*channels], s [*, 2*heads] : indexed by global node id
- *   rowptr [n_rows+1] (already offset to the first local row), col/perm : CSR arrays
+ *   sched [n_rows, 4] : b200gat_build_schedule of the (local slice of the) CSR rowptr; col/perm : CSR arrays
  *   bias [channels] or NULL; out [n_rows, channels] (head mean + bias)
  *   out_heads [n_rows, heads, channels] or NULL (per-head outputs, needed by the backward if heads>1)
  *   rowstat [n_rows, heads, 2] = (running max m (0 for CUSTOM), 1/(denominator+eps)) or NULL
  *   p_drop/seed : attention dropout (0 = off); the mask is a function of (seed, original edge id,
  *   head) only.
  */
-int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* rowptr, const int32_t* col,
+int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, const int32_t* col,
                          const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels, int policy,
                          float negative_slope, const float* bias, float* out, float* out_heads, float* rowstat,
                          float p_drop, uint64_t seed, void* stream);
@@ -111,16 +119,18 @@ int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* rowptr, 
 /* ---- (4) fused edge backward --------------------------------------------------------------------
  * Replaces autograd's replay of the lines above (loss.backward(), train_gat_custom.py:361).
  * node_prep : nodestat[r,h] = (s_dst, m, 1/D, t), t = (1/H) dout[r,:].out_heads[r,h,:]
- *             (for heads==1 pass out as out_heads, and bias to subtract it if it was added)
- * edge_bwd  : warp per SOURCE row over the CSC: dh[r,:,:] = sum_i alpha_ij dout_i / H (no atomics),
+ *             (for heads==1 pass out as out_heads, and bias to subtract it if it was added);
+ *             dbias (nullable) = column sums of dout in a fixed order (GATConv bias gradient),
+ *             workspace >= 1184*channels floats when dbias != NULL
+ * edge_bwd  : warp per SOURCE row over the CSC schedule: dh[r,:,:] = sum_i alpha_ij dout_i / H (no atomics),
  *             de[q,h] = d loss / d logit for CSC position q, ds_src[r*ld_ds + h] = sum_q de
  * ds_dst    : ds_dst[r*ld_ds + h] = sum over the in-edges of r (CSR order) of de[csr2csc[e], h]
  */
 int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
                           const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
-                          float* nodestat, void* stream);
+                          float* nodestat, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
-                         const int32_t* colptr, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
+                         const int32_t* sched, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
                          int64_t row_offset, int heads, int channels, int policy, float negative_slope, float* dh,
                          float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream);
 int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int heads,

@@ -42,7 +42,9 @@ _SIGS = {
     "b200gat_colsum_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
     "b200gat_edge_fwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P, _P, _P,
                                      c_float, c_uint64, _P]),
-    "b200gat_node_prep_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P]),
+    "b200gat_node_prep_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "b200gat_schedule_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(c_size_t)]),
+    "b200gat_build_schedule": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P,
                                      _P, c_int, c_float, c_uint64, _P]),
     "b200gat_ds_dst_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P]),
@@ -125,6 +127,22 @@ def graph_workspace_bytes(n_nodes: int, n_edges: int) -> int:
     out = c_size_t(0)
     _check(_lib.b200gat_graph_workspace_bytes(n_nodes, n_edges, ctypes.byref(out)), "graph_workspace_bytes")
     return out.value
+
+
+def schedule_workspace_bytes(n_rows: int) -> int:
+    out = c_size_t(0)
+    _check(_lib.b200gat_schedule_workspace_bytes(n_rows, ctypes.byref(out)), "schedule_workspace_bytes")
+    return out.value
+
+
+def build_schedule(ptr_tensor, offset: int, n_rows: int, degree_bound: int):
+    """Descending-degree row schedule (int32 [n_rows, 4]) of ptr_tensor[offset : offset+n_rows+1]."""
+    sched = torch.empty((max(n_rows, 1), 4), dtype=torch.int32, device=ptr_tensor.device)
+    wsb = schedule_workspace_bytes(n_rows)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=ptr_tensor.device)
+    with torch.cuda.device(ptr_tensor.device):
+        call("b200gat_build_schedule", ptr(ptr_tensor, offset), n_rows, degree_bound, ptr(sched), ptr(ws), wsb, stream())
+    return sched
 
 
 def dense_workspace_bytes(heads: int, channels: int, in_features: int) -> int:

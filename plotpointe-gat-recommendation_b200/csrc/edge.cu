@@ -60,113 +60,202 @@ struct Unroll {
 };
 
 // --------------------------------------------------------------------------------------------
+// row schedule: rows in descending-degree order, one int4 (row, beg, end, 0) each.  Persistent warps walk
+// the schedule round-robin, so every warp gets the same mix of long and short rows (hubs first) and the next
+// row's descriptor is a plain strided load that can be prefetched.
+// --------------------------------------------------------------------------------------------
+__global__ void degree_keys_kernel(const int32_t* __restrict__ ptr, int64_t n_rows, int32_t* __restrict__ keys) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+    keys[r] = ptr[r + 1] - ptr[r];
+}
+__global__ void build_schedule_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ asc_rows, int64_t n_rows,
+                                      int4* __restrict__ sched) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_rows; k += (int64_t)gridDim.x * blockDim.x) {
+    const int r = asc_rows[n_rows - 1 - k];   // descending degree
+    sched[k] = make_int4(r, ptr[r], ptr[r + 1], 0);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // forward
 // --------------------------------------------------------------------------------------------
+constexpr int kEdgeThreads = 128;
+
+template <int H, int CV>
+struct RowBuf {
+  float4 v[H][CV];
+};
+
 template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(128) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
-                                                       const int32_t* __restrict__ rowptr,
-                                                       const int32_t* __restrict__ col,
-                                                       const int32_t* __restrict__ perm, int n_rows, int row_offset,
-                                                       float neg_slope, const float* __restrict__ bias,
-                                                       float* __restrict__ out, float* __restrict__ out_heads,
-                                                       float2* __restrict__ rowstat, float p_drop, uint64_t seed) {
+__global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+                                                                const int4* __restrict__ sched,
+                                                                const int32_t* __restrict__ col,
+                                                                const int32_t* __restrict__ perm, int n_rows, int row_offset,
+                                                                float neg_slope, const float* __restrict__ bias,
+                                                                float* __restrict__ out, float* __restrict__ out_heads,
+                                                                float2* __restrict__ rowstat, float p_drop, uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  constexpr int U = Unroll<H, CV>::value;
+  constexpr int U = (H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : 4);   // rows per load group; two groups in flight
   const int lane = threadIdx.x & 31;
-  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (r >= n_rows) return;
-  const int beg = rowptr[r], end = rowptr[r + 1];
+  const int n_warps = gridDim.x * (kEdgeThreads / 32);
+  int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  if (idx >= n_rows) return;
   const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
 
-  float sd[H], m[H], l[H];
-  float4 acc[H][CV];
+  // metadata of the current row: descriptor + first chunk of (col, s_src), prefetched one row ahead
+  int4 d = __ldg(sched + idx);
+  int c_first = 0;
+  float ss_first[H];
+  {
+    const bool v = d.y + lane < d.z;
+    c_first = v ? __ldg(col + d.y + lane) : 0;
 #pragma unroll
-  for (int hh = 0; hh < H; ++hh) {
-    sd[hh] = s[(size_t)(row_offset + r) * (2 * H) + H + hh];
-    m[hh] = POLICY == kPyG ? -INFINITY : 0.f;
-    l[hh] = 0.f;
-#pragma unroll
-    for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hh = 0; hh < H; ++hh) ss_first[hh] = v ? __ldg(s + (size_t)c_first * (2 * H) + hh) : 0.f;
   }
 
-  for (int base = beg; base < end; base += 32) {
-    const int e = base + lane;
-    const bool valid = e < end;
-    int c = valid ? col[e] : 0;
-    float p[H];
+  auto load_group = [&](RowBuf<H, CV>(&buf)[U], int c, int k) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ck = __shfl_sync(kFull, c, (k + u) & 31);
+      const float* hp = h + (size_t)ck * HC + lane * 4;
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh)
+#pragma unroll
+        for (int cv = 0; cv < CV; ++cv) buf[u].v[hh][cv] = ldg4(hp + hh * C + cv * 128);
+    }
+  };
+
+  while (true) {
+    const int r = d.x, beg = d.y, end = d.z;
+    const int idx_next = idx + n_warps;
+    const bool has_next = idx_next < n_rows;
+    int4 dn = make_int4(0, 0, 0, 0);
+    if (has_next) dn = __ldg(sched + idx_next);          // in flight while this row is processed
+
+    float sd[H], m[H], l[H];
+    float4 acc[H][CV];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
-      float z = -INFINITY;
-      if (valid) z = activate<POLICY>(s[(size_t)c * (2 * H) + hh] + sd[hh], neg_slope);
-      if (POLICY == kPyG) {
-        const float nm = fmaxf(m[hh], warp_max(z));
-        if (nm != m[hh]) {  // warp-uniform
-          const float scale = expf(m[hh] - nm);
-          l[hh] *= scale;
+      sd[hh] = __ldg(s + (size_t)(row_offset + r) * (2 * H) + H + hh);
+      m[hh] = POLICY == kPyG ? -INFINITY : 0.f;
+      l[hh] = 0.f;
 #pragma unroll
-          for (int cv = 0; cv < CV; ++cv) {
-            acc[hh][cv].x *= scale; acc[hh][cv].y *= scale; acc[hh][cv].z *= scale; acc[hh][cv].w *= scale;
-          }
-          m[hh] = nm;
-        }
-        p[hh] = valid ? expf(z - nm) : 0.f;
+      for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int c_next = 0;
+    float ss_next[H];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ss_next[hh] = 0.f;
+
+    for (int base = beg; base < end; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < end;
+      int c;
+      float sv[H];
+      if (base == beg) {
+        c = c_first;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) sv[hh] = ss_first[hh];
       } else {
-        p[hh] = valid ? expf(z) : 0.f;
+        c = valid ? __ldg(col + e) : 0;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) sv[hh] = valid ? __ldg(s + (size_t)c * (2 * H) + hh) : 0.f;
       }
-      l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
-      if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)perm[e], hh, p_drop, inv_keep);
-    }
-    // zero-weight tail lanes re-read lane 0's row so they add no new cache lines
-    const int c0 = __shfl_sync(kFull, c, 0);
-    if (!valid) c = c0;
-    const int cnt = min(32, end - base);
-    for (int k = 0; k < cnt; k += U) {
-      float4 v[U][H][CV];
-      float pk[U][H];
+      // zero-weight tail lanes re-read lane 0's row so they add no new cache lines
+      const int c0 = __shfl_sync(kFull, c, 0);
+      if (!valid) c = c0;
+      const int cnt = min(32, end - base);
+      RowBuf<H, CV> bufA[U], bufB[U];
+      load_group(bufA, c, 0);                              // gathers start before the softmax math
+      if (U < cnt) load_group(bufB, c, U);
+
+      float p[H];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ck = __shfl_sync(kFull, c, (k + u) & 31);
-        const float* hp = h + (size_t)ck * HC + lane * 4;
+      for (int hh = 0; hh < H; ++hh) {
+        float z = -INFINITY;
+        if (valid) z = activate<POLICY>(sv[hh] + sd[hh], neg_slope);
+        if (POLICY == kPyG) {
+          const float nm = fmaxf(m[hh], warp_max(z));
+          if (nm != m[hh]) {  // warp-uniform
+            const float scale = expf(m[hh] - nm);
+            l[hh] *= scale;
 #pragma unroll
-        for (int hh = 0; hh < H; ++hh) {
-          pk[u][hh] = __shfl_sync(kFull, p[hh], (k + u) & 31);
+            for (int cv = 0; cv < CV; ++cv) {
+              acc[hh][cv].x *= scale; acc[hh][cv].y *= scale; acc[hh][cv].z *= scale; acc[hh][cv].w *= scale;
+            }
+            m[hh] = nm;
+          }
+          p[hh] = valid ? expf(z - nm) : 0.f;
+        } else {
+          p[hh] = valid ? expf(z) : 0.f;
+        }
+        l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
+        if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)__ldg(perm + e), hh, p_drop, inv_keep);
+      }
+      if (base == beg && has_next) {                       // next row's first chunk (its descriptor has landed by now)
+        const bool v = dn.y + lane < dn.z;
+        c_next = v ? __ldg(col + dn.y + lane) : 0;
 #pragma unroll
-          for (int cv = 0; cv < CV; ++cv) v[u][hh][cv] = ldg4(hp + hh * C + cv * 128);
+        for (int hh = 0; hh < H; ++hh) ss_next[hh] = v ? __ldg(s + (size_t)c_next * (2 * H) + hh) : 0.f;
+      }
+
+      auto consume = [&](RowBuf<H, CV>(&buf)[U], int k) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int hh = 0; hh < H; ++hh) {
+            const float pk = __shfl_sync(kFull, p[hh], (k + u) & 31);
+#pragma unroll
+            for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk, buf[u].v[hh][cv], acc[hh][cv]);
+          }
+      };
+      for (int k = 0; k < cnt; k += 2 * U) {
+        consume(bufA, k);
+        if (k + 2 * U < cnt) load_group(bufA, c, k + 2 * U);
+        if (k + U < cnt) {
+          consume(bufB, k + U);
+          if (k + 3 * U < cnt) load_group(bufB, c, k + 3 * U);
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh)
-#pragma unroll
-          for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk[u][hh], v[u][hh][cv], acc[hh][cv]);
     }
-  }
+    if (beg == end && has_next) {                          // empty row: the prefetch above did not run
+      const bool v = dn.y + lane < dn.z;
+      c_next = v ? __ldg(col + dn.y + lane) : 0;
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) ss_next[hh] = v ? __ldg(s + (size_t)c_next * (2 * H) + hh) : 0.f;
+    }
 
-  float inv[H];
-#pragma unroll
-  for (int hh = 0; hh < H; ++hh) {
-    const float lt = warp_sum(l[hh]);
-    inv[hh] = 1.f / (lt + (POLICY == kCustom ? 1e-9f : 1e-16f));
-    if (lane == 0 && rowstat) rowstat[(size_t)r * H + hh] = make_float2(beg < end ? m[hh] : 0.f, inv[hh]);
-  }
-#pragma unroll
-  for (int cv = 0; cv < CV; ++cv) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    float inv[H];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
-      float4 a = acc[hh][cv];
-      a.x *= inv[hh]; a.y *= inv[hh]; a.z *= inv[hh]; a.w *= inv[hh];
-      if (out_heads) st_stream4(out_heads + (size_t)r * HC + hh * C + cv * 128 + lane * 4, a);
-      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      const float lt = warp_sum(l[hh]);
+      inv[hh] = 1.f / (lt + (POLICY == kCustom ? 1e-9f : 1e-16f));
+      if (lane == 0 && rowstat) rowstat[(size_t)r * H + hh] = make_float2(beg < end ? m[hh] : 0.f, inv[hh]);
     }
-    if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
-    if (bias) {
-      const float4 b = ldg4(bias + cv * 128 + lane * 4);
-      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {
+        float4 a = acc[hh][cv];
+        a.x *= inv[hh]; a.y *= inv[hh]; a.z *= inv[hh]; a.w *= inv[hh];
+        if (out_heads) st_stream4(out_heads + (size_t)r * HC + hh * C + cv * 128 + lane * 4, a);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
+      if (bias) {
+        const float4 b = ldg4(bias + cv * 128 + lane * 4);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
     }
-    *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
+    if (!has_next) break;
+    idx = idx_next;
+    d = dn;
+    c_first = c_next;
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ss_first[hh] = ss_next[hh];
   }
 }
 
@@ -175,147 +264,213 @@ __global__ void __launch_bounds__(128) edge_fwd_kernel(const float* __restrict__
 //   t[i,h] = (1/H) * dout[i,:] . out_h[i,h,:]   (= sum_k alpha_ik dalpha_ik)
 // --------------------------------------------------------------------------------------------
 template <int H, int CV>
-__global__ void __launch_bounds__(128) node_prep_kernel(const float* __restrict__ dout,       // [n_rows, C]
+__global__ void __launch_bounds__(256) node_prep_kernel(const float* __restrict__ dout,       // [n_rows, C]
                                                         const float* __restrict__ out_heads,  // [n_rows, H, C]
                                                         const float* __restrict__ bias,       // subtracted (H==1, PyG)
                                                         const float* __restrict__ s, const float2* __restrict__ rowstat,
-                                                        int n_rows, int row_offset, float4* __restrict__ nodestat) {
+                                                        int n_rows, int row_offset, float4* __restrict__ nodestat,
+                                                        float* __restrict__ colsum_part /*[gridDim.x, C] or null*/) {
   constexpr int C = CV * 128;
-  const int lane = threadIdx.x & 31;
-  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (r >= n_rows) return;
-  float t[H];
-#pragma unroll
-  for (int hh = 0; hh < H; ++hh) t[hh] = 0.f;
+  __shared__ float4 red[8][CV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 csum[CV];
+  float4 b[CV];
 #pragma unroll
   for (int cv = 0; cv < CV; ++cv) {
-    const float4 g = ld_stream4(dout + (size_t)r * C + cv * 128 + lane * 4);
+    csum[cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[cv] = bias ? ldg4(bias + cv * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int r = blockIdx.x * 8 + warp; r < n_rows; r += gridDim.x * 8) {   // fixed row -> warp map: deterministic sums
+    float t[H];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) t[hh] = 0.f;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) {
+      const float4 g = ld_stream4(dout + (size_t)r * C + cv * 128 + lane * 4);
+      csum[cv].x += g.x; csum[cv].y += g.y; csum[cv].z += g.z; csum[cv].w += g.w;
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {
+        float4 o = ld_stream4(out_heads + ((size_t)r * H + hh) * C + cv * 128 + lane * 4);
+        o.x -= b[cv].x; o.y -= b[cv].y; o.z -= b[cv].z; o.w -= b[cv].w;
+        t[hh] += dot4(g, o);
+      }
+    }
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
-      float4 o = ld_stream4(out_heads + ((size_t)r * H + hh) * C + cv * 128 + lane * 4);
-      if (bias) {
-        const float4 b = ldg4(bias + cv * 128 + lane * 4);
-        o.x -= b.x; o.y -= b.y; o.z -= b.z; o.w -= b.w;
+      const float tt = warp_sum(t[hh]) * (1.f / H);
+      if (lane == 0) {
+        const float2 rs = rowstat[(size_t)r * H + hh];
+        nodestat[(size_t)r * H + hh] = make_float4(s[(size_t)(row_offset + r) * (2 * H) + H + hh], rs.x, rs.y, tt);
       }
-      t[hh] += dot4(g, o);
     }
   }
+  if (colsum_part) {
 #pragma unroll
-  for (int hh = 0; hh < H; ++hh) {
-    const float tt = warp_sum(t[hh]) * (1.f / H);
-    if (lane == 0) {
-      const float2 rs = rowstat[(size_t)r * H + hh];
-      nodestat[(size_t)r * H + hh] = make_float4(s[(size_t)(row_offset + r) * (2 * H) + H + hh], rs.x, rs.y, tt);
+    for (int cv = 0; cv < CV; ++cv) red[warp][cv][lane] = csum[cv];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int cv = 0; cv < CV; ++cv) {
+        float4 a = red[0][cv][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+          const float4 v = red[w][cv][lane];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(colsum_part + (size_t)blockIdx.x * C + cv * 128 + lane * 4) = a;
+      }
     }
   }
 }
 
+// out[c] = sum over parts, fixed order
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int k = 0; k < n_parts; ++k) a += part[(size_t)k * C + c];
+  out[c] = a;
+}
+
 // --------------------------------------------------------------------------------------------
-// backward, step 1: CSC pass (warp per source row)
+// backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
 template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(128) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
-                                                       const float* __restrict__ dout,
-                                                       const float4* __restrict__ nodestat,
-                                                       const int32_t* __restrict__ colptr,
-                                                       const int32_t* __restrict__ row,
-                                                       const int32_t* __restrict__ perm_csc, int n_rows, int row_offset,
-                                                       float neg_slope, float* __restrict__ dh,
-                                                       float* __restrict__ de, float* __restrict__ ds_src,
-                                                       int ld_ds, float p_drop, uint64_t seed) {
+__global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+                                                                const float* __restrict__ dout,
+                                                                const float4* __restrict__ nodestat,
+                                                                const int4* __restrict__ sched,
+                                                                const int32_t* __restrict__ row,
+                                                                const int32_t* __restrict__ perm_csc, int n_rows, int row_offset,
+                                                                float neg_slope, float* __restrict__ dh,
+                                                                float* __restrict__ de, float* __restrict__ ds_src,
+                                                                int ld_ds, float p_drop, uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  constexpr int U = Unroll<1, CV>::value >= 4 ? 4 : Unroll<1, CV>::value;
+  constexpr int U = CV >= 2 ? 2 : 4;   // dout rows per load group; two groups in flight
   const int lane = threadIdx.x & 31;
-  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (r >= n_rows) return;
-  const int beg = colptr[r], end = colptr[r + 1];
-  const size_t j = (size_t)row_offset + r;
+  const int n_warps = gridDim.x * (kEdgeThreads / 32);
+  int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  if (idx >= n_rows) return;
   const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
   constexpr float invH = 1.f / H;
 
-  float4 hj[H][CV], acc[H][CV];
-  float ssj[H], dss[H];
-#pragma unroll
-  for (int hh = 0; hh < H; ++hh) {
-    ssj[hh] = s[j * (2 * H) + hh];
-    dss[hh] = 0.f;
-#pragma unroll
-    for (int cv = 0; cv < CV; ++cv) {
-      hj[hh][cv] = (beg < end) ? ldg4(h + j * HC + hh * C + cv * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
+  int4 d = __ldg(sched + idx);
+  int i_first = (d.y + lane < d.z) ? __ldg(row + d.y + lane) : 0;
 
-  for (int base = beg; base < end; base += 32) {
-    const int q = base + lane;
-    const bool valid = q < end;
-    int i = valid ? row[q] : 0;
-    float alpha[H], agg[H], gsc[H], tt[H], ks[H], my_de[H];
+  struct GBuf { float4 g[CV]; };
+  auto load_group = [&](GBuf(&buf)[U], int i, int k) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ik = __shfl_sync(kFull, i, (k + u) & 31);
+#pragma unroll
+      for (int cv = 0; cv < CV; ++cv) buf[u].g[cv] = ldg4(dout + (size_t)ik * C + cv * 128 + lane * 4);
+    }
+  };
+
+  while (true) {
+    const int r = d.x, beg = d.y, end = d.z;
+    const int idx_next = idx + n_warps;
+    const bool has_next = idx_next < n_rows;
+    int4 dn = make_int4(0, 0, 0, 0);
+    if (has_next) dn = __ldg(sched + idx_next);
+    const size_t j = (size_t)row_offset + r;
+
+    float4 hj[H][CV], acc[H][CV];
+    float ssj[H], dss[H];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
-      alpha[hh] = agg[hh] = gsc[hh] = tt[hh] = my_de[hh] = 0.f;
-      ks[hh] = 1.f;
-      if (valid) {
-        const float4 st = __ldg(nodestat + (size_t)i * H + hh);  // (s_dst, m, 1/D, t)
-        const float z0 = ssj[hh] + st.x;
-        const float zl = z0 > 0.f ? z0 : z0 * neg_slope;
-        float zc = zl, pass = 1.f;
-        if (POLICY == kCustom) {
-          zc = fminf(fmaxf(zl, -10.f), 10.f);
-          pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;  // clamp passes gradient only inside [-10,10]
-        }
-        alpha[hh] = expf(zc - st.y) * st.z;
-        gsc[hh] = (z0 > 0.f ? 1.f : neg_slope) * pass;
-        tt[hh] = st.w;
-        if (DROPOUT) ks[hh] = dropout_scale(seed, (uint32_t)perm_csc[q], hh, p_drop, inv_keep);
-        agg[hh] = alpha[hh] * ks[hh] * invH;
+      ssj[hh] = __ldg(s + j * (2 * H) + hh);
+      dss[hh] = 0.f;
+#pragma unroll
+      for (int cv = 0; cv < CV; ++cv) {
+        hj[hh][cv] = (beg < end) ? ldg4(h + j * HC + hh * C + cv * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const int i0 = __shfl_sync(kFull, i, 0);
-    if (!valid) i = i0;
-    const int cnt = min(32, end - base);
-    for (int k = 0; k < cnt; k += U) {
-      float4 g[U][CV];
-      int kk[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        kk[u] = (k + u) & 31;
-        const int ik = __shfl_sync(kFull, i, kk[u]);
-#pragma unroll
-        for (int cv = 0; cv < CV; ++cv) g[u][cv] = ldg4(dout + (size_t)ik * C + cv * 128 + lane * 4);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) {
-          const float a = __shfl_sync(kFull, agg[hh], kk[u]);
-          float d = 0.f;
-#pragma unroll
-          for (int cv = 0; cv < CV; ++cv) {
-            acc[hh][cv] = fma4(a, g[u][cv], acc[hh][cv]);
-            d += dot4(hj[hh][cv], g[u][cv]);
-          }
-          d = warp_sum(d) * invH;  // d(out)/d(alpha'_ij) for this head
-          if (lane == kk[u]) my_de[hh] = alpha[hh] * (d * ks[hh] - tt[hh]) * gsc[hh];
-        }
-      }
-    }
-    if (valid) {
+    int i_next = 0;
+
+    for (int base = beg; base < end; base += 32) {
+      const int q = base + lane;
+      const bool valid = q < end;
+      int i = (base == beg) ? i_first : (valid ? __ldg(row + q) : 0);
+      const int i0 = __shfl_sync(kFull, i, 0);
+      if (!valid) i = i0;
+      const int cnt = min(32, end - base);
+      GBuf bufA[U], bufB[U];
+      load_group(bufA, i, 0);                      // dout gathers start before the per-edge scalar math
+      if (U < cnt) load_group(bufB, i, U);
+
+      float alpha[H], agg[H], gsc[H], tt[H], ks[H], my_de[H];
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) {
-        de[(size_t)q * H + hh] = my_de[hh];
-        dss[hh] += my_de[hh];
+        alpha[hh] = agg[hh] = gsc[hh] = tt[hh] = my_de[hh] = 0.f;
+        ks[hh] = 1.f;
+        if (valid) {
+          const float4 st = __ldg(nodestat + (size_t)i * H + hh);  // (s_dst, m, 1/D, t)
+          const float z0 = ssj[hh] + st.x;
+          const float zl = z0 > 0.f ? z0 : z0 * neg_slope;
+          float zc = zl, pass = 1.f;
+          if (POLICY == kCustom) {
+            zc = fminf(fmaxf(zl, -10.f), 10.f);
+            pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;  // clamp passes gradient only inside [-10,10]
+          }
+          alpha[hh] = expf(zc - st.y) * st.z;
+          gsc[hh] = (z0 > 0.f ? 1.f : neg_slope) * pass;
+          tt[hh] = st.w;
+          if (DROPOUT) ks[hh] = dropout_scale(seed, (uint32_t)__ldg(perm_csc + q), hh, p_drop, inv_keep);
+          agg[hh] = alpha[hh] * ks[hh] * invH;
+        }
+      }
+      if (base == beg && has_next) i_next = (dn.y + lane < dn.z) ? __ldg(row + dn.y + lane) : 0;
+
+      auto consume = [&](GBuf(&buf)[U], int k) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int kk = (k + u) & 31;
+#pragma unroll
+          for (int hh = 0; hh < H; ++hh) {
+            const float a = __shfl_sync(kFull, agg[hh], kk);
+            float dsum = 0.f;
+#pragma unroll
+            for (int cv = 0; cv < CV; ++cv) {
+              acc[hh][cv] = fma4(a, buf[u].g[cv], acc[hh][cv]);
+              dsum += dot4(hj[hh][cv], buf[u].g[cv]);
+            }
+            dsum = warp_sum(dsum) * invH;  // d(out)/d(alpha'_ij) for this head
+            if (lane == kk && k + u < cnt) my_de[hh] = alpha[hh] * (dsum * ks[hh] - tt[hh]) * gsc[hh];
+          }
+        }
+      };
+      for (int k = 0; k < cnt; k += 2 * U) {
+        consume(bufA, k);
+        if (k + 2 * U < cnt) load_group(bufA, i, k + 2 * U);
+        if (k + U < cnt) {
+          consume(bufB, k + U);
+          if (k + 3 * U < cnt) load_group(bufB, i, k + 3 * U);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+          de[(size_t)q * H + hh] = my_de[hh];
+          dss[hh] += my_de[hh];
+        }
       }
     }
-  }
+    if (beg == end && has_next) i_next = (dn.y + lane < dn.z) ? __ldg(row + dn.y + lane) : 0;
 #pragma unroll
-  for (int hh = 0; hh < H; ++hh) {
-    const float t = warp_sum(dss[hh]);
-    if (lane == 0) ds_src[(size_t)r * ld_ds + hh] = t;
+    for (int hh = 0; hh < H; ++hh) {
+      const float t = warp_sum(dss[hh]);
+      if (lane == 0) ds_src[(size_t)r * ld_ds + hh] = t;
 #pragma unroll
-    for (int cv = 0; cv < CV; ++cv)
-      *reinterpret_cast<float4*>(dh + (size_t)r * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
+      for (int cv = 0; cv < CV; ++cv)
+        *reinterpret_cast<float4*>(dh + (size_t)r * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
+    }
+    if (!has_next) break;
+    idx = idx_next;
+    d = dn;
+    i_first = i_next;
   }
 }
 
@@ -367,11 +522,54 @@ static int check_shape(int heads, int channels) {
 
 using namespace b200gat;
 
-extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* rowptr, const int32_t* col,
+template <typename K>
+static int persistent_grid(K kernel, int threads, int64_t n_rows, int* grid) {
+  int per_sm = 0;
+  B200GAT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = (n_rows + threads / 32 - 1) / (threads / 32);
+  const int64_t cap = (int64_t)kNumSMs * per_sm;   // one full wave of resident CTAs
+  *grid = (int)(want < cap ? want : cap);
+  return kOk;
+}
+
+extern "C" int b200gat_schedule_workspace_bytes(int64_t n_rows, size_t* bytes) {
+  B200GAT_CHECK_ARG(bytes && n_rows >= 0, "bad args");
+  const size_t e = ((size_t)(n_rows > 0 ? n_rows : 1) * 4 + 255) / 256 * 256;
+  *bytes = 3 * e + sort_workspace_bytes(n_rows) + 256;
+  return kOk;
+}
+
+// sched[k] = (row, ptr[row], ptr[row+1], 0) for the k-th row in descending-degree order (ties: descending row id).
+// degree_bound: any value > the largest row degree (e.g. number of edges + 1); it only sets the radix pass count.
+extern "C" int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_t degree_bound, int32_t* sched,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(ptr && (sched || n_rows == 0) && workspace && degree_bound > 0, "bad arguments");
+  size_t need;
+  b200gat_schedule_workspace_bytes(n_rows, &need);
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  if (n_rows == 0) return kOk;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)workspace;
+  const size_t e = ((size_t)n_rows * 4 + 255) / 256 * 256;
+  int32_t* keys = (int32_t*)p;
+  int32_t* sorted = (int32_t*)(p + e);
+  int32_t* asc_rows = (int32_t*)(p + 2 * e);
+  void* sort_ws = p + 3 * e;
+  const int grid = min(ceil_div(n_rows, 256), kNumSMs * 8);
+  count_launch(), degree_keys_kernel<<<grid, 256, 0, st>>>(ptr, n_rows, keys);
+  int rc = sort_pairs_stable(keys, n_rows, degree_bound, sorted, asc_rows, sort_ws, st);
+  if (rc) return rc;
+  count_launch(), build_schedule_kernel<<<grid, 256, 0, st>>>(ptr, asc_rows, n_rows, (int4*)sched);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, const int32_t* col,
                                     const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels,
                                     int policy, float negative_slope, const float* bias, float* out, float* out_heads,
                                     float* rowstat, float p_drop, uint64_t seed, void* stream) {
-  B200GAT_CHECK_ARG(h && s && rowptr && out, "null pointer");
+  B200GAT_CHECK_ARG(h && s && sched && out, "null pointer");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
   B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
   B200GAT_CHECK_ARG(p_drop == 0.f || perm, "dropout needs perm");
@@ -379,14 +577,17 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
   if (rc) return rc;
   if (n_rows == 0) return kOk;
   const int cv = channels / 128;
-  const int threads = 128;
-  const int grid = ceil_div(n_rows * 32, threads);
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = p_drop > 0.f;
-#define LAUNCH_FWD(P, D)                                                                                          \
-  count_launch(), edge_fwd_kernel<P, kH, kCV, D><<<grid, threads, 0, st>>>(h, s, rowptr, col, perm, (int)n_rows, (int)row_offset, \
-                                                           negative_slope, bias, out, out_heads, (float2*)rowstat,  \
-                                                           p_drop, seed)
+  int grid = 0;
+#define LAUNCH_FWD(P, D)                                                                                                \
+  do {                                                                                                                  \
+    rc = persistent_grid(edge_fwd_kernel<P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                                  \
+    if (rc) return rc;                                                                                                  \
+    count_launch(), edge_fwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                      \
+        h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,        \
+        (float2*)rowstat, p_drop, seed);                                                                                \
+  } while (0)
   B200GAT_DISPATCH_HC(heads, cv, {
     if (policy == kCustom) { if (drop) LAUNCH_FWD(kCustom, true); else LAUNCH_FWD(kCustom, false); }
     else { if (drop) LAUNCH_FWD(kPyG, true); else LAUNCH_FWD(kPyG, false); }
@@ -396,30 +597,39 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
   return kOk;
 }
 
+// dbias (nullable): column sums of dout in a fixed order; workspace >= 8*148*channels floats when dbias != NULL
 extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
                                      const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
-                                     float* nodestat, void* stream) {
+                                     float* nodestat, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
   B200GAT_CHECK_ARG(dout && out_heads && s && rowstat && nodestat, "null pointer");
   int rc = check_shape(heads, channels);
   if (rc) return rc;
-  if (n_rows == 0) return kOk;
-  const int cv = channels / 128;
-  const int grid = ceil_div(n_rows * 32, 128);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows == 0) {
+    if (dbias) B200GAT_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * channels, st));
+    return kOk;
+  }
+  const int cv = channels / 128;
+  const int64_t want_blocks = (n_rows + 7) / 8;
+  const int grid = (int)(want_blocks < (int64_t)kNumSMs * 8 ? want_blocks : (int64_t)kNumSMs * 8);
+  B200GAT_CHECK_ARG(!dbias || (workspace && workspace_bytes >= (size_t)grid * channels * sizeof(float)),
+                    "node_prep workspace too small");
   B200GAT_DISPATCH_HC(heads, cv, {
-    count_launch(), node_prep_kernel<kH, kCV><<<grid, 128, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
-                                                   (int)row_offset, (float4*)nodestat);
+    count_launch(), node_prep_kernel<kH, kCV><<<grid, 256, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
+                                                                   (int)row_offset, (float4*)nodestat,
+                                                                   dbias ? (float*)workspace : nullptr);
   })
+  if (dbias) count_launch(), colsum_finish_kernel<<<ceil_div(channels, 128), 128, 0, st>>>((const float*)workspace, grid, channels, dbias);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
 
 extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
-                                    const int32_t* colptr, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
+                                    const int32_t* sched, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
                                     int64_t row_offset, int heads, int channels, int policy, float negative_slope,
                                     float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
                                     void* stream) {
-  B200GAT_CHECK_ARG(h && s && dout && nodestat && colptr && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
+  B200GAT_CHECK_ARG(h && s && dout && nodestat && sched && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
   B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
   B200GAT_CHECK_ARG(p_drop == 0.f || perm_csc, "dropout needs perm_csc");
@@ -427,13 +637,17 @@ extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float*
   if (rc) return rc;
   if (n_rows == 0) return kOk;
   const int cv = channels / 128;
-  const int grid = ceil_div(n_rows * 32, 128);
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = p_drop > 0.f;
-#define LAUNCH_BWD(P, D)                                                                                             \
-  count_launch(), edge_bwd_kernel<P, kH, kCV, D><<<grid, 128, 0, st>>>(h, s, dout, (const float4*)nodestat, colptr, row, perm_csc,  \
-                                                       (int)n_rows, (int)row_offset, negative_slope, dh, de, ds_src, \
-                                                       ld_ds, p_drop, seed)
+  int grid = 0;
+#define LAUNCH_BWD(P, D)                                                                                               \
+  do {                                                                                                                 \
+    rc = persistent_grid(edge_bwd_kernel<P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                                 \
+    if (rc) return rc;                                                                                                 \
+    count_launch(), edge_bwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                     \
+        h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,          \
+        negative_slope, dh, de, ds_src, ld_ds, p_drop, seed);                                                          \
+  } while (0)
   B200GAT_DISPATCH_HC(heads, cv, {
     if (policy == kCustom) { if (drop) LAUNCH_BWD(kCustom, true); else LAUNCH_BWD(kCustom, false); }
     else { if (drop) LAUNCH_BWD(kPyG, true); else LAUNCH_BWD(kPyG, false); }

@@ -48,7 +48,7 @@ class GATLayerFunction(torch.autograd.Function):
             rowstat = _empty((n, heads, 2), x) if need_grad else None
             out_heads = _empty((n, heads, channels), x) if (need_grad and heads > 1) else None
             b = None if bias is None else _lib._f32(bias, "bias").contiguous()
-            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(graph.sched_fwd), _lib.ptr(graph.col),
                       _lib.ptr(graph.perm), n, 0, heads, channels, policy, negative_slope, _lib.ptr(b), _lib.ptr(out),
                       _lib.ptr(out_heads), _lib.ptr(rowstat), p_drop, seed, st)
         if need_grad:
@@ -68,19 +68,21 @@ class GATLayerFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             st = _lib.stream()
             nodestat = _empty((n, heads, 4), x)
+            ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            dbias = torch.empty_like(b) if (b is not None and ctx.needs_input_grad[4]) else None
             _lib.call("b200gat_node_prep_f32", _lib.ptr(dout), _lib.ptr(out_h), _lib.ptr(b if heads == 1 else None),
-                      _lib.ptr(s), _lib.ptr(rowstat), n, 0, heads, channels, _lib.ptr(nodestat), st)
+                      _lib.ptr(s), _lib.ptr(rowstat), n, 0, heads, channels, _lib.ptr(nodestat), _lib.ptr(dbias),
+                      _lib.ptr(ws), ws_bytes, st)
             dh = _empty((n, heads * channels), x)
             de = _empty((max(g.n_edges, 1), heads), x)
             ds = _empty((n, 2 * heads), x)
             _lib.call("b200gat_edge_bwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(dout), _lib.ptr(nodestat),
-                      _lib.ptr(g.colptr), _lib.ptr(g.row), _lib.ptr(g.perm_csc), n, 0, heads, channels, policy,
+                      _lib.ptr(g.sched_bwd), _lib.ptr(g.row), _lib.ptr(g.perm_csc), n, 0, heads, channels, policy,
                       negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
             _lib.call("b200gat_ds_dst_f32", _lib.ptr(de), _lib.ptr(g.rowptr), _lib.ptr(g.csr2csc), n, heads,
                       _lib.ptr(ds, heads), 2 * heads, st)
             del de
-            ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             dx = _empty((n, f_in), x) if ctx.needs_input_grad[0] else None
             dw = torch.empty_like(weight)
             da_s = torch.empty_like(a_s)
@@ -88,10 +90,6 @@ class GATLayerFunction(torch.autograd.Function):
             _lib.call("b200gat_project_bwd_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(dh),
                       _lib.ptr(ds), n, f_in, heads, channels, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(da_s), _lib.ptr(da_d),
                       _lib.ptr(ws), ws_bytes, st)
-            dbias = None
-            if b is not None and ctx.needs_input_grad[4]:
-                dbias = torch.empty_like(b)
-                _lib.call("b200gat_colsum_f32", _lib.ptr(dout), n, channels, _lib.ptr(dbias), _lib.ptr(ws), ws_bytes, st)
         sa, sd = ctx.att_shape
         return dx, dw, da_s.view(sa), da_d.view(sd), dbias, None, None, None, None, None, None, None
 

@@ -129,6 +129,9 @@ class ShardedGAT:
         self.perm_fwd = self.plan.fwd_sel[self.g_fwd.perm.long()].to(torch.int32).contiguous()
         self.perm_bwd = self.plan.bwd_sel[self.g_bwd.perm_csc.long()].to(torch.int32).contiguous()
         self.e_total = int(ei.shape[1])
+        # local row schedules (rows are block-local ids; beg/end index the sub-graph's col / row arrays)
+        self.sched_fwd = _lib.build_schedule(self.g_fwd.rowptr, lo, self.n_loc, self.g_fwd.n_edges + 1)
+        self.sched_bwd = _lib.build_schedule(self.g_bwd.colptr, lo, self.n_loc, self.g_bwd.n_edges + 1)
         del ei
 
         torch.manual_seed(seed)
@@ -187,7 +190,7 @@ class ShardedGAT:
             rowstat = self._empty(self.n_loc, H, 2)
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
-            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(self.g_fwd.rowptr, self.plan.lo),
+            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(self.sched_fwd),
                      lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.n_loc, self.plan.lo, H, C, self.policy, 0.2,
                      lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
             self.saved.append((x, h_full, s_full, rowstat, out if H == 1 else out_heads, p, seed))
@@ -216,15 +219,19 @@ class ShardedGAT:
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
             f_in = x.shape[1]
             nodestat = self._empty(self.n_loc, H, 4)
+            dwb = lib.dense_workspace_bytes(H, C, f_in)
+            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
+            db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
-                     lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), st)
+                     lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
+                     lib.ptr(dws), dwb, st)
             dout_full = all_gather_rows(dout, bounds)
             nodestat_full = all_gather_rows(nodestat, bounds)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
             lib.call("b200gat_edge_bwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(dout_full), lib.ptr(nodestat_full),
-                     lib.ptr(self.g_bwd.colptr, self.plan.lo), lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.n_loc,
+                     lib.ptr(self.sched_bwd), lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.n_loc,
                      self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh), lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
             ds_dst = self._empty(self.n, H)                                  # partial sums over this rank's edges
             lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n, H,
@@ -233,17 +240,13 @@ class ShardedGAT:
                 dist.all_reduce(ds_dst)
             ds[:, H:] = ds_dst[self.plan.lo:self.plan.hi]
             del de, dout_full, nodestat_full
-            dwb = lib.dense_workspace_bytes(H, C, f_in)
-            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             dx = self._empty(self.n_loc, f_in)
             dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
             lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      lib.ptr(dh), lib.ptr(ds), self.n_loc, f_in, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
                      lib.ptr(dws), dwb, st)
             grads[self.W[l]], grads[self.a_src[l]], grads[self.a_dst[l]] = dW, da_s, da_d
-            if self.bias[l] is not None:
-                db = torch.empty_like(self.bias[l])
-                lib.call("b200gat_colsum_f32", lib.ptr(dout), self.n_loc, C, lib.ptr(db), lib.ptr(dws), dwb, st)
+            if db is not None:
                 grads[self.bias[l]] = db
             dout = dx
         # input features: user rows take their gradient rows directly, item_proj through torch autograd

@@ -64,7 +64,7 @@ int b200gat_build_graph(const int64_t* edge_index, int64_t n_edges, int64_t n_no
 /* Row schedule for the edge kernels: sched[k] = (row, ptr[row], ptr[row+1], 0) (int32 x4) for the k-th row of
  * `ptr` (a CSR rowptr or CSC colptr slice, n_rows+1 entries) in descending-degree order.  The persistent warps
  * of (3)/(4) walk it round-robin: hubs start first and every warp gets the same degree mix.
- * degree_bound: any value > the largest degree (e.g. n_edges+1). */
+ * degree_bound: any value > the largest degree (e.g. n_edges+1); <= 0 keeps the natural row order. */
 int b200gat_schedule_workspace_bytes(int64_t n_rows, size_t* bytes /*host*/);
 int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_t degree_bound, int32_t* sched, void* workspace,
                            size_t workspace_bytes, void* stream);

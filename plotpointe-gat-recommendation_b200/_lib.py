@@ -137,6 +137,8 @@ def schedule_workspace_bytes(n_rows: int) -> int:
 
 def build_schedule(ptr_tensor, offset: int, n_rows: int, degree_bound: int):
     """Descending-degree row schedule (int32 [n_rows, 4]) of ptr_tensor[offset : offset+n_rows+1]."""
+    if os.environ.get("B200GAT_SCHED", "degree") == "natural":
+        degree_bound = 0
     sched = torch.empty((max(n_rows, 1), 4), dtype=torch.int32, device=ptr_tensor.device)
     wsb = schedule_workspace_bytes(n_rows)
     ws = torch.empty(wsb, dtype=torch.uint8, device=ptr_tensor.device)

@@ -71,7 +71,7 @@ __global__ void degree_keys_kernel(const int32_t* __restrict__ ptr, int64_t n_ro
 __global__ void build_schedule_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ asc_rows, int64_t n_rows,
                                       int4* __restrict__ sched) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_rows; k += (int64_t)gridDim.x * blockDim.x) {
-    const int r = asc_rows[n_rows - 1 - k];   // descending degree
+    const int r = asc_rows ? asc_rows[n_rows - 1 - k] : (int)k;   // descending degree (or natural order)
     sched[k] = make_int4(r, ptr[r], ptr[r + 1], 0);
   }
 }
@@ -87,7 +87,7 @@ struct RowBuf {
 };
 
 template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ col,
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
@@ -98,21 +98,10 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
   constexpr int HC = H * C;
   constexpr int U = (H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : 4);   // rows per load group; two groups in flight
   const int lane = threadIdx.x & 31;
-  const int n_warps = gridDim.x * (kEdgeThreads / 32);
-  int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
   if (idx >= n_rows) return;
   const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
-
-  // metadata of the current row: descriptor + first chunk of (col, s_src), prefetched one row ahead
-  int4 d = __ldg(sched + idx);
-  int c_first = 0;
-  float ss_first[H];
-  {
-    const bool v = d.y + lane < d.z;
-    c_first = v ? __ldg(col + d.y + lane) : 0;
-#pragma unroll
-    for (int hh = 0; hh < H; ++hh) ss_first[hh] = v ? __ldg(s + (size_t)c_first * (2 * H) + hh) : 0.f;
-  }
+  const int4 d = __ldg(sched + idx);
 
   auto load_group = [&](RowBuf<H, CV>(&buf)[U], int c, int k) {
 #pragma unroll
@@ -126,12 +115,8 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
     }
   };
 
-  while (true) {
+  {
     const int r = d.x, beg = d.y, end = d.z;
-    const int idx_next = idx + n_warps;
-    const bool has_next = idx_next < n_rows;
-    int4 dn = make_int4(0, 0, 0, 0);
-    if (has_next) dn = __ldg(sched + idx_next);          // in flight while this row is processed
 
     float sd[H], m[H], l[H];
     float4 acc[H][CV];
@@ -143,25 +128,13 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
 #pragma unroll
       for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    int c_next = 0;
-    float ss_next[H];
-#pragma unroll
-    for (int hh = 0; hh < H; ++hh) ss_next[hh] = 0.f;
-
     for (int base = beg; base < end; base += 32) {
       const int e = base + lane;
       const bool valid = e < end;
-      int c;
+      int c = valid ? __ldg(col + e) : 0;
       float sv[H];
-      if (base == beg) {
-        c = c_first;
 #pragma unroll
-        for (int hh = 0; hh < H; ++hh) sv[hh] = ss_first[hh];
-      } else {
-        c = valid ? __ldg(col + e) : 0;
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) sv[hh] = valid ? __ldg(s + (size_t)c * (2 * H) + hh) : 0.f;
-      }
+      for (int hh = 0; hh < H; ++hh) sv[hh] = valid ? __ldg(s + (size_t)c * (2 * H) + hh) : 0.f;
       // zero-weight tail lanes re-read lane 0's row so they add no new cache lines
       const int c0 = __shfl_sync(kFull, c, 0);
       if (!valid) c = c0;
@@ -193,13 +166,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
         l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
         if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)__ldg(perm + e), hh, p_drop, inv_keep);
       }
-      if (base == beg && has_next) {                       // next row's first chunk (its descriptor has landed by now)
-        const bool v = dn.y + lane < dn.z;
-        c_next = v ? __ldg(col + dn.y + lane) : 0;
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) ss_next[hh] = v ? __ldg(s + (size_t)c_next * (2 * H) + hh) : 0.f;
-      }
-
       auto consume = [&](RowBuf<H, CV>(&buf)[U], int k) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -219,13 +185,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
         }
       }
     }
-    if (beg == end && has_next) {                          // empty row: the prefetch above did not run
-      const bool v = dn.y + lane < dn.z;
-      c_next = v ? __ldg(col + dn.y + lane) : 0;
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh) ss_next[hh] = v ? __ldg(s + (size_t)c_next * (2 * H) + hh) : 0.f;
-    }
-
     float inv[H];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
@@ -250,12 +209,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_fwd_kernel(const float* __r
       }
       *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
     }
-    if (!has_next) break;
-    idx = idx_next;
-    d = dn;
-    c_first = c_next;
-#pragma unroll
-    for (int hh = 0; hh < H; ++hh) ss_first[hh] = ss_next[hh];
   }
 }
 
@@ -336,7 +289,7 @@ __global__ void colsum_finish_kernel(const float* __restrict__ part, int n_parts
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
 template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
                                                                 const float* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
                                                                 const int4* __restrict__ sched,
@@ -349,14 +302,11 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
   constexpr int HC = H * C;
   constexpr int U = CV >= 2 ? 2 : 4;   // dout rows per load group; two groups in flight
   const int lane = threadIdx.x & 31;
-  const int n_warps = gridDim.x * (kEdgeThreads / 32);
-  int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
   if (idx >= n_rows) return;
   const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
   constexpr float invH = 1.f / H;
-
-  int4 d = __ldg(sched + idx);
-  int i_first = (d.y + lane < d.z) ? __ldg(row + d.y + lane) : 0;
+  const int4 d = __ldg(sched + idx);
 
   struct GBuf { float4 g[CV]; };
   auto load_group = [&](GBuf(&buf)[U], int i, int k) {
@@ -368,12 +318,8 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
     }
   };
 
-  while (true) {
+  {
     const int r = d.x, beg = d.y, end = d.z;
-    const int idx_next = idx + n_warps;
-    const bool has_next = idx_next < n_rows;
-    int4 dn = make_int4(0, 0, 0, 0);
-    if (has_next) dn = __ldg(sched + idx_next);
     const size_t j = (size_t)row_offset + r;
 
     float4 hj[H][CV], acc[H][CV];
@@ -388,12 +334,10 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
         acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    int i_next = 0;
-
     for (int base = beg; base < end; base += 32) {
       const int q = base + lane;
       const bool valid = q < end;
-      int i = (base == beg) ? i_first : (valid ? __ldg(row + q) : 0);
+      int i = valid ? __ldg(row + q) : 0;
       const int i0 = __shfl_sync(kFull, i, 0);
       if (!valid) i = i0;
       const int cnt = min(32, end - base);
@@ -422,8 +366,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
           agg[hh] = alpha[hh] * ks[hh] * invH;
         }
       }
-      if (base == beg && has_next) i_next = (dn.y + lane < dn.z) ? __ldg(row + dn.y + lane) : 0;
-
       auto consume = [&](GBuf(&buf)[U], int k) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -458,7 +400,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
         }
       }
     }
-    if (beg == end && has_next) i_next = (dn.y + lane < dn.z) ? __ldg(row + dn.y + lane) : 0;
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
       const float t = warp_sum(dss[hh]);
@@ -467,10 +408,6 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bwd_kernel(const float* __r
       for (int cv = 0; cv < CV; ++cv)
         *reinterpret_cast<float4*>(dh + (size_t)r * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
     }
-    if (!has_next) break;
-    idx = idx_next;
-    d = dn;
-    i_first = i_next;
   }
 }
 
@@ -522,14 +459,10 @@ static int check_shape(int heads, int channels) {
 
 using namespace b200gat;
 
+// one warp per scheduled row; the hardware block scheduler hands out blocks in schedule order (longest rows first)
 template <typename K>
-static int persistent_grid(K kernel, int threads, int64_t n_rows, int* grid) {
-  int per_sm = 0;
-  B200GAT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-  if (per_sm < 1) per_sm = 1;
-  const int64_t want = (n_rows + threads / 32 - 1) / (threads / 32);
-  const int64_t cap = (int64_t)kNumSMs * per_sm;   // one full wave of resident CTAs
-  *grid = (int)(want < cap ? want : cap);
+static int persistent_grid(K, int threads, int64_t n_rows, int* grid) {
+  *grid = (int)((n_rows + threads / 32 - 1) / (threads / 32));
   return kOk;
 }
 
@@ -544,7 +477,7 @@ extern "C" int b200gat_schedule_workspace_bytes(int64_t n_rows, size_t* bytes) {
 // degree_bound: any value > the largest row degree (e.g. number of edges + 1); it only sets the radix pass count.
 extern "C" int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_t degree_bound, int32_t* sched,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-  B200GAT_CHECK_ARG(ptr && (sched || n_rows == 0) && workspace && degree_bound > 0, "bad arguments");
+  B200GAT_CHECK_ARG(ptr && (sched || n_rows == 0) && workspace, "bad arguments");
   size_t need;
   b200gat_schedule_workspace_bytes(n_rows, &need);
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
@@ -557,6 +490,11 @@ extern "C" int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_
   int32_t* asc_rows = (int32_t*)(p + 2 * e);
   void* sort_ws = p + 3 * e;
   const int grid = min(ceil_div(n_rows, 256), kNumSMs * 8);
+  if (degree_bound <= 0) {  // natural row order
+    count_launch(), build_schedule_kernel<<<grid, 256, 0, st>>>(ptr, nullptr, n_rows, (int4*)sched);
+    B200GAT_LAUNCH_CHECK();
+    return kOk;
+  }
   count_launch(), degree_keys_kernel<<<grid, 256, 0, st>>>(ptr, n_rows, keys);
   int rc = sort_pairs_stable(keys, n_rows, degree_bound, sorted, asc_rows, sort_ws, st);
   if (rc) return rc;

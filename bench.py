@@ -115,7 +115,7 @@ def run_ours(args):
     e = int(ei.shape[1])
     torch.manual_seed(42)
     model = b200gat.PyGGAT(nu, ni, 128, HIDDEN, LAYERS, heads=HEADS, attn_dropout=0.1).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
     eid, fd = ei.to(dev), feats.to(dev)
     u, i, j = synth.make_triples(nu, ni, S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))

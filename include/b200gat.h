@@ -95,6 +95,14 @@ int b200gat_project_bwd_f32(const float* x, const float* W, const float* a_src, 
                             const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx,
                             float* dW, float* da_src, float* da_dst, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* Item-feature projection of the node-feature assembly (item_proj, train_gat_custom.py:100,105-109):
+ * y[n, 0:out_features] (row pitch ldy) = x W^T + bias, so the result can be written straight into the tail rows of the
+ * [N, C] node-feature buffer (no torch.cat copy); backward: dW = dy^T x, dbias = column sums (x needs no gradient). */
+int b200gat_linear_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
+                       int out_features, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+int b200gat_linear_bwd_f32(const float* x, const float* dy, int64_t ldy, int64_t n_rows, int in_features,
+                           int out_features, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                           void* stream);
 /* out[c] = sum_n a[n, c] in a fixed order (GATConv bias gradient). workspace >= 296*channels floats. */
 int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, float* out, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -160,11 +160,25 @@ __global__ void att_grad_kernel(const float* __restrict__ W, const float* __rest
 // column sums of a [n, C] matrix with a fixed reduction tree: slabs of rows -> partial[slab, C] -> out[C]
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ a, int64_t n, int C, int64_t rows_per_slab,
                                                              float* __restrict__ part) {
+  // 8 warps stride over the slab's rows, lanes over 128-bit column chunks; fixed row -> warp map, fixed combine order
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = blockIdx.x * rows_per_slab, r1 = min(n, r0 + rows_per_slab);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t r = r0; r < r1; ++r) acc += a[r * C + c];
-    part[(int64_t)blockIdx.x * C + c] = acc;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const float4 v = ld_stream4(a + r * C + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      float4 t = red[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
+      *reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * C + c) = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -181,6 +195,9 @@ int tc_project_fwd(const float* x, const float* W, const float* a_src, const flo
                    float* h, float* s, void* workspace, cudaStream_t st);
 int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
                    int64_t n_rows, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st);
+int tc_linear_fwd(const float* x, const float* W, const float* bias, int64_t n_rows, float* out, int64_t ldo, void* workspace,
+                  cudaStream_t st);
+int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, void* workspace, cudaStream_t st);
 }  // namespace b200gat
 
 static size_t simt_workspace_bytes(int heads, int channels, int in_features) {
@@ -258,6 +275,58 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   if (rc) return rc;
   count_launch(), reduce_slabs_kernel<<<ceil_div((int64_t)H2 * F, 256), 256, 0, st>>>(part_v, n_slabs, (int64_t)H2 * F, (int64_t)H2 * F, v);
   count_launch(), att_grad_kernel<<<ceil_div((int64_t)HC * 32, 128), 128, 0, st>>>(W, v, heads, channels, F, da_src, da_dst);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// y[n, ldy] = x W^T + bias   (CustomGAT.item_proj, scripts/train_gat_custom.py:100,107; writes straight into the tail of the
+// [N, C] node-feature buffer, which removes the torch.cat copy of :109)
+extern "C" int b200gat_linear_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
+                                  int out_features, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  B200GAT_CHECK_ARG(x && W && y && ldy >= out_features, "null pointer / bad ld");
+  if (n_rows == 0) return kOk;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_supported(in_features, 1, out_features) && ldy % 4 == 0) {
+    B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(1), "workspace too small for the tensor-core path");
+    return tc_linear_fwd(x, W, bias, n_rows, y, ldy, workspace, st);
+  }
+  return launch_sgemm(x, in_features, 1, W, 1, in_features, y, ldy, (int)n_rows, out_features, in_features, 1, in_features, 0,
+                      bias, st);
+}
+
+// dW = dy^T x, dbias = column sums of dy   (backward of the above; x needs no gradient: item features are inputs)
+extern "C" int b200gat_linear_bwd_f32(const float* x, const float* dy, int64_t ldy, int64_t n_rows, int in_features,
+                                      int out_features, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  B200GAT_CHECK_ARG(x && dy && dW && workspace, "null pointer");
+  size_t need;
+  b200gat_dense_workspace_bytes(1, out_features, in_features, &need);
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows == 0) {
+    B200GAT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * out_features * in_features, st));
+    if (dbias) B200GAT_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * out_features, st));
+    return kOk;
+  }
+  int rc;
+  if (tc_supported(in_features, 1, out_features) && ldy == out_features) {
+    rc = tc_linear_dw(x, dy, n_rows, dW, workspace, st);
+  } else {
+    const int64_t k_slab = (n_rows + kSlabs - 1) / kSlabs;
+    const int n_slabs = (int)((n_rows + k_slab - 1) / k_slab);
+    float* part = (float*)workspace;
+    rc = launch_sgemm(dy, 1, ldy, x, in_features, 1, part, in_features, out_features, in_features, n_rows, n_slabs, k_slab,
+                      (int64_t)out_features * in_features, nullptr, st);
+    if (rc) return rc;
+    count_launch(), reduce_slabs_kernel<<<ceil_div((int64_t)out_features * in_features, 256), 256, 0, st>>>(
+        part, n_slabs, (int64_t)out_features * in_features, (int64_t)out_features * in_features, dW);
+  }
+  if (rc) return rc;
+  if (dbias) {
+    B200GAT_CHECK_ARG(ldy == out_features, "dbias needs contiguous dy");
+    return b200gat_colsum_f32(dy, n_rows, out_features, dbias, workspace, workspace_bytes, stream);
+  }
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

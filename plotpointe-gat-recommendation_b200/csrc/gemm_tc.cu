@@ -201,8 +201,12 @@ struct FwdParams {
   int heads;
 };
 
-template <bool DX>
+// FLAVOR 0: logits epilogue (projection forward); 1: A corrected on the fly (dx); 2: bias added in the epilogue (plain Linear)
+template <int FLAVOR>
 __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
+  constexpr bool DX = FLAVOR == 1;
+  constexpr bool LOGITS = FLAVOR == 0;
+  constexpr bool BIAS = FLAVOR == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -232,12 +236,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
     fence_barrier_init();
   }
   if (warp == kFwdProducerWarps + kFwdEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
-  if (!DX) {
+  if (LOGITS) {
     for (int i = threadIdx.x; i < 2 * kTileN; i += kFwdThreads)
       att[i] = i < kTileN ? p.att_src[head * kTileN + i] : p.att_dst[head * kTileN + i - kTileN];
-  } else {
+  } else if (DX) {
     for (int i = threadIdx.x; i < 2 * kTileN; i += kFwdThreads)
       att[i] = i < kTileN ? p.att_src[i] : p.att_dst[i - kTileN];
+  } else {
+    for (int i = threadIdx.x; i < kTileN; i += kFwdThreads) att[i] = p.att_src ? p.att_src[head * kTileN + i] : 0.f;  // bias
   }
   tc_fence_before();
   __syncthreads();
@@ -340,12 +346,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
       for (int c = 0; c < kTileN / 32; ++c) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + c * 32, v);
-        if (!DX) {
+        if (LOGITS) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             ps = fmaf(v[j], att[c * 32 + j], ps);
             pd = fmaf(v[j], att[kTileN + c * 32 + j], pd);
           }
+        }
+        if (BIAS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += att[c * 32 + j];
         }
         // transpose through smem: lane = row writes its 32 columns, then 8 lanes store one 128 B row segment
 #pragma unroll
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
-      if (!DX) {
+      if (LOGITS) {
         const int64_t row = row0 + lane;
         if (row < p.n_rows) {
           p.s[row * (2 * p.heads) + head] = ps;
@@ -447,7 +457,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
     fence_barrier_init();
   }
   if (warp == kDwProducerWarps + kDwEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
-  for (int i = threadIdx.x; i < 2 * kTileN; i += kDwThreads) att[i] = i < kTileN ? p.att_src[i] : p.att_dst[i - kTileN];
+  for (int i = threadIdx.x; i < 2 * kTileN; i += kDwThreads)
+    att[i] = p.ds ? (i < kTileN ? p.att_src[i] : p.att_dst[i - kTileN]) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -469,8 +480,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
         if (row < r_end) {
           g[i] = ld_stream4(p.dh + row * 128 + c4 * 4);
           xv[i] = ld_stream4(p.x + row * 128 + c4 * 4);
-          d0[i] = __ldg(p.ds + row * 2);
-          d1[i] = __ldg(p.ds + row * 2 + 1);
+          d0[i] = p.ds ? __ldg(p.ds + row * 2) : 0.f;
+          d1[i] = p.ds ? __ldg(p.ds + row * 2 + 1) : 0.f;
         } else {
           g[i] = xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           d0[i] = d1[i] = 0.f;
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
   __syncthreads();
   tc_fence_after();
   // side sums v[q, f]: fixed-order reduction over the 8 producer warps
-  if (threadIdx.x < 2 * kTileN) {
+  if (p.part_v && threadIdx.x < 2 * kTileN) {
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < kDwProducerWarps; ++w) a += vred[(w * 2 + threadIdx.x / kTileN) * kTileN + threadIdx.x % kTileN];
@@ -633,8 +644,9 @@ static int g_gemm_mode = B200GAT_GEMM_TF32X3;
 static int ensure_attrs() {
   static bool done = false;
   if (done) return kOk;
-  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
-  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
+  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
+  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
+  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDwSmem));
   done = true;
   return kOk;
@@ -666,7 +678,7 @@ int tc_project_fwd(const float* x, const float* W, const float* a_src, const flo
   p.att_src = a_src; p.att_dst = a_dst; p.s = s; p.ds = nullptr; p.heads = heads;
   const int64_t n_tiles = (n_rows + 127) / 128;
   dim3 grid((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), heads);
-  count_launch(), tc::proj_kernel<false><<<grid, tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
+  count_launch(), tc::proj_kernel<0><<<grid, tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -687,7 +699,7 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
     p.a = dh; p.lda = 128; p.b_images = image; p.out = dx; p.ldo = 128; p.n_rows = n_rows;
     p.att_src = a_src; p.att_dst = a_dst; p.s = nullptr; p.ds = ds; p.heads = 1;
     const int64_t n_tiles = (n_rows + 127) / 128;
-    count_launch(), tc::proj_kernel<true><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
+    count_launch(), tc::proj_kernel<1><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
   }
   tc::DwParams q{};
   q.dh = dh; q.ds = ds; q.x = x; q.att_src = a_src; q.att_dst = a_dst; q.n_rows = n_rows;
@@ -700,6 +712,40 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
   count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128, dW);
   count_launch(), tc::reduce_parts_kernel<<<1, 256, 0, st>>>(part_v, grid, 256, 256, v);
   count_launch(), tc::att_grad_tc_kernel<<<ceil_div(128 * 32, 128), 128, 0, st>>>(W, v, da_src, da_dst);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// out[n, ldo] (first 128 columns) = x[n,128] W[128,128]^T + bias
+int tc_linear_fwd(const float* x, const float* W, const float* bias, int64_t n_rows, float* out, int64_t ldo, void* workspace,
+                  cudaStream_t st) {
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  float* image = (float*)workspace;
+  count_launch(), tc::build_b_image_kernel<<<ceil_div(128 * 128 / 4, 256), 256, 0, st>>>(W, 128, 1, image);
+  tc::FwdParams p{};
+  p.a = x; p.lda = 128; p.b_images = image; p.out = out; p.ldo = ldo; p.n_rows = n_rows;
+  p.att_src = bias; p.att_dst = nullptr; p.s = nullptr; p.ds = nullptr; p.heads = 1;
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  count_launch(), tc::proj_kernel<2><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// dW[128,128] = dy^T x
+int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, void* workspace, cudaStream_t st) {
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  float* part_dw = (float*)workspace + tc::kBImageBytes / 4;
+  tc::DwParams q{};
+  q.dh = dy; q.ds = nullptr; q.x = x; q.att_src = nullptr; q.att_dst = nullptr; q.n_rows = n_rows;
+  int64_t per = (n_rows + kNumSMs - 1) / kNumSMs;
+  per = (per + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
+  q.rows_per_cta = per;
+  const int grid = (int)((n_rows + per - 1) / per);
+  q.part_dw = part_dw; q.part_v = nullptr;
+  count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
+  count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128, dW);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -94,6 +94,51 @@ class GATLayerFunction(torch.autograd.Function):
         return dx, dw, da_s.view(sa), da_d.view(sd), dbias, None, None, None, None, None, None, None
 
 
+class NodeFeaturesFunction(torch.autograd.Function):
+    """x0 = cat[user_emb.weight, item_proj(item_feats)] (CustomGAT.node_features, scripts/train_gat_custom.py:105-109)
+    without the concat copy: the projection writes straight into the tail rows of the [N, C] buffer."""
+
+    @staticmethod
+    def forward(ctx, user_w, proj_w, proj_b, item_feats):
+        if not item_feats.is_cuda:
+            raise RuntimeError("b200gat node_features: tensors must be CUDA tensors (there is no CPU fallback)")
+        nu, c = user_w.shape
+        ni, f = item_feats.shape
+        feats = _lib._f32(item_feats, "item_feats").contiguous()
+        w = _lib._f32(proj_w, "item_proj.weight").contiguous()
+        b = None if proj_b is None else _lib._f32(proj_b, "item_proj.bias").contiguous()
+        x0 = _empty((nu + ni, c), feats)
+        x0[:nu].copy_(user_w)
+        ws_bytes = _lib.dense_workspace_bytes(1, c, f)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.call("b200gat_linear_f32", _lib.ptr(feats), _lib.ptr(w), _lib.ptr(b), ni, f, c, _lib.ptr(x0, nu * c), c,
+                      _lib.ptr(ws), ws_bytes, _lib.stream())
+        ctx.save_for_backward(feats)
+        ctx.dims = (nu, ni, c, f, b is not None)
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        (feats,) = ctx.saved_tensors
+        nu, ni, c, f, has_bias = ctx.dims
+        dx0 = dx0.contiguous()
+        dw = torch.empty((c, f), dtype=torch.float32, device=feats.device)
+        db = torch.empty((c,), dtype=torch.float32, device=feats.device) if has_bias else None
+        ws_bytes = _lib.dense_workspace_bytes(1, c, f)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.call("b200gat_linear_bwd_f32", _lib.ptr(feats), _lib.ptr(dx0, nu * c), c, ni, f, c, _lib.ptr(dw), _lib.ptr(db),
+                      _lib.ptr(ws), ws_bytes, _lib.stream())
+        return dx0[:nu], dw, db, None
+
+
+def node_features(user_w, proj_w, proj_b, item_feats):
+    if item_feats.requires_grad:
+        raise NotImplementedError("b200gat node_features: item_feats is an input and must not require grad")
+    return NodeFeaturesFunction.apply(user_w, proj_w, proj_b, item_feats)
+
+
 def gat_layer(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, negative_slope=0.2, p_drop=0.0, seed=0):
     return GATLayerFunction.apply(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, float(negative_slope),
                                   float(p_drop), int(seed))

@@ -14,7 +14,7 @@ import math
 import torch
 
 from . import _lib
-from .functional import gat_layer
+from .functional import gat_layer, node_features
 from .graph import graph_for
 
 
@@ -126,7 +126,8 @@ class CustomGAT(torch.nn.Module):
         self.layers = torch.nn.ModuleList([SimpleGATLayer(hidden, hidden) for _ in range(layers)])
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
-        return torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0)
+        # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy
+        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats)
 
     def forward(self, item_feats: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         x = self.node_features(item_feats)
@@ -151,7 +152,8 @@ class PyGGAT(torch.nn.Module):
                                       concat=False))
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
-        return torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0)
+        # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy
+        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats)
 
     def forward(self, item_feats: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         x = self.node_features(item_feats)

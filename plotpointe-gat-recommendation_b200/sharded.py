@@ -153,7 +153,7 @@ class ShardedGAT:
             self.bias.append(None if kind == "custom" else P(lay.bias.detach().clone().to(self.dev)))
         del full
         self.replicated = list(self.item_proj.parameters()) + self.W + self.a_src + self.a_dst + [b for b in self.bias if b is not None]
-        self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay)
+        self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay, fused=True)
         self.step_no = 0
         self.seed = seed
         self.comm_ms: List[float] = []

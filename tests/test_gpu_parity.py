@@ -322,3 +322,22 @@ def test_full_size_forward_linearity_and_rowsum(dev):
         y1 = layer(torch.ones(n, c, device=dev), eid)
         assert torch.allclose(y1[deg > 0], torch.ones(1, device=dev), rtol=1e-5)
         assert torch.count_nonzero(y1[deg == 0]) == 0
+
+
+@pytest.mark.parametrize("nu,ni,f,c", [(50, 70, 128, 128), (0, 300, 128, 128), (33, 1, 128, 128), (20, 40, 64, 128)])
+def test_node_features_matches_torch(dev, nu, ni, f, c):
+    """cat[user_emb, item_proj(feats)] through the library (tensor-core path when f == c == 128, FFMA otherwise)."""
+    from b200gat.functional import node_features
+    torch.manual_seed(nu + ni)
+    uw = torch.randn(nu, c, device=dev, requires_grad=True)
+    pw = (torch.randn(c, f, device=dev) * 0.1).requires_grad_(True)
+    pb = torch.randn(c, device=dev, requires_grad=True)
+    feats = torch.randn(ni, f, device=dev)
+    g = torch.randn(nu + ni, c, device=dev)
+    x0 = node_features(uw, pw, pb, feats)
+    (x0 * g).sum().backward()
+    ref = torch.cat([uw.detach().double(), feats.double() @ pw.detach().double().t() + pb.detach().double()])
+    close(x0, ref, name="x0")
+    close(uw.grad, g[:nu].double(), name="d user_emb") if nu else None
+    close(pw.grad, g[nu:].double().t() @ feats.double(), name="d item_proj.weight")
+    close(pb.grad, g[nu:].double().sum(0), name="d item_proj.bias")

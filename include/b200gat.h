@@ -112,15 +112,22 @@ int b200gat_colsum_f32(const float* a, int64_t n_rows, int channels, float* out,
  * normalise, dropout, index_add aggregate) / GATConv's propagate at train_gat_pyg.py:87.
  * Persistent warps, one destination row at a time; local row r is global node `row_offset + r`.
  *   h [*, heads*channels], s [*, 2*heads] : indexed by global node id
- *   sched [n_rows, 4] : b200gat_build_schedule of the (local slice of the) CSR rowptr; col/perm : CSR arrays
+ *   sched [n_sched, 4] : (row, beg, end, slot+1 | 0).  Entries with a non-zero 4th field are SEGMENTS of a long
+ *     row that the host split (a hub row processed by one warp would be the tail of the launch): the warp
+ *     parks its un-normalised softmax state in partial[slot] (heads*(channels+4) floats per slot) and a second
+ *     small kernel merges the segments of each long row in order.  long_table [n_long, 4] = (row, first slot,
+ *     n segments, degree); n_long may be 0 (then long_table/partial may be NULL).  The backward uses the same
+ *     scheme with heads*channels+4 floats per slot.
+ *   col/perm : CSR arrays
  *   bias [channels] or NULL; out [n_rows, channels] (head mean + bias)
  *   out_heads [n_rows, heads, channels] or NULL (per-head outputs, needed by the backward if heads>1)
  *   rowstat [n_rows, heads, 2] = (running max m (0 for CUSTOM), 1/(denominator+eps)) or NULL
  *   p_drop/seed : attention dropout (0 = off); the mask is a function of (seed, original edge id,
  *   head) only.
  */
-int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, const int32_t* col,
-                         const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels, int policy,
+int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, int64_t n_sched,
+                         const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                         const int32_t* perm, int64_t row_offset, int heads, int channels, int policy,
                          float negative_slope, const float* bias, float* out, float* out_heads, float* rowstat,
                          float p_drop, uint64_t seed, void* stream);
 
@@ -138,9 +145,10 @@ int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float
                           const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
                           float* nodestat, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
-                         const int32_t* sched, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
-                         int64_t row_offset, int heads, int channels, int policy, float negative_slope, float* dh,
-                         float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream);
+                         const int32_t* sched, int64_t n_sched, const int32_t* long_table, int64_t n_long,
+                         float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset, int heads,
+                         int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
+                         int ld_ds, float p_drop, uint64_t seed, void* stream);
 int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int heads,
                        float* ds_dst, int ld_ds, void* stream);
 

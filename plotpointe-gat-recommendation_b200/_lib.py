@@ -42,13 +42,13 @@ _SIGS = {
     "b200gat_linear_f32": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int64, _P, c_size_t, _P]),
     "b200gat_linear_bwd_f32": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "b200gat_colsum_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
-    "b200gat_edge_fwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P, _P, _P,
-                                     c_float, c_uint64, _P]),
+    "b200gat_edge_fwd_f32": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P,
+                                     _P, _P, _P, c_float, c_uint64, _P]),
     "b200gat_node_prep_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "b200gat_schedule_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_build_schedule": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
-    "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P,
-                                     _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int,
+                                     c_float, _P, _P, _P, c_int, c_float, c_uint64, _P]),
     "b200gat_ds_dst_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P]),
     "b200gat_loss_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_rank_loss_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, c_int, c_int, _P, _P,
@@ -135,6 +135,50 @@ def schedule_workspace_bytes(n_rows: int) -> int:
     out = c_size_t(0)
     _check(_lib.b200gat_schedule_workspace_bytes(n_rows, ctypes.byref(out)), "schedule_workspace_bytes")
     return out.value
+
+
+SPLIT_DEGREE = 128   # rows longer than this are cut into segments of this many edges (one warp each)
+
+
+class Schedule:
+    """Row schedule of one direction: ``sched`` [n_sched, 4] = (row, beg, end, slot+1 | 0) in descending-degree order
+    with long rows cut into segments; ``table`` [n_long, 4] = (row, first slot, n segments, degree)."""
+
+    def __init__(self, sched, table, n_slots):
+        self.sched, self.table, self.n_slots = sched, table, n_slots
+        self.n_sched = int(sched.shape[0]) if sched is not None else 0
+        self.n_long = 0 if table is None else int(table.shape[0])
+
+    def partial(self, floats_per_slot: int):
+        if self.n_slots == 0:
+            return None
+        return torch.empty(self.n_slots * floats_per_slot, dtype=torch.float32, device=self.sched.device)
+
+
+def make_schedule(ptr_tensor, offset: int, n_rows: int, degree_bound: int, split: int = None) -> Schedule:
+    """Descending-degree schedule with rows of more than ``split`` edges cut into ``split``-edge segments (host logic,
+    once per graph: a handful of torch ops on the sorted schedule)."""
+    split = SPLIT_DEGREE if split is None else split
+    sched = build_schedule(ptr_tensor, offset, n_rows, degree_bound)
+    if n_rows == 0:
+        return Schedule(sched[:0], None, 0)
+    if os.environ.get("B200GAT_SCHED", "degree") == "natural" or split <= 0:
+        return Schedule(sched, None, 0)
+    deg = (sched[:, 2] - sched[:, 1]).long()
+    n_long = int((deg > split).sum())            # the schedule is sorted: the long rows are the first n_long entries
+    if n_long == 0:
+        return Schedule(sched, None, 0)
+    lng = sched[:n_long].long()
+    nseg = (deg[:n_long] + split - 1) // split
+    first = torch.cumsum(nseg, 0) - nseg
+    total = int(nseg.sum())
+    rid = torch.repeat_interleave(torch.arange(n_long, device=sched.device), nseg)
+    k = torch.arange(total, device=sched.device) - first[rid]
+    beg = lng[rid, 1] + k * split
+    end = torch.minimum(lng[rid, 2], beg + split)
+    segs = torch.stack([lng[rid, 0], beg, end, torch.arange(1, total + 1, device=sched.device)], dim=1).to(torch.int32)
+    table = torch.stack([lng[:, 0], first, nseg, deg[:n_long]], dim=1).to(torch.int32).contiguous()
+    return Schedule(torch.cat([segs, sched[n_long:]], dim=0).contiguous(), table, total)
 
 
 def build_schedule(ptr_tensor, offset: int, n_rows: int, degree_bound: int):

@@ -86,6 +86,37 @@ struct RowBuf {
   float4 v[H][CV];
 };
 
+template <int POLICY, int H, int CV>
+__device__ __forceinline__ void finalize_row(int r, bool has_edges, const float (&m)[H], const float (&lt)[H], float4 (&acc)[H][CV],
+                                             const float* __restrict__ bias, float* __restrict__ out,
+                                             float* __restrict__ out_heads, float2* __restrict__ rowstat, int lane) {
+  constexpr int C = CV * 128;
+  constexpr int HC = H * C;
+  float inv[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    inv[hh] = 1.f / (lt[hh] + (POLICY == kCustom ? 1e-9f : 1e-16f));
+    if (lane == 0 && rowstat) rowstat[(size_t)r * H + hh] = make_float2(has_edges ? m[hh] : 0.f, inv[hh]);
+  }
+#pragma unroll
+  for (int cv = 0; cv < CV; ++cv) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      float4 a = acc[hh][cv];
+      a.x *= inv[hh]; a.y *= inv[hh]; a.z *= inv[hh]; a.w *= inv[hh];
+      if (out_heads) st_stream4(out_heads + (size_t)r * HC + hh * C + cv * 128 + lane * 4, a);
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
+    if (bias) {
+      const float4 b = ldg4(bias + cv * 128 + lane * 4);
+      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
+  }
+}
+
 template <int POLICY, int H, int CV, bool DROPOUT>
 __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
@@ -93,7 +124,8 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
                                                                 float neg_slope, const float* __restrict__ bias,
                                                                 float* __restrict__ out, float* __restrict__ out_heads,
-                                                                float2* __restrict__ rowstat, float p_drop, uint64_t seed) {
+                                                                float2* __restrict__ rowstat, float* __restrict__ partial,
+                                                                float p_drop, uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
   constexpr int U = (H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : 4);   // rows per load group; two groups in flight
@@ -185,31 +217,68 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
         }
       }
     }
-    float inv[H];
+    float lt[H];
 #pragma unroll
-    for (int hh = 0; hh < H; ++hh) {
-      const float lt = warp_sum(l[hh]);
-      inv[hh] = 1.f / (lt + (POLICY == kCustom ? 1e-9f : 1e-16f));
-      if (lane == 0 && rowstat) rowstat[(size_t)r * H + hh] = make_float2(beg < end ? m[hh] : 0.f, inv[hh]);
-    }
-#pragma unroll
-    for (int cv = 0; cv < CV; ++cv) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hh = 0; hh < H; ++hh) lt[hh] = warp_sum(l[hh]);
+    if (d.w > 0) {  // segment of a split (long) row: park the un-normalised state, fwd_combine_kernel finishes the row
+      float* ps = partial + (size_t)(d.w - 1) * (H * (C + 4));
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) {
-        float4 a = acc[hh][cv];
-        a.x *= inv[hh]; a.y *= inv[hh]; a.z *= inv[hh]; a.w *= inv[hh];
-        if (out_heads) st_stream4(out_heads + (size_t)r * HC + hh * C + cv * 128 + lane * 4, a);
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        if (lane == 0) { ps[hh * 4] = m[hh]; ps[hh * 4 + 1] = lt[hh]; }
+#pragma unroll
+        for (int cv = 0; cv < CV; ++cv)
+          *reinterpret_cast<float4*>(ps + 4 * H + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
       }
-      if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
-      if (bias) {
-        const float4 b = ldg4(bias + cv * 128 + lane * 4);
-        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      return;
+    }
+    finalize_row<POLICY, H, CV>(r, beg < end, m, lt, acc, bias, out, out_heads, rowstat, lane);
+  }
+}
+
+// merges the segments of the split rows in segment order (deterministic) and finishes them
+template <int POLICY, int H, int CV>
+__global__ void __launch_bounds__(kEdgeThreads) fwd_combine_kernel(const float* __restrict__ partial, const int4* __restrict__ table,
+                                                                   int n_long, const float* __restrict__ bias,
+                                                                   float* __restrict__ out, float* __restrict__ out_heads,
+                                                                   float2* __restrict__ rowstat) {
+  constexpr int C = CV * 128;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  if (idx >= n_long) return;
+  const int4 t = __ldg(table + idx);   // (row, first slot, n segments, degree)
+  float m[H], lt[H];
+  float4 acc[H][CV];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    m[hh] = POLICY == kPyG ? -INFINITY : 0.f;
+    lt[hh] = 0.f;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int k = 0; k < t.z; ++k) {
+    const float* ps = partial + (size_t)(t.y + k) * (H * (C + 4));
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      const float mk = ps[hh * 4], lk = ps[hh * 4 + 1];
+      float so = 1.f, sn = 1.f;
+      if (POLICY == kPyG) {
+        const float nm = fmaxf(m[hh], mk);
+        so = expf(m[hh] - nm);
+        sn = expf(mk - nm);
+        m[hh] = nm;
       }
-      *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
+      lt[hh] = lt[hh] * so + lk * sn;
+#pragma unroll
+      for (int cv = 0; cv < CV; ++cv) {
+        const float4 a = *reinterpret_cast<const float4*>(ps + 4 * H + hh * C + cv * 128 + lane * 4);
+        acc[hh][cv].x = acc[hh][cv].x * so + a.x * sn;
+        acc[hh][cv].y = acc[hh][cv].y * so + a.y * sn;
+        acc[hh][cv].z = acc[hh][cv].z * so + a.z * sn;
+        acc[hh][cv].w = acc[hh][cv].w * so + a.w * sn;
+      }
     }
   }
+  finalize_row<POLICY, H, CV>(t.x, true, m, lt, acc, bias, out, out_heads, rowstat, lane);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -297,7 +366,8 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
                                                                 const int32_t* __restrict__ perm_csc, int n_rows, int row_offset,
                                                                 float neg_slope, float* __restrict__ dh,
                                                                 float* __restrict__ de, float* __restrict__ ds_src,
-                                                                int ld_ds, float p_drop, uint64_t seed) {
+                                                                int ld_ds, float* __restrict__ partial, float p_drop,
+                                                                uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
   constexpr int U = CV >= 2 ? 2 : 4;   // dout rows per load group; two groups in flight
@@ -400,6 +470,17 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
         }
       }
     }
+    if (d.w > 0) {  // segment of a split (long) row: bwd_combine_kernel sums the segments in order
+      float* ps = partial + (size_t)(d.w - 1) * (HC + 4);
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {
+        const float t = warp_sum(dss[hh]);
+        if (lane == 0) ps[hh] = t;
+#pragma unroll
+        for (int cv = 0; cv < CV; ++cv) *reinterpret_cast<float4*>(ps + 4 + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
+      }
+      return;
+    }
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) {
       const float t = warp_sum(dss[hh]);
@@ -408,6 +489,45 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
       for (int cv = 0; cv < CV; ++cv)
         *reinterpret_cast<float4*>(dh + (size_t)r * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
     }
+  }
+}
+
+template <int H, int CV>
+__global__ void __launch_bounds__(kEdgeThreads) bwd_combine_kernel(const float* __restrict__ partial, const int4* __restrict__ table,
+                                                                   int n_long, float* __restrict__ dh, float* __restrict__ ds_src,
+                                                                   int ld_ds) {
+  constexpr int C = CV * 128;
+  constexpr int HC = H * C;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+  if (idx >= n_long) return;
+  const int4 t = __ldg(table + idx);
+  float dss[H];
+  float4 acc[H][CV];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    dss[hh] = 0.f;
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int k = 0; k < t.z; ++k) {
+    const float* ps = partial + (size_t)(t.y + k) * (HC + 4);
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      dss[hh] += ps[hh];
+#pragma unroll
+      for (int cv = 0; cv < CV; ++cv) {
+        const float4 a = *reinterpret_cast<const float4*>(ps + 4 + hh * C + cv * 128 + lane * 4);
+        acc[hh][cv].x += a.x; acc[hh][cv].y += a.y; acc[hh][cv].z += a.z; acc[hh][cv].w += a.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    if (lane == 0) ds_src[(size_t)t.x * ld_ds + hh] = dss[hh];
+#pragma unroll
+    for (int cv = 0; cv < CV; ++cv)
+      *reinterpret_cast<float4*>(dh + (size_t)t.x * HC + hh * C + cv * 128 + lane * 4) = acc[hh][cv];
   }
 }
 
@@ -503,11 +623,13 @@ extern "C" int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_
   return kOk;
 }
 
-extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, const int32_t* col,
-                                    const int32_t* perm, int64_t n_rows, int64_t row_offset, int heads, int channels,
+extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, int64_t n_rows,
+                                    const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                    const int32_t* perm, int64_t row_offset, int heads, int channels,
                                     int policy, float negative_slope, const float* bias, float* out, float* out_heads,
                                     float* rowstat, float p_drop, uint64_t seed, void* stream) {
   B200GAT_CHECK_ARG(h && s && sched && out, "null pointer");
+  B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
   B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
   B200GAT_CHECK_ARG(p_drop == 0.f || perm, "dropout needs perm");
@@ -524,7 +646,10 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
     if (rc) return rc;                                                                                                  \
     count_launch(), edge_fwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                      \
         h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,        \
-        (float2*)rowstat, p_drop, seed);                                                                                \
+        (float2*)rowstat, partial, p_drop, seed);                                                                       \
+    if (n_long > 0)                                                                                                     \
+      count_launch(), fwd_combine_kernel<P, kH, kCV><<<ceil_div(n_long * 32, kEdgeThreads), kEdgeThreads, 0, st>>>(     \
+          partial, (const int4*)long_table, (int)n_long, bias, out, out_heads, (float2*)rowstat);                       \
   } while (0)
   B200GAT_DISPATCH_HC(heads, cv, {
     if (policy == kCustom) { if (drop) LAUNCH_FWD(kCustom, true); else LAUNCH_FWD(kCustom, false); }
@@ -563,11 +688,13 @@ extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, 
 }
 
 extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
-                                    const int32_t* sched, const int32_t* row, const int32_t* perm_csc, int64_t n_rows,
+                                    const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
+                                    float* partial, const int32_t* row, const int32_t* perm_csc,
                                     int64_t row_offset, int heads, int channels, int policy, float negative_slope,
                                     float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
                                     void* stream) {
   B200GAT_CHECK_ARG(h && s && dout && nodestat && sched && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
+  B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
   B200GAT_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dropout p=%f outside [0,1)", p_drop);
   B200GAT_CHECK_ARG(p_drop == 0.f || perm_csc, "dropout needs perm_csc");
@@ -584,7 +711,10 @@ extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float*
     if (rc) return rc;                                                                                                 \
     count_launch(), edge_bwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                     \
         h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,          \
-        negative_slope, dh, de, ds_src, ld_ds, p_drop, seed);                                                          \
+        negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                                 \
+    if (n_long > 0)                                                                                                    \
+      count_launch(), bwd_combine_kernel<kH, kCV><<<ceil_div(n_long * 32, kEdgeThreads), kEdgeThreads, 0, st>>>(       \
+          partial, (const int4*)long_table, (int)n_long, dh, ds_src, ld_ds);                                           \
   } while (0)
   B200GAT_DISPATCH_HC(heads, cv, {
     if (policy == kCustom) { if (drop) LAUNCH_BWD(kCustom, true); else LAUNCH_BWD(kCustom, false); }

@@ -48,9 +48,11 @@ class GATLayerFunction(torch.autograd.Function):
             rowstat = _empty((n, heads, 2), x) if need_grad else None
             out_heads = _empty((n, heads, channels), x) if (need_grad and heads > 1) else None
             b = None if bias is None else _lib._f32(bias, "bias").contiguous()
-            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(graph.sched_fwd), _lib.ptr(graph.col),
-                      _lib.ptr(graph.perm), n, 0, heads, channels, policy, negative_slope, _lib.ptr(b), _lib.ptr(out),
-                      _lib.ptr(out_heads), _lib.ptr(rowstat), p_drop, seed, st)
+            sf = graph.sched_fwd
+            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(sf.sched), sf.n_sched, _lib.ptr(sf.table),
+                      sf.n_long, _lib.ptr(sf.partial(heads * (channels + 4))), _lib.ptr(graph.col), _lib.ptr(graph.perm), 0,
+                      heads, channels, policy, negative_slope, _lib.ptr(b), _lib.ptr(out), _lib.ptr(out_heads),
+                      _lib.ptr(rowstat), p_drop, seed, st)
         if need_grad:
             ctx.save_for_backward(x, weight, a_s, a_d, b, h, s, rowstat, out if heads == 1 else out_heads)
             ctx.graph = graph
@@ -77,9 +79,11 @@ class GATLayerFunction(torch.autograd.Function):
             dh = _empty((n, heads * channels), x)
             de = _empty((max(g.n_edges, 1), heads), x)
             ds = _empty((n, 2 * heads), x)
+            sb = g.sched_bwd
             _lib.call("b200gat_edge_bwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(dout), _lib.ptr(nodestat),
-                      _lib.ptr(g.sched_bwd), _lib.ptr(g.row), _lib.ptr(g.perm_csc), n, 0, heads, channels, policy,
-                      negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
+                      _lib.ptr(sb.sched), sb.n_sched, _lib.ptr(sb.table), sb.n_long,
+                      _lib.ptr(sb.partial(heads * channels + 4)), _lib.ptr(g.row), _lib.ptr(g.perm_csc), 0, heads, channels,
+                      policy, negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
             _lib.call("b200gat_ds_dst_f32", _lib.ptr(de), _lib.ptr(g.rowptr), _lib.ptr(g.csr2csc), n, heads,
                       _lib.ptr(ds, heads), 2 * heads, st)
             del de

@@ -25,8 +25,8 @@ class GraphStructure:
     row: torch.Tensor       # int32 [E]    destination of each edge, CSC order
     perm_csc: torch.Tensor  # int32 [E]
     csr2csc: torch.Tensor   # int32 [E]    CSC position of the edge at each CSR position
-    sched_fwd: torch.Tensor = None   # int32 [N, 4] destination rows by descending in-degree: (row, beg, end, 0)
-    sched_bwd: torch.Tensor = None   # int32 [N, 4] source rows by descending out-degree
+    sched_fwd: "_lib.Schedule" = None   # destination rows by descending in-degree, long rows split into segments
+    sched_bwd: "_lib.Schedule" = None   # source rows by descending out-degree
 
 
 def build_graph(edge_index: torch.Tensor, n_nodes: int, check: bool = True) -> GraphStructure:
@@ -53,8 +53,8 @@ def build_graph(edge_index: torch.Tensor, n_nodes: int, check: bool = True) -> G
         _lib.call("b200gat_build_graph", _lib.ptr(ei), n_edges, n_nodes, _lib.ptr(g.rowptr), _lib.ptr(g.col),
                   _lib.ptr(g.perm), _lib.ptr(g.colptr), _lib.ptr(g.row), _lib.ptr(g.perm_csc), _lib.ptr(g.csr2csc),
                   _lib.ptr(n_bad), _lib.ptr(ws), ws_bytes, _lib.stream())
-    g.sched_fwd = _lib.build_schedule(g.rowptr, 0, n_nodes, n_edges + 1)
-    g.sched_bwd = _lib.build_schedule(g.colptr, 0, n_nodes, n_edges + 1)
+    g.sched_fwd = _lib.make_schedule(g.rowptr, 0, n_nodes, n_edges + 1)
+    g.sched_bwd = _lib.make_schedule(g.colptr, 0, n_nodes, n_edges + 1)
     if check:
         bad = int(n_bad.item())
         if bad:

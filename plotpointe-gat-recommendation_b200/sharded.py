@@ -74,9 +74,13 @@ def all_gather_rows(local: torch.Tensor, bounds: List[int], out: Optional[torch.
     """Concatenate the ranks' row blocks (block k has bounds[k+1]-bounds[k] rows) into one [N, ...] tensor."""
     world = len(bounds) - 1
     n = bounds[-1]
+    if world == 1 and out is None:
+        return local
     if out is None:
         out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     if world == 1:
+        if out is None:
+            return local
         out.copy_(local)
         return out
     pieces = [out[bounds[k]:bounds[k + 1]] for k in range(world)]
@@ -130,8 +134,8 @@ class ShardedGAT:
         self.perm_bwd = self.plan.bwd_sel[self.g_bwd.perm_csc.long()].to(torch.int32).contiguous()
         self.e_total = int(ei.shape[1])
         # local row schedules (rows are block-local ids; beg/end index the sub-graph's col / row arrays)
-        self.sched_fwd = _lib.build_schedule(self.g_fwd.rowptr, lo, self.n_loc, self.g_fwd.n_edges + 1)
-        self.sched_bwd = _lib.build_schedule(self.g_bwd.colptr, lo, self.n_loc, self.g_bwd.n_edges + 1)
+        self.sched_fwd = _lib.make_schedule(self.g_fwd.rowptr, lo, self.n_loc, self.g_fwd.n_edges + 1)
+        self.sched_bwd = _lib.make_schedule(self.g_bwd.colptr, lo, self.n_loc, self.g_bwd.n_edges + 1)
         del ei
 
         torch.manual_seed(seed)
@@ -170,8 +174,9 @@ class ShardedGAT:
         """Returns the local rows of Z; keeps what the backward needs in ``self.saved``."""
         L, H, C, lib = self._lib, self.heads, self.hidden, self._lib
         st = lib.stream()
+        from .functional import node_features
         with torch.enable_grad():
-            x0 = torch.cat([self.user_emb, self.item_proj(self.feats_loc)], dim=0)
+            x0 = node_features(self.user_emb, self.item_proj.weight, self.item_proj.bias, self.feats_loc)
         self.x0 = x0
         x = x0.detach()
         self.saved = []
@@ -190,9 +195,10 @@ class ShardedGAT:
             rowstat = self._empty(self.n_loc, H, 2)
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
-            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(self.sched_fwd),
-                     lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.n_loc, self.plan.lo, H, C, self.policy, 0.2,
-                     lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
+            sf = self.sched_fwd
+            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(sf.sched), sf.n_sched, lib.ptr(sf.table),
+                     sf.n_long, lib.ptr(sf.partial(H * (C + 4))), lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.plan.lo,
+                     H, C, self.policy, 0.2, lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
             self.saved.append((x, h_full, s_full, rowstat, out if H == 1 else out_heads, p, seed))
             x = out
         return x
@@ -230,9 +236,11 @@ class ShardedGAT:
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
+            sb = self.sched_bwd
             lib.call("b200gat_edge_bwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(dout_full), lib.ptr(nodestat_full),
-                     lib.ptr(self.sched_bwd), lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.n_loc,
-                     self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh), lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
+                     lib.ptr(sb.sched), sb.n_sched, lib.ptr(sb.table), sb.n_long, lib.ptr(sb.partial(H * C + 4)),
+                     lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh),
+                     lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
             ds_dst = self._empty(self.n, H)                                  # partial sums over this rank's edges
             lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n, H,
                      lib.ptr(ds_dst), H, st)

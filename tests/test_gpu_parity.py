@@ -104,11 +104,14 @@ def _custom_inputs(n, e, c, seed, scale, hub=None):
     return ei, x, W, a_s, a_d, gy
 
 
-@pytest.mark.parametrize("n,e,scale,hub", [(200, 3000, 1.0, None), (150, 2500, 12.0, 7), (40, 20, 1.0, None), (2000, 60000, 3.0, 5)])
-def test_custom_layer_forward_backward(dev, n, e, scale, hub):
+@pytest.mark.parametrize("n,e,scale,hub,flip", [(200, 3000, 1.0, None, False), (150, 2500, 12.0, 7, False), (40, 20, 1.0, None, False),
+                                               (2000, 60000, 3.0, 5, False), (2000, 60000, 3.0, 5, True)])
+def test_custom_layer_forward_backward(dev, n, e, scale, hub, flip):
     import b200gat
     c = 128
     ei, x, W, a_s, a_d, gy = _custom_inputs(n, e, c, 7, scale, hub)
+    if flip:                      # the hub becomes a SOURCE with 15k out-edges: split rows in the backward pass
+        ei = ei.flip(0).contiguous()
     # oracle in fp32 (what the reference computes) and fp64 (the truth both are judged against)
     ref = {}
     for dt in (torch.float32, torch.float64):
@@ -132,15 +135,19 @@ def test_custom_layer_forward_backward(dev, n, e, scale, hub):
         assert err_ours <= max(4 * err_ref, RTOL * scale_), (name, err_ours, err_ref, scale_)
         close(gt, r64, rtol=2e-5, name=name)
     # rows without in-edges are exactly zero (reference: zeros_like + index_add_)
-    assert torch.count_nonzero(y[-3:]) == 0
+    if not flip:
+        assert torch.count_nonzero(y[-3:]) == 0
 
 
 @pytest.mark.parametrize("heads", [1, 2, 4])
-def test_gatconv_forward_backward(dev, heads):
+@pytest.mark.parametrize("hub_is_source", [False, True])
+def test_gatconv_forward_backward(dev, heads, hub_is_source):
     import b200gat
     n, e, c = 300, 6000, 128
     torch.manual_seed(heads)
-    ei = random_multigraph(n, e, 100 + heads, hub=3)
+    ei = random_multigraph(n, e, 100 + heads, hub=3)          # 1500 edges on one node: exercises the split-row path
+    if hub_is_source:
+        ei = ei.flip(0).contiguous()
     conv = b200gat.GATConv(c, c, heads=heads, concat=False, add_self_loops=False, dropout=0.1).to(dev).eval()
     with torch.no_grad():
         conv.bias.uniform_(-0.5, 0.5)
@@ -158,7 +165,8 @@ def test_gatconv_forward_backward(dev, heads):
     close(xd.grad, x64.grad, rtol=2e-5, name="dx")
     for nm, p, r in zip(["dW", "datt_src", "datt_dst", "dbias"], (conv.lin.weight, conv.att_src, conv.att_dst, conv.bias), p64):
         close(p.grad, r.grad, rtol=2e-5, name=nm)
-    assert torch.equal(y[-3:], conv.bias.expand(3, c)), "rows without in-edges must equal the bias"
+    if not hub_is_source:
+        assert torch.equal(y[-3:], conv.bias.expand(3, c)), "rows without in-edges must equal the bias"
 
 
 @pytest.mark.parametrize("name", ["custom_layer_plain.npz", "custom_layer_clamped.npz"])

@@ -159,18 +159,21 @@ int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* cs
  *   loss : device float[1]; an out-of-range triple makes it NaN.
  *   The forward leaves per-triple coefficients and node-sorted incidence lists in `workspace`; pass the
  *   same workspace to the backward.  grad_out : device float[1].  The backward writes the gradient
- *   rows of nodes [node_begin, node_begin+node_count) into dz [node_count, channels] (a row shard;
- *   0 / n_users+n_items = everything); every row written (rows without triples = 0); no atomics,
- *   bitwise reproducible.
+ *   rows of nodes [node_begin, node_begin+node_count) -- or of the nodes listed in node_list
+ *   [node_count] when it is not NULL -- into dz [node_count, channels] (a row shard; 0 / n_users+n_items
+ *   = everything); every row written (rows without triples = 0); no atomics, bitwise reproducible.
+ *   node_map (nullable, int32 [n_users+n_items]): row of z that holds node v (a row-sharded z is stored
+ *   block-permuted); NULL = identity.
  */
 int b200gat_loss_workspace_bytes(int64_t n_nodes, int64_t n_triples, size_t* bytes /*host*/);
 int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
-                              const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind, int need_backward,
-                              float* loss, void* workspace, size_t workspace_bytes, void* stream);
+                              const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
+                              int loss_kind, int need_backward, float* loss, void* workspace, size_t workspace_bytes,
+                              void* stream);
 int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
-                              const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
-                              const float* grad_out, int64_t node_begin, int64_t node_count, float* dz,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
+                              int loss_kind, const float* grad_out, const int32_t* node_list, int64_t node_begin,
+                              int64_t node_count, float* dz, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

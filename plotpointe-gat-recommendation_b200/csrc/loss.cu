@@ -22,6 +22,7 @@ template <int LOSS>
 __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ z, int C, int64_t n_users, int64_t n_items,
                                                        const int64_t* __restrict__ u, const int64_t* __restrict__ i,
                                                        const int64_t* __restrict__ j, int64_t S,
+                                                       const int32_t* __restrict__ node_map,
                                                        float* __restrict__ coef /*[2S]: d/dpos, d/dneg*/,
                                                        double* __restrict__ partial, int32_t* __restrict__ n_bad) {
   __shared__ float wsum[8];
@@ -32,9 +33,11 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
     int64_t uu = u[t], ii = i[t], jj = j[t];
     const bool ok = uu >= 0 && uu < n_users && ii >= 0 && ii < n_items && jj >= 0 && jj < n_items;
     if (!ok) { uu = 0; ii = 0; jj = 0; if (lane == 0) atomicAdd(n_bad, 1); }
-    const float* zu = z + uu * C;
-    const float* zi = z + (n_users + ii) * C;
-    const float* zj = z + (n_users + jj) * C;
+    int64_t nu_ = uu, ni_ = n_users + ii, nj_ = n_users + jj;
+    if (node_map) { nu_ = node_map[nu_]; ni_ = node_map[ni_]; nj_ = node_map[nj_]; }
+    const float* zu = z + nu_ * C;
+    const float* zi = z + ni_ * C;
+    const float* zj = z + nj_ * C;
     float pos = 0.f, neg = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
       const float4 a = ldg4(zu + c);
@@ -100,16 +103,18 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ j, int64_t S,
                                                        const float* __restrict__ coef, const int32_t* __restrict__ ptr,
                                                        const int32_t* __restrict__ ids, const float* __restrict__ grad_out,
-                                                       float scale, int64_t node_begin, int64_t node_count,
+                                                       float scale, const int32_t* __restrict__ node_list, int64_t node_begin,
+                                                       int64_t node_count, const int32_t* __restrict__ node_map,
                                                        float* __restrict__ dz /*[node_count, C]*/) {
   const int lane = threadIdx.x & 31;
   const int64_t local = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (local >= node_count) return;
-  const int64_t n = node_begin + local;
+  const int64_t n = node_list ? (int64_t)node_list[local] : node_begin + local;
   const int beg = ptr[n], end = ptr[n + 1];
   const float g = grad_out[0] * scale;
   const int64_t n_items = n_nodes - n_users;
   auto safe = [](int64_t v, int64_t lim) { return (v < 0 || v >= lim) ? (int64_t)0 : v; };
+  auto zrow = [&](int64_t node) { return node_map ? (int64_t)node_map[node] : node; };
   for (int c = lane * 4; c < C; c += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = beg; q < end; ++q) {
@@ -117,10 +122,10 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
       const int role = id / (int)S;
       const int64_t t = id - (int64_t)role * S;
       if (role == 0) {
-        acc = fma4(coef[t], ldg4(z + (n_users + safe(i[t], n_items)) * C + c), acc);
-        acc = fma4(coef[S + t], ldg4(z + (n_users + safe(j[t], n_items)) * C + c), acc);
+        acc = fma4(coef[t], ldg4(z + zrow(n_users + safe(i[t], n_items)) * C + c), acc);
+        acc = fma4(coef[S + t], ldg4(z + zrow(n_users + safe(j[t], n_items)) * C + c), acc);
       } else {
-        acc = fma4(coef[(role - 1) * S + t], ldg4(z + safe(u[t], n_users) * C + c), acc);
+        acc = fma4(coef[(role - 1) * S + t], ldg4(z + zrow(safe(u[t], n_users)) * C + c), acc);
       }
     }
     acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
@@ -165,9 +170,9 @@ LossWs carve(void* ws, int64_t n_nodes, int64_t S) {
 
 // loss[0] = mean over triples.  Leaves coef + the node-sorted incidence lists in `workspace` for the backward.
 extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
-                                         const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
-                                         int need_backward, float* loss, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
+                                         int loss_kind, int need_backward, float* loss, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
   B200GAT_CHECK_ARG(z && loss && workspace, "null pointer");
   B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
   B200GAT_CHECK_ARG(channels % 4 == 0, "channels must be a multiple of 4");
@@ -182,10 +187,10 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
   B200GAT_CUDA(cudaMemsetAsync(w.n_bad, 0, 4, st));
   const int blocks = ceil_div(S, 8);
   if (loss_kind == kBpr) {
-    count_launch(), loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    count_launch(), loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, node_map, w.coef, w.partial, w.n_bad);
     count_launch(), loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 1.0 / (double)S, w.n_bad, loss);
   } else {
-    count_launch(), loss_fwd_kernel<kBce><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, w.coef, w.partial, w.n_bad);
+    count_launch(), loss_fwd_kernel<kBce><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, node_map, w.coef, w.partial, w.n_bad);
     count_launch(), loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 0.5 / (double)S, w.n_bad, loss);
   }
   B200GAT_LAUNCH_CHECK();
@@ -201,9 +206,10 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
 }
 
 extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
-                                         const int64_t* i, const int64_t* j, int64_t n_triples, int loss_kind,
-                                         const float* grad_out, int64_t node_begin, int64_t node_count, float* dz,
-                                         void* workspace, size_t workspace_bytes, void* stream) {
+                                         const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
+                                         int loss_kind, const float* grad_out, const int32_t* node_list, int64_t node_begin,
+                                         int64_t node_count, float* dz, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   B200GAT_CHECK_ARG(z && grad_out && dz && workspace && u && i && j, "null pointer");
   B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
   size_t need;
@@ -212,12 +218,12 @@ extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t S = n_triples, N = n_users + n_items;
-  B200GAT_CHECK_ARG(node_begin >= 0 && node_count >= 0 && node_begin + node_count <= N, "bad node range");
+  B200GAT_CHECK_ARG(node_count >= 0 && (node_list || (node_begin >= 0 && node_begin + node_count <= N)), "bad node range");
   if (node_count == 0) return kOk;
   LossWs w = carve(workspace, N, S);
   const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
   count_launch(), loss_bwd_kernel<<<ceil_div(node_count * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids,
-                                                                 grad_out, scale, node_begin, node_count, dz);
+                                                                 grad_out, scale, node_list, node_begin, node_count, node_map, dz);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -170,7 +170,7 @@ class RankLossFunction(torch.autograd.Function):
         loss = _empty((1,), z)
         with torch.cuda.device(z.device):
             _lib.call("b200gat_rank_loss_fwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(idx[0]), _lib.ptr(idx[1]),
-                      _lib.ptr(idx[2]), s, kind, int(need), _lib.ptr(loss), _lib.ptr(ws), ws_bytes, _lib.stream())
+                      _lib.ptr(idx[2]), s, None, kind, int(need), _lib.ptr(loss), _lib.ptr(ws), ws_bytes, _lib.stream())
         if need:
             ctx.save_for_backward(z, idx[0], idx[1], idx[2], ws)
             ctx.meta = (n_users, n_items, c, s, kind, ws_bytes)
@@ -184,7 +184,8 @@ class RankLossFunction(torch.autograd.Function):
         dz = torch.empty_like(z)
         with torch.cuda.device(z.device):
             _lib.call("b200gat_rank_loss_bwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), s,
-                      kind, _lib.ptr(go), 0, n_users + n_items, _lib.ptr(dz), _lib.ptr(ws), ws_bytes, _lib.stream())
+                      None, kind, _lib.ptr(go), None, 0, n_users + n_items, _lib.ptr(dz), _lib.ptr(ws), ws_bytes,
+                      _lib.stream())
         return dz, None, None, None, None, None
 
 

@@ -1,8 +1,8 @@
 """Row-sharded full-graph GAT training over P GPUs of one node (one process per GPU, torch.distributed/NCCL).
 
-The node space [0, N) is cut into P contiguous blocks balanced by in+out edge count.  Rank p owns the rows of its
-block: their input features, their destination rows in the forward (CSR slice) and their source rows in the
-backward (CSC slice).  Per layer the exchange steps are:
+Nodes are dealt round-robin to the P ranks (user u -> rank u % P, item i -> rank i % P), which balances rows and, for
+the reference's graphs, edges.  Rank p owns its nodes' rows: their input features, their destination rows in the
+forward (CSR slice) and their source rows in the backward (CSC slice).  Per layer the exchange steps are:
 
   forward : all-gather of the projected rows [h | s]   (N x (H*C + 2H) floats)      -> fused edge forward on local rows
   backward: all-gather of dout rows and of the per-destination scalars (N x (C + 4H)) -> fused edge backward on local
@@ -12,7 +12,7 @@ backward (CSC slice).  Per layer the exchange steps are:
             rows of its own block.
 
 The collectives go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the
-single-GPU path.  The plan (block bounds, per-rank edge selections) is plain torch and also runs on CPU tensors, which
+single-GPU path.  The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which
 is how the gloo tests exercise it.
 """
 from __future__ import annotations
@@ -31,69 +31,62 @@ import torch.distributed as dist
 # ------------------------------------------------------------------------------------------------------ the plan
 @dataclass
 class ShardPlan:
-    bounds: List[int]            # P+1 node boundaries
+    """Round-robin block layout.  Users u and items i go to rank u % P / i % P, so every rank owns (within one row) the
+    same number of users and of items and, for a random graph, the same number of edges.  Inside a block users come
+    first, then items (the order node_features produces).  Blocks are padded to ``n_max`` rows so that one
+    ``all_gather_into_tensor`` moves a layer; ``perm_map[v]`` is the row of node v in the gathered [P*n_max, ...]
+    tensors, and every index array the kernels see (col, row, schedules) is expressed in that row space."""
     rank: int
     world: int
-    fwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose destination is in the local block
-    bwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose source is in the local block
+    n_users: int
+    n_items: int
+    n_max: int
+    n_loc: int
+    cu: int                      # users owned by this rank
+    ci: int                      # items owned by this rank
+    perm_map: torch.Tensor       # int64 [N]  node id -> gathered row
+    local_nodes: torch.Tensor    # int64 [n_loc] node ids of the local rows, in local row order
+    fwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose destination is local
+    bwd_sel: torch.Tensor        # int64 ids (ascending) of the edges whose source is local
 
     @property
     def lo(self):
-        return self.bounds[self.rank]
+        return self.rank * self.n_max
 
     @property
-    def hi(self):
-        return self.bounds[self.rank + 1]
+    def n_rows_total(self):
+        return self.world * self.n_max
 
 
-def partition_bounds(edge_index: torch.Tensor, n_nodes: int, world: int) -> List[int]:
-    """Contiguous node blocks with (approximately) equal in-edge + out-edge counts.  Deterministic, so every rank
-    computes the same bounds from the same edge list."""
-    w = torch.bincount(edge_index[0], minlength=n_nodes) + torch.bincount(edge_index[1], minlength=n_nodes)
-    w = w.to(torch.float64) + 1e-3                      # isolated nodes still cost a row
-    cum = torch.cumsum(w, 0)
-    total = float(cum[-1])
-    targets = torch.tensor([total * k / world for k in range(1, world)], dtype=torch.float64, device=cum.device)
-    cuts = torch.searchsorted(cum, targets).tolist() if world > 1 else []
-    bounds = [0] + [min(int(c) + 1, n_nodes) for c in cuts] + [n_nodes]
-    for k in range(1, len(bounds)):                     # monotone, no empty interior blocks when N >= P
-        bounds[k] = max(bounds[k], bounds[k - 1])
-    return bounds
+def owner_of(nodes: torch.Tensor, n_users: int, world: int) -> torch.Tensor:
+    return torch.where(nodes < n_users, nodes % world, (nodes - n_users) % world)
 
 
-def make_plan(edge_index: torch.Tensor, n_nodes: int, rank: int, world: int) -> ShardPlan:
-    bounds = partition_bounds(edge_index, n_nodes, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
+def make_plan(edge_index: torch.Tensor, n_users: int, n_items: int, rank: int, world: int) -> ShardPlan:
+    dev = edge_index.device
+    cu_all = [(n_users - b + world - 1) // world for b in range(world)]
+    ci_all = [(n_items - b + world - 1) // world for b in range(world)]
+    n_max = max(a + b for a, b in zip(cu_all, ci_all))
+    cu_t = torch.tensor(cu_all, dtype=torch.int64, device=dev)
+    u = torch.arange(n_users, dtype=torch.int64, device=dev)
+    i = torch.arange(n_items, dtype=torch.int64, device=dev)
+    perm_map = torch.cat([(u % world) * n_max + u // world, (i % world) * n_max + cu_t[i % world] + i // world])
+    local_nodes = torch.cat([torch.arange(rank, max(n_users, rank), world, dtype=torch.int64, device=dev),
+                             n_users + torch.arange(rank, max(n_items, rank), world, dtype=torch.int64, device=dev)])
     src, dst = edge_index[0], edge_index[1]
-    fwd_sel = torch.nonzero((dst >= lo) & (dst < hi)).flatten()
-    bwd_sel = torch.nonzero((src >= lo) & (src < hi)).flatten()
-    return ShardPlan(bounds, rank, world, fwd_sel, bwd_sel)
+    fwd_sel = torch.nonzero(owner_of(dst, n_users, world) == rank).flatten()
+    bwd_sel = torch.nonzero(owner_of(src, n_users, world) == rank).flatten()
+    return ShardPlan(rank, world, n_users, n_items, n_max, cu_all[rank] + ci_all[rank], cu_all[rank], ci_all[rank], perm_map,
+                     local_nodes, fwd_sel, bwd_sel)
 
 
-def all_gather_rows(local: torch.Tensor, bounds: List[int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Concatenate the ranks' row blocks (block k has bounds[k+1]-bounds[k] rows) into one [N, ...] tensor."""
-    world = len(bounds) - 1
-    n = bounds[-1]
-    if world == 1 and out is None:
-        return local
-    if out is None:
-        out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+def all_gather_rows(local: torch.Tensor, world: int) -> torch.Tensor:
+    """Gather the ranks' padded row blocks ([n_max, ...] each) into one [world*n_max, ...] tensor."""
     if world == 1:
-        if out is None:
-            return local
-        out.copy_(local)
-        return out
-    pieces = [out[bounds[k]:bounds[k + 1]] for k in range(world)]
-    sizes = {p.shape[0] for p in pieces}
-    if len(sizes) == 1:
-        dist.all_gather_into_tensor(out, local.contiguous())
-    else:
-        # uneven blocks: one broadcast per owner, straight into its slice of the output (works on NCCL and gloo)
-        rank = dist.get_rank()
-        pieces[rank].copy_(local)
-        handles = [dist.broadcast(pieces[k], src=k, async_op=True) for k in range(world) if pieces[k].numel()]
-        for h in handles:
-            h.wait()
+        return local
+    local = local.contiguous()
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)
     return out
 
 
@@ -123,30 +116,30 @@ class ShardedGAT:
         self.policy = _lib.POLICY_CUSTOM if kind == "custom" else _lib.POLICY_PYG
 
         ei = edge_index.to(self.dev)
-        self.plan = make_plan(ei, self.n, self.rank, self.world)
-        lo, hi = self.plan.lo, self.plan.hi
-        self.n_loc = hi - lo
-        self.g_fwd = build_graph(ei[:, self.plan.fwd_sel].contiguous(), self.n)
-        self.g_bwd = build_graph(ei[:, self.plan.bwd_sel].contiguous(), self.n)
+        self.plan = plan = make_plan(ei, n_users, n_items, self.rank, self.world)
+        self.n_loc, self.n_max, self.n_pad = plan.n_loc, plan.n_max, plan.n_rows_total
+        ei_p = plan.perm_map[ei]                                   # the same edges in gathered-row space
+        self.g_fwd = build_graph(ei_p[:, plan.fwd_sel].contiguous(), self.n_pad)
+        self.g_bwd = build_graph(ei_p[:, plan.bwd_sel].contiguous(), self.n_pad)
         # dropout masks are keyed on the ORIGINAL edge id so that the rank that owns an edge's destination (forward)
         # and the rank that owns its source (backward) regenerate the same bit
-        self.perm_fwd = self.plan.fwd_sel[self.g_fwd.perm.long()].to(torch.int32).contiguous()
-        self.perm_bwd = self.plan.bwd_sel[self.g_bwd.perm_csc.long()].to(torch.int32).contiguous()
+        self.perm_fwd = plan.fwd_sel[self.g_fwd.perm.long()].to(torch.int32).contiguous()
+        self.perm_bwd = plan.bwd_sel[self.g_bwd.perm_csc.long()].to(torch.int32).contiguous()
         self.e_total = int(ei.shape[1])
         # local row schedules (rows are block-local ids; beg/end index the sub-graph's col / row arrays)
-        self.sched_fwd = _lib.make_schedule(self.g_fwd.rowptr, lo, self.n_loc, self.g_fwd.n_edges + 1)
-        self.sched_bwd = _lib.make_schedule(self.g_bwd.colptr, lo, self.n_loc, self.g_bwd.n_edges + 1)
-        del ei
+        self.sched_fwd = _lib.make_schedule(self.g_fwd.rowptr, plan.lo, self.n_loc, self.g_fwd.n_edges + 1)
+        self.sched_bwd = _lib.make_schedule(self.g_bwd.colptr, plan.lo, self.n_loc, self.g_bwd.n_edges + 1)
+        self.node_map = plan.perm_map.to(torch.int32).contiguous()
+        self.node_list = plan.local_nodes.to(torch.int32).contiguous()
+        del ei, ei_p
 
         torch.manual_seed(seed)
         full = (CustomGAT(n_users, n_items, item_feats.shape[1], hidden, layers) if kind == "custom"
                 else PyGGAT(n_users, n_items, item_feats.shape[1], hidden, layers, heads, attn_dropout))
-        self.u_lo, self.u_hi = min(lo, n_users), min(hi, n_users)              # user rows in the block
-        self.i_lo, self.i_hi = max(lo, n_users) - n_users, max(hi, n_users) - n_users   # item rows in the block
         P = torch.nn.Parameter
-        self.user_emb = P(full.user_emb.weight.detach()[self.u_lo:self.u_hi].clone().to(self.dev))
+        self.user_emb = P(full.user_emb.weight.detach()[self.rank::self.world].clone().to(self.dev))
         self.item_proj = full.item_proj.to(self.dev)
-        self.feats_loc = item_feats[self.i_lo:self.i_hi].to(self.dev).contiguous()
+        self.feats_loc = item_feats[self.rank::self.world].to(self.dev).contiguous()
         self.W, self.a_src, self.a_dst, self.bias = [], [], [], []
         for l in range(layers):
             lay = full.layers[l] if kind == "custom" else full.convs[l]
@@ -160,11 +153,14 @@ class ShardedGAT:
         self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay, fused=True)
         self.step_no = 0
         self.seed = seed
-        self.comm_ms: List[float] = []
 
     # -------------------------------------------------------------------------------------------- helpers
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def _rows(self, *shape):
+        """Buffer for a tensor that is exchanged: padded to n_max rows (kernels fill the first n_loc)."""
+        return torch.empty((self.n_max,) + shape, dtype=torch.float32, device=self.dev)
 
     def _layer_seed(self, layer: int) -> int:
         return (self.seed * 1_000_003 + self.step_no * 101 + layer) & (2 ** 62 - 1)
@@ -181,17 +177,16 @@ class ShardedGAT:
         x = x0.detach()
         self.saved = []
         p = self.p_drop if self.training else 0.0
-        bounds = self.plan.bounds
         for l in range(self.n_layers):
             f_in = x.shape[1]
-            h_loc, s_loc = self._empty(self.n_loc, H * C), self._empty(self.n_loc, 2 * H)
+            h_loc, s_loc = self._rows(H * C), self._rows(2 * H)
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             lib.call("b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), lib.ptr(dws), dwb, st)
-            h_full = all_gather_rows(h_loc, bounds)
-            s_full = all_gather_rows(s_loc, bounds)
-            out = self._empty(self.n_loc, C)
+            h_full = all_gather_rows(h_loc, self.world)
+            s_full = all_gather_rows(s_loc, self.world)
+            out = self._rows(C)
             rowstat = self._empty(self.n_loc, H, 2)
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
@@ -206,33 +201,33 @@ class ShardedGAT:
     def loss_and_backward(self, z_loc: torch.Tensor, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
         lib, H, C = self._lib, self.heads, self.hidden
         st = lib.stream()
-        bounds = self.plan.bounds
-        z_full = all_gather_rows(z_loc, bounds)
+        z_full = all_gather_rows(z_loc, self.world)
         s_tr = int(u.shape[0])
         ws_bytes = lib.loss_workspace_bytes(self.n, s_tr)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
         loss = self._empty(1)
         kind = lib.LOSS_BPR if loss_kind == "bpr" else lib.LOSS_BCE
         lib.call("b200gat_rank_loss_fwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                 kind, 1, lib.ptr(loss), lib.ptr(ws), ws_bytes, st)
+                 lib.ptr(self.node_map), kind, 1, lib.ptr(loss), lib.ptr(ws), ws_bytes, st)
         one = torch.ones(1, dtype=torch.float32, device=self.dev)
-        dout = self._empty(self.n_loc, C)
+        dout = self._rows(C)
         lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                 kind, lib.ptr(one), self.plan.lo, self.n_loc, lib.ptr(dout), lib.ptr(ws), ws_bytes, st)
+                 lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.node_list), 0, self.n_loc, lib.ptr(dout), lib.ptr(ws),
+                 ws_bytes, st)
         del z_full
         grads = {}
         for l in reversed(range(self.n_layers)):
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
             f_in = x.shape[1]
-            nodestat = self._empty(self.n_loc, H, 4)
+            nodestat = self._rows(H, 4)
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
                      lib.ptr(dws), dwb, st)
-            dout_full = all_gather_rows(dout, bounds)
-            nodestat_full = all_gather_rows(nodestat, bounds)
+            dout_full = all_gather_rows(dout, self.world)
+            nodestat_full = all_gather_rows(nodestat, self.world)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
@@ -241,14 +236,14 @@ class ShardedGAT:
                      lib.ptr(sb.sched), sb.n_sched, lib.ptr(sb.table), sb.n_long, lib.ptr(sb.partial(H * C + 4)),
                      lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh),
                      lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
-            ds_dst = self._empty(self.n, H)                                  # partial sums over this rank's edges
-            lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n, H,
+            ds_dst = self._empty(self.n_pad, H)                              # partial sums over this rank's edges
+            lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad, H,
                      lib.ptr(ds_dst), H, st)
             if self.world > 1:
                 dist.all_reduce(ds_dst)
-            ds[:, H:] = ds_dst[self.plan.lo:self.plan.hi]
+            ds[:, H:] = ds_dst[self.plan.lo:self.plan.lo + self.n_loc]
             del de, dout_full, nodestat_full
-            dx = self._empty(self.n_loc, f_in)
+            dx = self._rows(f_in)
             dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
             lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      lib.ptr(dh), lib.ptr(ds), self.n_loc, f_in, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
@@ -260,7 +255,7 @@ class ShardedGAT:
         # input features: user rows take their gradient rows directly, item_proj through torch autograd
         for p_ in [self.user_emb] + list(self.item_proj.parameters()):
             p_.grad = None
-        self.x0.backward(dout)
+        self.x0.backward(dout[:self.n_loc])
         for p_, g in grads.items():
             p_.grad = g
         if self.world > 1:
@@ -285,7 +280,7 @@ class ShardedGAT:
     def export_item_embeddings(self) -> torch.Tensor:
         """Config 4: forward-only, returns Z[n_users:] gathered on every rank (tools/export_item_embeddings.py:140-142)."""
         was, self.training = self.training, False
-        z = all_gather_rows(self.forward(), self.plan.bounds)
+        z = all_gather_rows(self.forward(), self.world)[self.plan.perm_map]     # back to node order
         self.training = was
         self.saved = []
         return z[self.nu:]
@@ -340,8 +335,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{B.LAYERS}, d={B.HIDDEN}, heads={B.HEADS}, BPR on "
                                    f"{B.S_TRIPLES} triples, train mode, Adam step; {e} edges", "n_nodes": nu + ni, "n_edges": e,
-                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs, NCCL all-gather per layer",
-                       "block_bounds": tr.plan.bounds,
+                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs (round-robin node blocks), NCCL all-gather per layer",
+                       "rows_per_rank": tr.n_loc,
                        "l2": "per-step working set exceeds the 126 MB L2"},
             "e2e": {"value": e * B.LAYERS / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(3 * B.S_TRIPLES * 8), "d2h_bytes_per_step": 4},

@@ -17,9 +17,9 @@ def main():
     # wrap collectives with events
     coll = []
     orig = sharded.all_gather_rows
-    def timed_gather(local_t, bounds, out=None):
+    def timed_gather(local_t, w):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); r = orig(local_t, bounds, out); b.record(); coll.append(("all_gather_rows", a, b)); return r
+        a.record(); r = orig(local_t, w); b.record(); coll.append(("all_gather_rows", a, b)); return r
     sharded.all_gather_rows = timed_gather
     orig_ar = dist.all_reduce
     def timed_ar(t, *a_, **k_):

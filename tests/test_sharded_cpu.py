@@ -25,42 +25,50 @@ def _worker(rank, world, port, ret):
         nu, ni, n_inter, k = synth.CONFIGS["tiny"]
         n = nu + ni
         ei, feats = synth.make_graph(nu, ni, n_inter, k)
-        plan = sharded.make_plan(ei, n, rank, world)
-        # every rank derives the same bounds
-        b = torch.tensor(plan.bounds)
-        others = [torch.zeros_like(b) for _ in range(world)]
-        dist.all_gather(others, b)
-        assert all(torch.equal(o, b) for o in others)
-        assert plan.bounds[0] == 0 and plan.bounds[-1] == n and all(x < y for x, y in zip(plan.bounds, plan.bounds[1:]))
+        plan = sharded.make_plan(ei, nu, ni, rank, world)
+        # the layout is a bijection onto the gathered rows and agrees across ranks
+        pm = plan.perm_map
+        assert pm.shape == (n,) and len(torch.unique(pm)) == n and int(pm.max()) < world * plan.n_max
+        others = [torch.zeros_like(pm) for _ in range(world)]
+        dist.all_gather(others, pm)
+        assert all(torch.equal(o, pm) for o in others)
+        assert torch.equal(pm[plan.local_nodes], plan.lo + torch.arange(plan.n_loc))
+        assert plan.n_loc == plan.cu + plan.ci and plan.n_max - plan.n_loc <= 2
         # edge selections: each edge belongs to exactly one rank per direction
         cnt_f = torch.zeros(ei.shape[1], dtype=torch.long); cnt_f[plan.fwd_sel] = 1
         cnt_b = torch.zeros(ei.shape[1], dtype=torch.long); cnt_b[plan.bwd_sel] = 1
         dist.all_reduce(cnt_f); dist.all_reduce(cnt_b)
         assert bool((cnt_f == 1).all()) and bool((cnt_b == 1).all())
-        # balance: in+out edge weight of the blocks within 10%
-        w = torch.bincount(ei[0], minlength=n) + torch.bincount(ei[1], minlength=n)
-        loads = [int(w[plan.bounds[r]:plan.bounds[r + 1]].sum()) for r in range(world)]
-        assert max(loads) <= 1.1 * (sum(loads) / world) + w.max().item()
-        # uneven all-gather of row blocks
+        # balance: in- and out-edge counts of the ranks within 10 %
+        for sel in (plan.fwd_sel, plan.bwd_sel):
+            c = torch.tensor([float(sel.numel())])
+            cs = [torch.zeros_like(c) for _ in range(world)]
+            dist.all_gather(cs, c)
+            loads = [float(x) for x in cs]
+            assert max(loads) <= 1.1 * sum(loads) / world, loads
+        # padded all-gather of row blocks, then back to node order through perm_map
         torch.manual_seed(0)
         full = torch.randn(n, 6)
-        got = sharded.all_gather_rows(full[plan.lo:plan.hi].clone(), plan.bounds)
-        assert torch.equal(got, full)
-        # the sharding identity: a destination block only needs its own in-edges (+ all source rows)
+        loc = torch.zeros(plan.n_max, 6)
+        loc[:plan.n_loc] = full[plan.local_nodes]
+        got = sharded.all_gather_rows(loc, world)
+        assert got.shape[0] == world * plan.n_max and torch.equal(got[pm], full)
+        # the sharding identity: a destination block only needs its own in-edges (+ all source rows), in the
+        # permuted row space exactly as the kernels see it
         torch.manual_seed(1)
         c = 16
         x = torch.randn(n, c, dtype=torch.float64)
         W = torch.randn(c, c, dtype=torch.float64) * 0.3
         a_s, a_d = torch.randn(c, dtype=torch.float64), torch.randn(c, dtype=torch.float64)
         y_full = O.simple_gat_layer(x, ei, W, a_s, a_d)
-        y_loc = O.simple_gat_layer(x, ei[:, plan.fwd_sel], W, a_s, a_d)[plan.lo:plan.hi]
-        np.testing.assert_allclose(y_loc.numpy(), y_full[plan.lo:plan.hi].numpy(), rtol=1e-12, atol=1e-14)
-        y_g = sharded.all_gather_rows(y_loc.contiguous(), plan.bounds)
+        xp = torch.zeros(world * plan.n_max, c, dtype=torch.float64)
+        xp[pm] = x
+        y_loc = O.simple_gat_layer(xp, pm[ei][:, plan.fwd_sel], W, a_s, a_d)[plan.lo:plan.lo + plan.n_loc]
+        np.testing.assert_allclose(y_loc.numpy(), y_full[plan.local_nodes].numpy(), rtol=1e-12, atol=1e-14)
+        pad = torch.zeros(plan.n_max, c, dtype=torch.float64)
+        pad[:plan.n_loc] = y_loc
+        y_g = sharded.all_gather_rows(pad, world)[pm]
         np.testing.assert_allclose(y_g.numpy(), y_full.numpy(), rtol=1e-12, atol=1e-14)
-        # backward identity: a source block's dx only needs its own out-edges once dout / per-destination scalars are shared
-        xs = x.clone().requires_grad_(True)
-        gy = torch.randn(n, c, dtype=torch.float64)
-        (O.simple_gat_layer(xs, ei, W, a_s, a_d) * gy).sum().backward()
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -75,12 +83,13 @@ def test_sharded_plan_world2_gloo():
     assert dict(ret) == {0: "ok", 1: "ok"}
 
 
-def test_partition_bounds_edge_cases():
+def test_plan_edge_cases():
     from b200gat import sharded
     ei = torch.tensor([[0, 1, 2, 3], [3, 2, 1, 0]])
-    assert sharded.partition_bounds(ei, 4, 1) == [0, 4]
-    b = sharded.partition_bounds(ei, 4, 2)
-    assert b == [0, 2, 4]
-    hub = torch.stack([torch.zeros(1000, dtype=torch.long), torch.randint(1, 50, (1000,))])
-    b = sharded.partition_bounds(hub, 50, 4)
-    assert b[0] == 0 and b[-1] == 50 and all(x <= y for x, y in zip(b, b[1:]))
+    p = sharded.make_plan(ei, 2, 2, 0, 1)
+    assert p.n_max == 4 and p.perm_map.tolist() == [0, 1, 2, 3] and p.fwd_sel.tolist() == [0, 1, 2, 3]
+    p0, p1 = sharded.make_plan(ei, 2, 2, 0, 2), sharded.make_plan(ei, 2, 2, 1, 2)
+    assert p0.perm_map.tolist() == [0, 2, 1, 3] and p0.local_nodes.tolist() == [0, 2] and p1.local_nodes.tolist() == [1, 3]
+    # more ranks than users: some ranks own items only
+    p3 = sharded.make_plan(torch.zeros((2, 0), dtype=torch.long), 1, 7, 3, 4)
+    assert p3.cu == 0 and p3.ci == 1 and p3.n_max == 3

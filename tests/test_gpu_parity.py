@@ -349,3 +349,54 @@ def test_node_features_matches_torch(dev, nu, ni, f, c):
     close(uw.grad, g[:nu].double(), name="d user_emb") if nu else None
     close(pw.grad, g[nu:].double().t() @ feats.double(), name="d item_proj.weight")
     close(pb.grad, g[nu:].double().sum(0), name="d item_proj.bias")
+
+
+@pytest.mark.parametrize("heads", [1, 4])
+def test_wide_channels_c256(dev, heads):
+    """BASELINE config 5 uses d=256: two 128-wide chunks per lane, CUDA-core projection (the tensor-core path is 128x128)."""
+    import b200gat
+    n, e, c = 400, 9000, 256
+    torch.manual_seed(3)
+    ei = random_multigraph(n, e, 33, hub=2)
+    conv = b200gat.GATConv(c, c, heads=heads, concat=False, add_self_loops=False).to(dev).eval()
+    with torch.no_grad():
+        conv.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(n, c)
+    gy = torch.randn(n, c)
+    xd = x.to(dev).requires_grad_(True)
+    y = conv(xd, ei.to(dev))
+    (y * gy.to(dev)).sum().backward()
+    p64 = [p.detach().cpu().double().requires_grad_(True) for p in (conv.lin.weight, conv.att_src, conv.att_dst, conv.bias)]
+    x64 = x.double().requires_grad_(True)
+    y64 = O.gatconv(x64, ei, p64[0], p64[1], p64[2], p64[3], heads)
+    (y64 * gy.double()).sum().backward()
+    close(y, y64, name="out")
+    close(xd.grad, x64.grad, rtol=2e-5, name="dx")
+    for nm, p, r in zip(["dW", "datt_src", "datt_dst", "dbias"], (conv.lin.weight, conv.att_src, conv.att_dst, conv.bias), p64):
+        close(p.grad, r.grad, rtol=2e-5, name=nm)
+
+
+@pytest.mark.parametrize("kind,loss_name", [("custom", "bpr"), ("pyg4", "bce")])
+def test_config1_shape_against_oracle(dev, kind, loss_name):
+    """BASELINE config 1 (10k users, 20k items, 200k interactions + k=20 kNN = 800k edges, 2 layers, d=128): the whole
+    step against the fp64 oracle; config 3's head count and BCE loss on the same graph."""
+    import b200gat
+    from b200gat import synth
+    nu, ni, n_inter, k = synth.CONFIGS["cfg1"]
+    ei, feats = synth.make_graph(nu, ni, n_inter, k)
+    u, i, j = synth.make_triples(nu, ni, 20000)
+    torch.manual_seed(11)
+    heads = 4 if kind == "pyg4" else 1
+    m = (b200gat.CustomGAT(nu, ni, 128, 128, 2) if kind == "custom" else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1)).eval()
+    state = {k_: v.detach().double().requires_grad_(True) for k_, v in m.state_dict().items()}
+    z_ref = (O.custom_gat_forward(state, feats.double(), ei) if kind == "custom" else O.pyg_gat_forward(state, feats.double(), ei, heads))
+    l_ref = (O.bpr_loss if loss_name == "bpr" else O.bce_loss)(z_ref, nu, u, i, j)
+    l_ref.backward()
+    m = m.to(dev)
+    z = m(feats.to(dev), ei.to(dev))
+    loss = (b200gat.bpr_loss if loss_name == "bpr" else b200gat.bce_loss)(z, nu, u.to(dev), i.to(dev), j.to(dev))
+    loss.backward()
+    close(z, z_ref, name="z")
+    np.testing.assert_allclose(loss.item(), l_ref.item(), rtol=RTOL)
+    for k_, p in m.named_parameters():
+        close(p.grad, state[k_].grad, rtol=1e-4, name=k_)

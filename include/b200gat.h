@@ -75,7 +75,7 @@ int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_t degree_bo
  *   x [n_rows, in_features]; W [heads*channels, in_features]; a_src, a_dst [heads, channels]
  *   h [n_rows, heads*channels]; s [n_rows, 2*heads]
  * precision: B200GAT_GEMM_FP32 = CUDA-core FFMA; B200GAT_GEMM_TF32X3 = tcgen05 tensor cores, every
- * fp32 operand split into tf32 hi + lo and three UMMAs per K step (fp32-accurate, error ~2^-22).
+ * fp32 operand split into tf32 hi + lo and four UMMAs per K step (element error ~1e-7 relative).
  * The tensor-core path needs in_features == channels == 128; other shapes use the FP32 kernels.
  */
 #define B200GAT_GEMM_FP32 0

@@ -148,7 +148,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
 }
 __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
   hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  // lo is rounded to tf32 here (round-to-nearest) so that the tensor core's own truncation of its inputs is a no-op
+  lo.x = tf32_hi(v.x - hi.x); lo.y = tf32_hi(v.y - hi.y); lo.z = tf32_hi(v.z - hi.z); lo.w = tf32_hi(v.w - hi.w);
 }
 // byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a [rows][128 B] tile with the 128B swizzle
 // (8-row groups of 1 KB, chunk index XORed with the row index inside the group)
@@ -321,9 +322,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
             const uint32_t ko = k * kUmmaK * 4;
             const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
             const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-            umma_tf32(d, dah, dbh, idesc, (kb | k) != 0);
+            umma_tf32(d, dal, dbl, idesc, (kb | k) != 0);
             umma_tf32(d, dal, dbh, idesc, 1);
             umma_tf32(d, dah, dbl, idesc, 1);
+            umma_tf32(d, dah, dbh, idesc, 1);
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
@@ -537,9 +539,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
           const uint32_t ko = kg * 4096;
           const uint64_t dah = make_desc(a_hi + ko, 512, 2048, 1), dal = make_desc(a_lo + ko, 512, 2048, 1);
           const uint64_t dbh = make_desc(b_hi + ko, 512, 2048, 1), dbl = make_desc(b_lo + ko, 512, 2048, 1);
-          umma_tf32(d, dah, dbh, idesc, (in_grp | kg) != 0);
+          umma_tf32(d, dal, dbl, idesc, (in_grp | kg) != 0);
           umma_tf32(d, dal, dbh, idesc, 1);
           umma_tf32(d, dah, dbl, idesc, 1);
+          umma_tf32(d, dah, dbh, idesc, 1);
         }
         umma_commit(bar_empty + 8 * stage);
         if (in_grp == kDwGroup - 1 || it == n_stages_total - 1) umma_commit(bar_tfull + 8 * buf);

@@ -345,13 +345,25 @@ __global__ void __launch_bounds__(256) node_prep_kernel(const float* __restrict_
   }
 }
 
-// out[c] = sum over parts, fixed order
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f;
-  for (int k = 0; k < n_parts; ++k) a += part[(size_t)k * C + c];
-  out[c] = a;
+// out[c] = sum over parts; 8 interleaved stripes per column, combined in a fixed order
+__global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out) {
+  __shared__ float red[8][128];
+  const int lc = threadIdx.x & 127, stripe = threadIdx.x >> 7;
+  for (int c0 = 0; c0 < C; c0 += 128) {
+    const int c = c0 + lc;
+    float a = 0.f;
+    if (c < C)
+      for (int k = stripe; k < n_parts; k += 8) a += part[(size_t)k * C + c];
+    red[stripe][lc] = a;
+    __syncthreads();
+    if (stripe == 0 && c < C) {
+      float t = red[0][lc];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += red[w][lc];
+      out[c] = t;
+    }
+    __syncthreads();
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -682,7 +694,7 @@ extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, 
                                                                    (int)row_offset, (float4*)nodestat,
                                                                    dbias ? (float*)workspace : nullptr);
   })
-  if (dbias) count_launch(), colsum_finish_kernel<<<ceil_div(channels, 128), 128, 0, st>>>((const float*)workspace, grid, channels, dbias);
+  if (dbias) count_launch(), colsum_finish_kernel<<<1, 1024, 0, st>>>((const float*)workspace, grid, channels, dbias);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -86,6 +86,14 @@ int b200gat_project_f32(const float* x, const float* W, const float* a_src, cons
                         int in_features, int heads, int channels, float* h, float* s, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* "bf16 projection" (BASELINE config 3): operands rounded to bf16 on the way into shared memory, one UMMA
+ * kind::f16 per K step, fp32 accumulation in TMEM; h is STORED as bf16 [n_rows, heads*128] (the edge kernels
+ * then gather 256-byte rows), s is taken from the fp32 accumulator.  Needs in_features == channels == 128;
+ * workspace >= heads * 32 KB.  The backward keeps fp32 gradients (b200gat_project_bwd_f32 with the fp32 x). */
+int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                         int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Backward of (2).  `dh` holds the aggregation part on entry and may be overwritten with the full
  * gradient of h (adds ds_src*a_src + ds_dst*a_dst); ds = [ds_src | ds_dst] [n_rows, 2*heads].
  * workspace (both directions): b200gat_dense_workspace_bytes.
@@ -130,25 +138,39 @@ int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, i
                          const int32_t* perm, int64_t row_offset, int heads, int channels, int policy,
                          float negative_slope, const float* bias, float* out, float* out_heads, float* rowstat,
                          float p_drop, uint64_t seed, void* stream);
+/* same, h stored as bf16 (b200gat_project_bf16); accumulation and outputs stay fp32 */
+int b200gat_edge_fwd_bf16(const void* h_bf16, const float* s, const int32_t* sched, int64_t n_sched,
+                          const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                          const int32_t* perm, int64_t row_offset, int heads, int channels, int policy,
+                          float negative_slope, const float* bias, float* out, float* out_heads, float* rowstat,
+                          float p_drop, uint64_t seed, void* stream);
 
 /* ---- (4) fused edge backward --------------------------------------------------------------------
  * Replaces autograd's replay of the lines above (loss.backward(), train_gat_custom.py:361).
  * node_prep : nodestat[r,h] = (s_dst, m, 1/D, t), t = (1/H) dout[r,:].out_heads[r,h,:]
  *             (for heads==1 pass out as out_heads, and bias to subtract it if it was added);
  *             dbias (nullable) = column sums of dout in a fixed order (GATConv bias gradient),
- *             workspace >= 1184*channels floats when dbias != NULL
+ *             workspace >= 1184*channels floats when dbias != NULL;
+ *             dout_bf16 (nullable) = bf16 copy of dout [n_rows, channels] for b200gat_edge_bwd_bf16
  * edge_bwd  : warp per SOURCE row over the CSC schedule: dh[r,:,:] = sum_i alpha_ij dout_i / H (no atomics),
  *             de[q,h] = d loss / d logit for CSC position q, ds_src[r*ld_ds + h] = sum_q de
  * ds_dst    : ds_dst[r*ld_ds + h] = sum over the in-edges of r (CSR order) of de[csr2csc[e], h]
  */
 int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
                           const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
-                          float* nodestat, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+                          float* nodestat, float* dbias, void* dout_bf16, void* workspace, size_t workspace_bytes,
+                          void* stream);
 int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
                          const int32_t* sched, int64_t n_sched, const int32_t* long_table, int64_t n_long,
                          float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset, int heads,
                          int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
                          int ld_ds, float p_drop, uint64_t seed, void* stream);
+/* same, with h and the gathered dout stored as bf16 */
+int b200gat_edge_bwd_bf16(const void* h_bf16, const float* s, const void* dout_bf16, const float* nodestat,
+                          const int32_t* sched, int64_t n_sched, const int32_t* long_table, int64_t n_long,
+                          float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset, int heads,
+                          int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
+                          int ld_ds, float p_drop, uint64_t seed, void* stream);
 int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int heads,
                        float* ds_dst, int ld_ds, void* stream);
 

@@ -14,6 +14,8 @@
 //
 // Row width is H*C floats with C a multiple of 128 (lane l owns channels [4l,4l+4) of every
 // 128-wide chunk), H in {1,2,4}.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/b200gat.h"
 
@@ -54,6 +56,18 @@ __device__ __forceinline__ float activate(float z0, float neg_slope) {
   return z;
 }
 
+// One lane's 4-channel piece of a feature row, as stored (fp32: 16 B, bf16: 8 B) and as computed on (float4).
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+__device__ __forceinline__ float4 ld_raw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint2 ld_raw4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 to_f4(float4 v) { return v; }
+__device__ __forceinline__ float4 to_f4(uint2 v) {   // bf16 -> fp32 is a 16-bit shift
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+
 template <int H, int CV>
 struct Unroll {
   static constexpr int value = (H * CV >= 8) ? 1 : (H * CV >= 4 ? 2 : (H * CV >= 2 ? 4 : 8));
@@ -81,9 +95,9 @@ __global__ void build_schedule_kernel(const int32_t* __restrict__ ptr, const int
 // --------------------------------------------------------------------------------------------
 constexpr int kEdgeThreads = 128;
 
-template <int H, int CV>
+template <typename T, int H, int CV>
 struct RowBuf {
-  float4 v[H][CV];
+  typename Raw4<T>::type v[H][CV];
 };
 
 template <int POLICY, int H, int CV>
@@ -117,8 +131,8 @@ __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float 
   }
 }
 
-template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
+template <typename T, int POLICY, int H, int CV, bool DROPOUT>
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ col,
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
@@ -135,15 +149,15 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
   const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
   const int4 d = __ldg(sched + idx);
 
-  auto load_group = [&](RowBuf<H, CV>(&buf)[U], int c, int k) {
+  auto load_group = [&](RowBuf<T, H, CV>(&buf)[U], int c, int k) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int ck = __shfl_sync(kFull, c, (k + u) & 31);
-      const float* hp = h + (size_t)ck * HC + lane * 4;
+      const T* hp = h + (size_t)ck * HC + lane * 4;
 #pragma unroll
       for (int hh = 0; hh < H; ++hh)
 #pragma unroll
-        for (int cv = 0; cv < CV; ++cv) buf[u].v[hh][cv] = ldg4(hp + hh * C + cv * 128);
+        for (int cv = 0; cv < CV; ++cv) buf[u].v[hh][cv] = ld_raw4(hp + hh * C + cv * 128);
     }
   };
 
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
       const int c0 = __shfl_sync(kFull, c, 0);
       if (!valid) c = c0;
       const int cnt = min(32, end - base);
-      RowBuf<H, CV> bufA[U], bufB[U];
+      RowBuf<T, H, CV> bufA[U], bufB[U];
       load_group(bufA, c, 0);                              // gathers start before the softmax math
       if (U < cnt) load_group(bufB, c, U);
 
@@ -198,14 +212,14 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
         l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
         if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)__ldg(perm + e), hh, p_drop, inv_keep);
       }
-      auto consume = [&](RowBuf<H, CV>(&buf)[U], int k) {
+      auto consume = [&](RowBuf<T, H, CV>(&buf)[U], int k) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int hh = 0; hh < H; ++hh) {
             const float pk = __shfl_sync(kFull, p[hh], (k + u) & 31);
 #pragma unroll
-            for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk, buf[u].v[hh][cv], acc[hh][cv]);
+            for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk, to_f4(buf[u].v[hh][cv]), acc[hh][cv]);
           }
       };
       for (int k = 0; k < cnt; k += 2 * U) {
@@ -291,7 +305,8 @@ __global__ void __launch_bounds__(256) node_prep_kernel(const float* __restrict_
                                                         const float* __restrict__ bias,       // subtracted (H==1, PyG)
                                                         const float* __restrict__ s, const float2* __restrict__ rowstat,
                                                         int n_rows, int row_offset, float4* __restrict__ nodestat,
-                                                        float* __restrict__ colsum_part /*[gridDim.x, C] or null*/) {
+                                                        float* __restrict__ colsum_part /*[gridDim.x, C] or null*/,
+                                                        __nv_bfloat16* __restrict__ dout_bf16 /*[n_rows, C] or null*/) {
   constexpr int C = CV * 128;
   __shared__ float4 red[8][CV][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -309,6 +324,13 @@ __global__ void __launch_bounds__(256) node_prep_kernel(const float* __restrict_
 #pragma unroll
     for (int cv = 0; cv < CV; ++cv) {
       const float4 g = ld_stream4(dout + (size_t)r * C + cv * 128 + lane * 4);
+      if (dout_bf16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dout_bf16 + (size_t)r * C + cv * 128 + lane * 4) = pk;
+      }
       csum[cv].x += g.x; csum[cv].y += g.y; csum[cv].z += g.z; csum[cv].w += g.w;
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) {
@@ -369,9 +391,9 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
 // --------------------------------------------------------------------------------------------
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
-template <int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_kernel(const float* __restrict__ h, const float* __restrict__ s,
-                                                                const float* __restrict__ dout,
+template <typename T, int POLICY, int H, int CV, bool DROPOUT>
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+                                                                const T* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ row,
@@ -390,13 +412,13 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
   constexpr float invH = 1.f / H;
   const int4 d = __ldg(sched + idx);
 
-  struct GBuf { float4 g[CV]; };
+  struct GBuf { typename Raw4<T>::type g[CV]; };
   auto load_group = [&](GBuf(&buf)[U], int i, int k) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int ik = __shfl_sync(kFull, i, (k + u) & 31);
 #pragma unroll
-      for (int cv = 0; cv < CV; ++cv) buf[u].g[cv] = ldg4(dout + (size_t)ik * C + cv * 128 + lane * 4);
+      for (int cv = 0; cv < CV; ++cv) buf[u].g[cv] = ld_raw4(dout + (size_t)ik * C + cv * 128 + lane * 4);
     }
   };
 
@@ -412,7 +434,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
       dss[hh] = 0.f;
 #pragma unroll
       for (int cv = 0; cv < CV; ++cv) {
-        hj[hh][cv] = (beg < end) ? ldg4(h + j * HC + hh * C + cv * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hj[hh][cv] = (beg < end) ? to_f4(ld_raw4(h + j * HC + hh * C + cv * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         acc[hh][cv] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -458,8 +480,9 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
             float dsum = 0.f;
 #pragma unroll
             for (int cv = 0; cv < CV; ++cv) {
-              acc[hh][cv] = fma4(a, buf[u].g[cv], acc[hh][cv]);
-              dsum += dot4(hj[hh][cv], buf[u].g[cv]);
+              const float4 gv = to_f4(buf[u].g[cv]);
+              acc[hh][cv] = fma4(a, gv, acc[hh][cv]);
+              dsum += dot4(hj[hh][cv], gv);
             }
             dsum = warp_sum(dsum) * invH;  // d(out)/d(alpha'_ij) for this head
             if (lane == kk && k + u < cnt) my_de[hh] = alpha[hh] * (dsum * ks[hh] - tt[hh]) * gsc[hh];
@@ -635,11 +658,11 @@ extern "C" int b200gat_build_schedule(const int32_t* ptr, int64_t n_rows, int64_
   return kOk;
 }
 
-extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, int64_t n_rows,
-                                    const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
-                                    const int32_t* perm, int64_t row_offset, int heads, int channels,
-                                    int policy, float negative_slope, const float* bias, float* out, float* out_heads,
-                                    float* rowstat, float p_drop, uint64_t seed, void* stream) {
+template <typename T>
+static int edge_fwd_impl(const T* h, const float* s, const int32_t* sched, int64_t n_rows, const int32_t* long_table,
+                         int64_t n_long, float* partial, const int32_t* col, const int32_t* perm, int64_t row_offset, int heads,
+                         int channels, int policy, float negative_slope, const float* bias, float* out, float* out_heads,
+                         float* rowstat, float p_drop, uint64_t seed, void* stream) {
   B200GAT_CHECK_ARG(h && s && sched && out, "null pointer");
   B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
@@ -654,9 +677,9 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
   int grid = 0;
 #define LAUNCH_FWD(P, D)                                                                                                \
   do {                                                                                                                  \
-    rc = persistent_grid(edge_fwd_kernel<P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                                  \
+    rc = persistent_grid(edge_fwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                               \
     if (rc) return rc;                                                                                                  \
-    count_launch(), edge_fwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                      \
+    count_launch(), edge_fwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                   \
         h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,        \
         (float2*)rowstat, partial, p_drop, seed);                                                                       \
     if (n_long > 0)                                                                                                     \
@@ -672,10 +695,30 @@ extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_
   return kOk;
 }
 
+extern "C" int b200gat_edge_fwd_f32(const float* h, const float* s, const int32_t* sched, int64_t n_rows,
+                                    const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                    const int32_t* perm, int64_t row_offset, int heads, int channels,
+                                    int policy, float negative_slope, const float* bias, float* out, float* out_heads,
+                                    float* rowstat, float p_drop, uint64_t seed, void* stream) {
+  return edge_fwd_impl<float>(h, s, sched, n_rows, long_table, n_long, partial, col, perm, row_offset, heads, channels, policy,
+                              negative_slope, bias, out, out_heads, rowstat, p_drop, seed, stream);
+}
+// same with the gathered matrix h stored as bf16 (half the gather bytes; fp32 accumulation and outputs)
+extern "C" int b200gat_edge_fwd_bf16(const void* h_bf16, const float* s, const int32_t* sched, int64_t n_rows,
+                                     const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                     const int32_t* perm, int64_t row_offset, int heads, int channels,
+                                     int policy, float negative_slope, const float* bias, float* out, float* out_heads,
+                                     float* rowstat, float p_drop, uint64_t seed, void* stream) {
+  return edge_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)h_bf16, s, sched, n_rows, long_table, n_long, partial, col, perm,
+                                      row_offset, heads, channels, policy, negative_slope, bias, out, out_heads, rowstat, p_drop,
+                                      seed, stream);
+}
+
 // dbias (nullable): column sums of dout in a fixed order; workspace >= 8*148*channels floats when dbias != NULL
 extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, const float* bias, const float* s,
                                      const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, int channels,
-                                     float* nodestat, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+                                     float* nodestat, float* dbias, void* dout_bf16, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   B200GAT_CHECK_ARG(dout && out_heads && s && rowstat && nodestat, "null pointer");
   int rc = check_shape(heads, channels);
   if (rc) return rc;
@@ -692,19 +735,18 @@ extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, 
   B200GAT_DISPATCH_HC(heads, cv, {
     count_launch(), node_prep_kernel<kH, kCV><<<grid, 256, 0, st>>>(dout, out_heads, bias, s, (const float2*)rowstat, (int)n_rows,
                                                                    (int)row_offset, (float4*)nodestat,
-                                                                   dbias ? (float*)workspace : nullptr);
+                                                                   dbias ? (float*)workspace : nullptr, (__nv_bfloat16*)dout_bf16);
   })
   if (dbias) count_launch(), colsum_finish_kernel<<<1, 1024, 0, st>>>((const float*)workspace, grid, channels, dbias);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
 
-extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
-                                    const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
-                                    float* partial, const int32_t* row, const int32_t* perm_csc,
-                                    int64_t row_offset, int heads, int channels, int policy, float negative_slope,
-                                    float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
-                                    void* stream) {
+template <typename T>
+static int edge_bwd_impl(const T* h, const float* s, const T* dout, const float* nodestat, const int32_t* sched, int64_t n_rows,
+                         const int32_t* long_table, int64_t n_long, float* partial, const int32_t* row, const int32_t* perm_csc,
+                         int64_t row_offset, int heads, int channels, int policy, float negative_slope, float* dh, float* de,
+                         float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream) {
   B200GAT_CHECK_ARG(h && s && dout && nodestat && sched && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
   B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
@@ -719,9 +761,9 @@ extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float*
   int grid = 0;
 #define LAUNCH_BWD(P, D)                                                                                               \
   do {                                                                                                                 \
-    rc = persistent_grid(edge_bwd_kernel<P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                                 \
+    rc = persistent_grid(edge_bwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                              \
     if (rc) return rc;                                                                                                 \
-    count_launch(), edge_bwd_kernel<P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                     \
+    count_launch(), edge_bwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                  \
         h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,          \
         negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                                 \
     if (n_long > 0)                                                                                                    \
@@ -735,6 +777,27 @@ extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float*
 #undef LAUNCH_BWD
   B200GAT_LAUNCH_CHECK();
   return kOk;
+}
+
+extern "C" int b200gat_edge_bwd_f32(const float* h, const float* s, const float* dout, const float* nodestat,
+                                    const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
+                                    float* partial, const int32_t* row, const int32_t* perm_csc,
+                                    int64_t row_offset, int heads, int channels, int policy, float negative_slope,
+                                    float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
+                                    void* stream) {
+  return edge_bwd_impl<float>(h, s, dout, nodestat, sched, n_rows, long_table, n_long, partial, row, perm_csc, row_offset, heads,
+                              channels, policy, negative_slope, dh, de, ds_src, ld_ds, p_drop, seed, stream);
+}
+// same with h and the gathered dout stored as bf16 (dout_bf16 is written by b200gat_node_prep_f32)
+extern "C" int b200gat_edge_bwd_bf16(const void* h_bf16, const float* s, const void* dout_bf16, const float* nodestat,
+                                     const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
+                                     float* partial, const int32_t* row, const int32_t* perm_csc,
+                                     int64_t row_offset, int heads, int channels, int policy, float negative_slope,
+                                     float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
+                                     void* stream) {
+  return edge_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)h_bf16, s, (const __nv_bfloat16*)dout_bf16, nodestat, sched, n_rows,
+                                      long_table, n_long, partial, row, perm_csc, row_offset, heads, channels, policy,
+                                      negative_slope, dh, de, ds_src, ld_ds, p_drop, seed, stream);
 }
 
 extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows,

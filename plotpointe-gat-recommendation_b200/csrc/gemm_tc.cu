@@ -23,6 +23,8 @@
 //
 // Shapes: in_features = 128 and channels = 128 per head (heads handled as grid.y for proj_fwd);
 // anything else is served by dense_simt.cu.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/b200gat.h"
 
@@ -392,6 +394,186 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// proj_bf16 : h_bf16[n,128] = bf16(x) . bf16(W)^T with fp32 accumulation ("bf16 projection", BASELINE config 3).
+// Operands are rounded to bf16 while they are staged (no split: one UMMA kind::f16 per K step of 16), h is stored as
+// bf16 -- the edge kernels then gather 256-byte rows -- and the logits are still taken from the fp32 accumulator.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHKB = 64;                                    // bf16 elements per 128-byte swizzle row
+constexpr int kHStages = 4;
+constexpr int kHAStageBytes = kTileM * 128;                 // 16 KB
+constexpr int kHBImageBytes = (kK / kHKB) * kTileN * 128;   // 32 KB
+constexpr int kHSmem = 1024 + kHBImageBytes + kHStages * kHAStageBytes + 2 * kTileN * 4 + 256;
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float4& a, const float4& b) {
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&p0); r.y = *reinterpret_cast<const uint32_t*>(&p1);
+  r.z = *reinterpret_cast<const uint32_t*>(&p2); r.w = *reinterpret_cast<const uint32_t*>(&p3);
+  return r;
+}
+
+// image[kb][row n][64 bf16 swizzled] of W[n, k]
+__global__ void build_b_image_bf16_kernel(const float* __restrict__ w, uint8_t* __restrict__ image) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk (8 consecutive k) each
+  if (idx >= kTileN * kK / 8) return;
+  const int n = idx / (kK / 8), k8 = idx % (kK / 8);
+  const int kb = k8 / 8, chunk = k8 % 8;
+  const float4 a = *reinterpret_cast<const float4*>(w + n * kK + k8 * 8);
+  const float4 b = *reinterpret_cast<const float4*>(w + n * kK + k8 * 8 + 4);
+  *reinterpret_cast<uint4*>(image + kb * (kTileN * 128) + sw128(n, chunk)) = pack8_bf16(a, b);
+}
+
+struct HParams {
+  const float* a;          // x [n_rows, 128] fp32
+  const uint8_t* b_images; // [heads][kHBImageBytes]
+  __nv_bfloat16* out;      // h [n_rows, heads*128] bf16
+  int64_t n_rows;
+  const float* att_src;
+  const float* att_dst;
+  float* s;
+  int heads;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1) proj_bf16_kernel(HParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sB = base;
+  const uint32_t sA = sB + kHBImageBytes;
+  float* att = reinterpret_cast<float*>(sm + kHBImageBytes + kHStages * kHAStageBytes);
+  const uint32_t sBar = sA + kHStages * kHAStageBytes + 2 * kTileN * 4;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 32, bar_tfull = sBar + 64, bar_tempty = sBar + 80, bar_b = sBar + 96;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 112);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int64_t n_tiles = (p.n_rows + kTileM - 1) / kTileM;
+  const int64_t ldo = (int64_t)p.heads * kTileN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kHStages; ++i) {
+      mbar_init(bar_full + 8 * i, kFwdProducerWarps * 32);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, kFwdEpiWarps * 32);
+    }
+    mbar_init(bar_b, 1);
+    fence_barrier_init();
+  }
+  if (warp == kFwdProducerWarps + kFwdEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+  for (int i = threadIdx.x; i < 2 * kTileN; i += kFwdThreads)
+    att[i] = i < kTileN ? p.att_src[head * kTileN + i] : p.att_dst[head * kTileN + i - kTileN];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < kFwdProducerWarps) {
+    const int t = threadIdx.x;
+    const int chunk = t & 7, r0 = t >> 3;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * kTileM;
+      for (int kb = 0; kb < kK / kHKB; ++kb) {
+        float4 v[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row0 + r0 + 16 * i;
+          if (row < p.n_rows) {
+            v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
+            v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
+          } else {
+            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        uint8_t* dst = sm + kHBImageBytes + stage * kHAStageBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 16 * i, chunk)) = pack8_bf16(v[i][0], v[i][1]);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * stage);
+        if (++stage == kHStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_b, kHBImageBytes);
+      bulk_g2s(sB, p.b_images + (size_t)head * kHBImageBytes, kHBImageBytes, bar_b);
+      mbar_wait(bar_b, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, kTileN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * kTileN;
+        for (int kb = 0; kb < kK / kHKB; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a0 = sA + stage * kHAStageBytes, b0 = sB + kb * kTileN * 128;
+#pragma unroll
+          for (int k = 0; k < kHKB / 16; ++k)
+            umma_bf16(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc, (kb | k) != 0);
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == kHStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row = tile * kTileM + q * 32 + lane;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      float ps = 0.f, pd = 0.f;
+      for (int c = 0; c < kTileN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ps = fmaf(v[j], att[c * 32 + j], ps);
+          pd = fmaf(v[j], att[kTileN + c * 32 + j], pd);
+        }
+        if (row < p.n_rows) {   // 64 contiguous bytes of this thread's row
+          uint4* o = reinterpret_cast<uint4*>(p.out + row * ldo + head * kTileN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack8_bf16(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                              make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      if (row < p.n_rows) {
+        p.s[row * (2 * p.heads) + head] = ps;
+        p.s[row * (2 * p.heads) + p.heads + head] = pd;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kFwdProducerWarps + kFwdEpiWarps) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
 // proj_dw : dW[c, f] = sum_n dh_full[n, c] * x[n, f]   (+ v[q, f] = sum_n ds[n, q] x[n, f])
 // ------------------------------------------------------------------------------------------------
 constexpr int kDwProducerWarps = 8, kDwEpiWarps = 4;
@@ -650,6 +832,7 @@ static int ensure_attrs() {
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
+  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kHSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDwSmem));
   done = true;
   return kOk;
@@ -754,6 +937,35 @@ int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, voi
 }
 
 }  // namespace b200gat
+
+// h_bf16 [n, heads*128] = bf16(x) bf16(W)^T (fp32 accumulate), s = fp32 row dots of the accumulator with a_src / a_dst
+extern "C" int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                                    int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  using namespace b200gat;
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && h_bf16 && s && workspace, "null pointer");
+  if (in_features != 128 || channels != 128) {
+    set_error("bf16 projection needs in_features == channels == 128 (got %d, %d)", in_features, channels);
+    return kErrUnsupported;
+  }
+  B200GAT_CHECK_ARG(workspace_bytes >= (size_t)heads * tc::kHBImageBytes, "workspace too small");
+  if (n_rows == 0) return kOk;
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* images = (uint8_t*)workspace;
+  for (int hh = 0; hh < heads; ++hh)
+    count_launch(), tc::build_b_image_bf16_kernel<<<ceil_div(128 * 128 / 8, 256), 256, 0, st>>>(
+        W + (size_t)hh * 128 * 128, images + (size_t)hh * tc::kHBImageBytes);
+  tc::HParams p{};
+  p.a = x; p.b_images = images; p.out = (__nv_bfloat16*)h_bf16; p.n_rows = n_rows;
+  p.att_src = a_src; p.att_dst = a_dst; p.s = s; p.heads = heads;
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  dim3 grid((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), heads);
+  count_launch(), tc::proj_bf16_kernel<<<grid, tc::kFwdThreads, tc::kHSmem, st>>>(p);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
 
 extern "C" int b200gat_set_gemm_mode(int mode) {
   B200GAT_CHECK_ARG(mode == B200GAT_GEMM_FP32 || mode == B200GAT_GEMM_TF32X3, "unsupported gemm mode %d", mode);

@@ -9,7 +9,7 @@ from . import _lib
 from .graph import GraphStructure
 
 
-def _empty(shape, like, dtype=torch.float32):
+def _empty(shape, like, dtype=torch.float32):  # noqa: D401
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
@@ -23,7 +23,7 @@ class GATLayerFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, a_src, a_dst, bias, graph: GraphStructure, heads: int, channels: int, policy: int,
-                negative_slope: float, p_drop: float, seed: int):
+                negative_slope: float, p_drop: float, seed: int, bf16: bool = False):
         if not x.is_cuda:
             raise RuntimeError("b200gat GAT layer: x must be a CUDA tensor (there is no CPU fallback)")
         x = _lib._f32(x, "x").contiguous()
@@ -38,32 +38,33 @@ class GATLayerFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:5])
         with torch.cuda.device(x.device):
             st = _lib.stream()
-            h = _empty((n, heads * channels), x)
+            h = _empty((n, heads * channels), x, torch.bfloat16 if bf16 else torch.float32)
             s = _empty((n, 2 * heads), x)
             ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            _lib.call("b200gat_project_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), n, f_in, heads,
-                      channels, _lib.ptr(h), _lib.ptr(s), _lib.ptr(ws), ws_bytes, st)
+            _lib.call("b200gat_project_bf16" if bf16 else "b200gat_project_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s),
+                      _lib.ptr(a_d), n, f_in, heads, channels, _lib.ptr(h), _lib.ptr(s), _lib.ptr(ws), ws_bytes, st)
             out = _empty((n, channels), x)
             rowstat = _empty((n, heads, 2), x) if need_grad else None
             out_heads = _empty((n, heads, channels), x) if (need_grad and heads > 1) else None
             b = None if bias is None else _lib._f32(bias, "bias").contiguous()
             sf = graph.sched_fwd
-            _lib.call("b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(sf.sched), sf.n_sched, _lib.ptr(sf.table),
+            _lib.call("b200gat_edge_fwd_bf16" if bf16 else "b200gat_edge_fwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(sf.sched),
+                      sf.n_sched, _lib.ptr(sf.table),
                       sf.n_long, _lib.ptr(sf.partial(heads * (channels + 4))), _lib.ptr(graph.col), _lib.ptr(graph.perm), 0,
                       heads, channels, policy, negative_slope, _lib.ptr(b), _lib.ptr(out), _lib.ptr(out_heads),
                       _lib.ptr(rowstat), p_drop, seed, st)
         if need_grad:
             ctx.save_for_backward(x, weight, a_s, a_d, b, h, s, rowstat, out if heads == 1 else out_heads)
             ctx.graph = graph
-            ctx.cfg = (heads, channels, policy, negative_slope, p_drop, seed)
+            ctx.cfg = (heads, channels, policy, negative_slope, p_drop, seed, bf16)
             ctx.att_shape = (a_src.shape, a_dst.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, weight, a_s, a_d, b, h, s, rowstat, out_h = ctx.saved_tensors
-        heads, channels, policy, negative_slope, p_drop, seed = ctx.cfg
+        heads, channels, policy, negative_slope, p_drop, seed, bf16 = ctx.cfg
         g = ctx.graph
         n, f_in = x.shape
         dout = dout.contiguous()
@@ -73,14 +74,16 @@ class GATLayerFunction(torch.autograd.Function):
             ws_bytes = _lib.dense_workspace_bytes(heads, channels, f_in)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             dbias = torch.empty_like(b) if (b is not None and ctx.needs_input_grad[4]) else None
+            dout_g = _empty((n, channels), x, torch.bfloat16) if bf16 else None   # bf16 copy that the edge kernel gathers
             _lib.call("b200gat_node_prep_f32", _lib.ptr(dout), _lib.ptr(out_h), _lib.ptr(b if heads == 1 else None),
                       _lib.ptr(s), _lib.ptr(rowstat), n, 0, heads, channels, _lib.ptr(nodestat), _lib.ptr(dbias),
-                      _lib.ptr(ws), ws_bytes, st)
+                      _lib.ptr(dout_g), _lib.ptr(ws), ws_bytes, st)
             dh = _empty((n, heads * channels), x)
             de = _empty((max(g.n_edges, 1), heads), x)
             ds = _empty((n, 2 * heads), x)
             sb = g.sched_bwd
-            _lib.call("b200gat_edge_bwd_f32", _lib.ptr(h), _lib.ptr(s), _lib.ptr(dout), _lib.ptr(nodestat),
+            _lib.call("b200gat_edge_bwd_bf16" if bf16 else "b200gat_edge_bwd_f32", _lib.ptr(h), _lib.ptr(s),
+                      _lib.ptr(dout_g if bf16 else dout), _lib.ptr(nodestat),
                       _lib.ptr(sb.sched), sb.n_sched, _lib.ptr(sb.table), sb.n_long,
                       _lib.ptr(sb.partial(heads * channels + 4)), _lib.ptr(g.row), _lib.ptr(g.perm_csc), 0, heads, channels,
                       policy, negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
@@ -95,7 +98,7 @@ class GATLayerFunction(torch.autograd.Function):
                       _lib.ptr(ds), n, f_in, heads, channels, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(da_s), _lib.ptr(da_d),
                       _lib.ptr(ws), ws_bytes, st)
         sa, sd = ctx.att_shape
-        return dx, dw, da_s.view(sa), da_d.view(sd), dbias, None, None, None, None, None, None, None
+        return dx, dw, da_s.view(sa), da_d.view(sd), dbias, None, None, None, None, None, None, None, None
 
 
 class NodeFeaturesFunction(torch.autograd.Function):
@@ -143,9 +146,14 @@ def node_features(user_w, proj_w, proj_b, item_feats):
     return NodeFeaturesFunction.apply(user_w, proj_w, proj_b, item_feats)
 
 
-def gat_layer(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, negative_slope=0.2, p_drop=0.0, seed=0):
+def gat_layer(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, negative_slope=0.2, p_drop=0.0, seed=0,
+              feature_dtype=torch.float32):
+    """``feature_dtype=torch.bfloat16`` selects the bf16 projection: h (and the dout copy the backward gathers) are stored as
+    bf16, everything is accumulated and returned in fp32 (tolerance tier 2e-2 instead of 1e-5)."""
+    if feature_dtype not in (torch.float32, torch.bfloat16):
+        raise NotImplementedError(f"feature_dtype {feature_dtype} is not supported (float32 or bfloat16)")
     return GATLayerFunction.apply(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, float(negative_slope),
-                                  float(p_drop), int(seed))
+                                  float(p_drop), int(seed), feature_dtype == torch.bfloat16)
 
 
 class RankLossFunction(torch.autograd.Function):

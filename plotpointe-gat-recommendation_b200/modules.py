@@ -28,8 +28,9 @@ def _dropout_seed(training: bool, p: float) -> int:
 class SimpleGATLayer(torch.nn.Module):
     """Single-head GAT layer with the reference's custom softmax dialect (train_gat_custom.py:63-93)."""
 
-    def __init__(self, in_dim: int, out_dim: int, attn_dropout: float = 0.1):
+    def __init__(self, in_dim: int, out_dim: int, attn_dropout: float = 0.1, feature_dtype=torch.float32):
         super().__init__()
+        self.feature_dtype = feature_dtype      # torch.bfloat16: bf16 projection / bf16 gathers (not in the reference API)
         self.lin = torch.nn.Linear(in_dim, out_dim, bias=False)
         self.a_src = torch.nn.Parameter(torch.empty(out_dim))
         self.a_dst = torch.nn.Parameter(torch.empty(out_dim))
@@ -43,7 +44,7 @@ class SimpleGATLayer(torch.nn.Module):
         graph = graph_for(edge_index, x.shape[0])
         p = self.attn_dropout if self.training else 0.0
         return gat_layer(x, self.lin.weight, self.a_src, self.a_dst, None, graph, 1, self.out_dim, _lib.POLICY_CUSTOM,
-                         0.2, p, _dropout_seed(self.training, p))
+                         0.2, p, _dropout_seed(self.training, p), self.feature_dtype)
 
 
 class GATConv(torch.nn.Module):
@@ -53,8 +54,9 @@ class GATConv(torch.nn.Module):
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
                  negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True, edge_dim=None,
-                 fill_value="mean", bias: bool = True, residual: bool = False, **kwargs):
+                 fill_value="mean", bias: bool = True, residual: bool = False, feature_dtype=torch.float32, **kwargs):
         super().__init__()
+        self.feature_dtype = feature_dtype      # torch.bfloat16: bf16 projection / bf16 gathers (not a PyG argument)
         if kwargs:
             raise NotImplementedError(f"GATConv: unsupported arguments {sorted(kwargs)}")
         if not isinstance(in_channels, int):
@@ -108,7 +110,7 @@ class GATConv(torch.nn.Module):
         graph = graph_for(edge_index, x.shape[0])
         p = self.dropout if self.training else 0.0
         return gat_layer(x, self.lin.weight, self.att_src, self.att_dst, self.bias, graph, self.heads, self.out_channels,
-                         _lib.POLICY_PYG, self.negative_slope, p, _dropout_seed(self.training, p))
+                         _lib.POLICY_PYG, self.negative_slope, p, _dropout_seed(self.training, p), self.feature_dtype)
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"
@@ -117,13 +119,13 @@ class GATConv(torch.nn.Module):
 class CustomGAT(torch.nn.Module):
     """scripts/train_gat_custom.py:96-115 with the layers swapped for the B200 ones."""
 
-    def __init__(self, n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int):
+    def __init__(self, n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int, feature_dtype=torch.float32):
         super().__init__()
         self.n_users, self.n_items = n_users, n_items
         self.user_emb = torch.nn.Embedding(n_users, hidden)
         torch.nn.init.normal_(self.user_emb.weight, std=0.1)
         self.item_proj = torch.nn.Linear(item_feat_dim, hidden)
-        self.layers = torch.nn.ModuleList([SimpleGATLayer(hidden, hidden) for _ in range(layers)])
+        self.layers = torch.nn.ModuleList([SimpleGATLayer(hidden, hidden, feature_dtype=feature_dtype) for _ in range(layers)])
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
         # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy
@@ -140,7 +142,7 @@ class PyGGAT(torch.nn.Module):
     """scripts/train_gat_pyg.py:68-88 with ``GATConv`` swapped for the B200 one."""
 
     def __init__(self, n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int, heads: int,
-                 attn_dropout: float):
+                 attn_dropout: float, feature_dtype=torch.float32):
         super().__init__()
         self.n_users, self.n_items = n_users, n_items
         self.user_emb = torch.nn.Embedding(n_users, hidden)
@@ -149,7 +151,7 @@ class PyGGAT(torch.nn.Module):
         self.convs = torch.nn.ModuleList()
         for _ in range(layers):
             self.convs.append(GATConv(hidden, hidden, heads=heads, dropout=attn_dropout, add_self_loops=False,
-                                      concat=False))
+                                      concat=False, feature_dtype=feature_dtype))
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
         # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy

@@ -225,7 +225,7 @@ class ShardedGAT:
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
-                     lib.ptr(dws), dwb, st)
+                     None, lib.ptr(dws), dwb, st)
             dout_full = all_gather_rows(dout, self.world)
             nodestat_full = all_gather_rows(nodestat, self.world)
             dh = self._empty(self.n_loc, H * C)

@@ -420,3 +420,35 @@ def test_config1_shape_against_oracle(dev, kind, loss_name):
                 assert rel(p.grad.cpu().double(), g64[k_]) <= bound, (mode, k_, rel(p.grad.cpu().double(), g64[k_]), bound)
     finally:
         _lib.set_gemm_mode(_lib.GEMM_TF32X3)
+
+
+@pytest.mark.parametrize("kind,heads", [("custom", 1), ("pyg", 1), ("pyg", 4)])
+def test_bf16_projection_tier(dev, kind, heads):
+    """BASELINE config 3 ("bf16 projection"): h and the gathered dout are stored as bf16, accumulation in fp32.
+    Tolerance tier of the north star for bf16: rtol 2e-2 (against the fp64 oracle, floor 2e-2 x max|ref|)."""
+    import b200gat
+    from b200gat import synth
+    nu, ni, n_inter, k = 3000, 5000, 40000, 8
+    ei, feats = synth.make_graph(nu, ni, n_inter, k)
+    u, i, j = synth.make_triples(nu, ni, 20000)
+    torch.manual_seed(5)
+    m = (b200gat.CustomGAT(nu, ni, 128, 128, 2, feature_dtype=torch.bfloat16) if kind == "custom"
+         else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1, feature_dtype=torch.bfloat16)).eval()
+    st = {k_: v.detach().double().requires_grad_(True) for k_, v in m.state_dict().items()}
+    z_ref = O.custom_gat_forward(st, feats.double(), ei) if kind == "custom" else O.pyg_gat_forward(st, feats.double(), ei, heads)
+    l_ref = O.bce_loss(z_ref, nu, u, i, j)
+    l_ref.backward()
+    m = m.to(dev)
+    z = m(feats.to(dev), ei.to(dev))
+    assert z.dtype == torch.float32
+    loss = b200gat.bce_loss(z, nu, u.to(dev), i.to(dev), j.to(dev))
+    loss.backward()
+    close(z, z_ref, rtol=2e-2, name="z")
+    np.testing.assert_allclose(loss.item(), l_ref.item(), rtol=2e-2)
+    for k_, p in m.named_parameters():
+        close(p.grad, st[k_].grad, rtol=2e-2, name=k_)
+    # and it is a different computation from the fp32 tier (bf16 rounding is visible at 1e-5)
+    m32 = (b200gat.CustomGAT(nu, ni, 128, 128, 2) if kind == "custom" else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1)).to(dev).eval()
+    m32.load_state_dict(m.state_dict())
+    z32 = m32(feats.to(dev), ei.to(dev))
+    assert (z32 - z).abs().max() > 1e-6 * z32.abs().max()

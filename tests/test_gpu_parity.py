@@ -446,7 +446,14 @@ def test_bf16_projection_tier(dev, kind, heads):
     close(z, z_ref, rtol=2e-2, name="z")
     np.testing.assert_allclose(loss.item(), l_ref.item(), rtol=2e-2)
     for k_, p in m.named_parameters():
-        close(p.grad, st[k_].grad, rtol=2e-2, name=k_)
+        ref_g = st[k_].grad
+        scale = float(ref_g.abs().max())
+        if k_.endswith("att_dst") or k_.endswith("a_dst"):
+            # a per-destination logit shift cancels in the softmax (only the LeakyReLU kink leaks through), so this
+            # gradient is ~0 by construction: judge it on the scale of its att_src twin
+            scale = max(scale, float(st[k_.replace("dst", "src")].grad.abs().max()))
+        err = float((p.grad.detach().cpu().double() - ref_g).abs().max())
+        assert err <= 2e-2 * scale, (k_, err, scale)
     # and it is a different computation from the fp32 tier (bf16 rounding is visible at 1e-5)
     m32 = (b200gat.CustomGAT(nu, ni, 128, 128, 2) if kind == "custom" else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1)).to(dev).eval()
     m32.load_state_dict(m.state_dict())

@@ -434,6 +434,10 @@ def test_bf16_projection_tier(dev, kind, heads):
     torch.manual_seed(5)
     m = (b200gat.CustomGAT(nu, ni, 128, 128, 2, feature_dtype=torch.bfloat16) if kind == "custom"
          else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1, feature_dtype=torch.bfloat16)).eval()
+    with torch.no_grad():          # sharpen the attention: near-uniform attention makes every logit gradient a ~0 difference
+        for lay in (m.layers if kind == "custom" else m.convs):
+            (lay.a_src if kind == "custom" else lay.att_src).mul_(6.0)
+        m.user_emb.weight.mul_(3.0)
     st = {k_: v.detach().double().requires_grad_(True) for k_, v in m.state_dict().items()}
     z_ref = O.custom_gat_forward(st, feats.double(), ei) if kind == "custom" else O.pyg_gat_forward(st, feats.double(), ei, heads)
     l_ref = O.bce_loss(z_ref, nu, u, i, j)

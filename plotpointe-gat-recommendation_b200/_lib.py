@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gat.so")
+LIB_PATH = os.environ.get("B200GAT_LIB", os.path.join(_HERE, "libb200gat.so"))   # override: A/B builds of the library
 
 POLICY_CUSTOM, POLICY_PYG = 0, 1
 LOSS_BPR, LOSS_BCE = 0, 1

@@ -94,6 +94,16 @@ __global__ void build_schedule_kernel(const int32_t* __restrict__ ptr, const int
 // forward
 // --------------------------------------------------------------------------------------------
 constexpr int kEdgeThreads = 128;
+// tuning knobs (A/B builds): rows per load group for the H*C == 128 instantiation, minimum resident blocks per SM
+#ifndef EDGE_U_FWD
+#define EDGE_U_FWD 4
+#endif
+#ifndef EDGE_U_BWD
+#define EDGE_U_BWD 4
+#endif
+#ifndef EDGE_MINB
+#define EDGE_MINB 8
+#endif
 
 template <typename T, int H, int CV>
 struct RowBuf {
@@ -132,7 +142,7 @@ __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float 
 }
 
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : 1) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ col,
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
@@ -142,7 +152,8 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_fwd_
                                                                 float p_drop, uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  constexpr int U = (H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : 4);   // rows per load group; two groups in flight
+  // rows per load group; two groups in flight.  bf16 rows are half the registers, so twice the rows are kept in flight
+  constexpr int U = ((H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : EDGE_U_FWD)) * (sizeof(T) == 2 ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
   if (idx >= n_rows) return;
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : 1) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const T* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
                                                                 const int4* __restrict__ sched,
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? 8 : 1) edge_bwd_
                                                                 uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  constexpr int U = CV >= 2 ? 2 : 4;   // dout rows per load group; two groups in flight
+  constexpr int U = (CV >= 2 ? 2 : EDGE_U_BWD) * (sizeof(T) == 2 ? 2 : 1);   // dout rows per load group; two groups in flight
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
   if (idx >= n_rows) return;

@@ -86,11 +86,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(n, e, h, c, dropout):
-    """Gather-model bytes per launch of the two edge kernels."""
-    fwd = e * (4 + 4 * h + h * c * 4 + (4 if dropout else 0)) + n * (4 + 4 * h + 4 * c + 8 * h)
-    bwd = e * (4 + 16 * h + 4 * c + 4 * h + (4 if dropout else 0)) + n * (4 + 2 * h * c * 4 + 8 * h)
-    return {"b200gat_edge_fwd_f32": fwd, "b200gat_edge_bwd_f32": bwd}
+def algorithmic_bytes(n, e, h, c, dropout, row_bytes=4):
+    """Gather-model bytes per launch of the two edge kernels.  row_bytes = bytes per
+    element of the gathered matrix (4: fp32 tier, 2: bf16 tier)."""
+    s = row_bytes
+    fwd = e * (4 + 4 * h + h * c * s + (4 if dropout else 0)) + n * (16 + 4 * h + 4 * c + 8 * h)
+    bwd = e * (4 + 16 * h + c * s + 4 * h + (4 if dropout else 0)) + n * (16 + h * c * s + h * c * 4 + 8 * h)
+    sfx = "bf16" if row_bytes == 2 else "f32"
+    return {f"b200gat_edge_fwd_{sfx}": fwd, f"b200gat_edge_bwd_{sfx}": bwd}
 
 
 # ----------------------------------------------------------------------------------------------------- ours
@@ -114,7 +117,9 @@ def run_ours(args):
     ei, feats = synth.make_graph(nu, ni, n_inter, k)
     e = int(ei.shape[1])
     torch.manual_seed(42)
-    model = b200gat.PyGGAT(nu, ni, 128, HIDDEN, LAYERS, heads=HEADS, attn_dropout=0.1).to(dev).train()
+    bf16 = args.tier == "bf16"
+    model = b200gat.PyGGAT(nu, ni, 128, HIDDEN, LAYERS, heads=HEADS, attn_dropout=0.1,
+                           feature_dtype=torch.bfloat16 if bf16 else torch.float32).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
     eid, fd = ei.to(dev), feats.to(dev)
     u, i, j = synth.make_triples(nu, ni, S_TRIPLES)
@@ -173,7 +178,7 @@ def run_ours(args):
         per_call[name] = {"calls_per_step": len(ts) / args.steps, "avg_ms": sum(ts) / len(ts),
                           "ms_per_step": sum(ts) / args.steps}
     pk, pk_kind = peaks()
-    alg = algorithmic_bytes(n, e, HEADS, HIDDEN, dropout=True)
+    alg = algorithmic_bytes(n, e, HEADS, HIDDEN, dropout=True, row_bytes=2 if bf16 else 4)
     edge_names = [k_ for k_ in alg if k_ in per_call]
     dom = max(edge_names, key=lambda k_: per_call[k_]["ms_per_step"])
     ach = alg[dom] / (per_call[dom]["avg_ms"] * 1e-3) / 1e9
@@ -194,7 +199,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": e * LAYERS / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{LAYERS}, d={HIDDEN}, heads={HEADS}, BPR on "
                                f"{S_TRIPLES} triples, train mode (attention dropout 0.1), Adam step; {nu} users, {ni} items, "
                                f"{n_inter} interactions + k={k} item kNN = {e} edges",
@@ -295,6 +300,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="amazon", choices=["amazon", "cfg1", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tier", default="f32", choices=["f32", "bf16"],
+                    help="f32 (headline, rtol 1e-5 tier) or bf16 projection (h / gathered dout stored as bf16, rtol 2e-2 tier)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -255,49 +255,63 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
 
   if (warp < kFwdProducerWarps) {
     // =========================== producers: A tiles =============================================
+    // Software pipelined: the global loads of k-block it+1 are in flight while k-block it is split and stored.
     const int t = threadIdx.x;          // 0..127
     const int chunk = t & 7, r0 = t >> 3;
-    uint32_t stage = 0, phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * kTileM;
-      for (int kb = 0; kb < kK / kKB; ++kb) {
-        float4 v[8];
-        float dsv[8][2];
+    constexpr int KB = kK / kKB;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_it = my_tiles * KB;
+    auto load = [&](int64_t it, float4(&v)[8], float(&dsv)[8][2]) {
+      const int64_t row0 = (blockIdx.x + (it / KB) * gridDim.x) * kTileM;
+      const int kb = (int)(it % KB);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + r0 + 16 * i;
+        if (row < p.n_rows) {
+          v[i] = ld_stream4(p.a + row * p.lda + kb * kKB + chunk * 4);
+          if (DX) { dsv[i][0] = __ldg(p.ds + row * 2); dsv[i][1] = __ldg(p.ds + row * 2 + 1); }
+        } else {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (DX) dsv[i][0] = dsv[i][1] = 0.f;
+        }
+      }
+    };
+    auto store = [&](int64_t it, float4(&v)[8], float(&dsv)[8][2]) {
+      const int kb = (int)(it % KB);
+      const uint32_t stage = (uint32_t)(it % kAStages), phase = (uint32_t)((it / kAStages) & 1);
+      if (DX) {  // dh_full = dh + ds_src * a_src + ds_dst * a_dst
+        const float4 as = *reinterpret_cast<const float4*>(att + kb * kKB + chunk * 4);
+        const float4 ad = *reinterpret_cast<const float4*>(att + kTileN + kb * kKB + chunk * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int64_t row = row0 + r0 + 16 * i;
-          if (row < p.n_rows) {
-            v[i] = ld_stream4(p.a + row * p.lda + kb * kKB + chunk * 4);
-            if (DX) { dsv[i][0] = __ldg(p.ds + row * 2); dsv[i][1] = __ldg(p.ds + row * 2 + 1); }
-          } else {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (DX) dsv[i][0] = dsv[i][1] = 0.f;
-          }
+          v[i].x += dsv[i][0] * as.x + dsv[i][1] * ad.x;
+          v[i].y += dsv[i][0] * as.y + dsv[i][1] * ad.y;
+          v[i].z += dsv[i][0] * as.z + dsv[i][1] * ad.z;
+          v[i].w += dsv[i][0] * as.w + dsv[i][1] * ad.w;
         }
-        if (DX) {  // dh_full = dh + ds_src * a_src + ds_dst * a_dst
-          const float4 as = *reinterpret_cast<const float4*>(att + kb * kKB + chunk * 4);
-          const float4 ad = *reinterpret_cast<const float4*>(att + kTileN + kb * kKB + chunk * 4);
+      }
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+      uint8_t* dst = sm + kBImageBytes + stage * kAStageBytes;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i].x += dsv[i][0] * as.x + dsv[i][1] * ad.x;
-            v[i].y += dsv[i][0] * as.y + dsv[i][1] * ad.y;
-            v[i].z += dsv[i][0] * as.z + dsv[i][1] * ad.z;
-            v[i].w += dsv[i][0] * as.w + dsv[i][1] * ad.w;
-          }
-        }
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        uint8_t* dst = sm + kBImageBytes + stage * kAStageBytes;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 hi, lo;
-          split4(v[i], hi, lo);
-          const uint32_t off = sw128(r0 + 16 * i, chunk);
-          *reinterpret_cast<float4*>(dst + off) = hi;
-          *reinterpret_cast<float4*>(dst + kTileM * 128 + off) = lo;
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * stage);
-        if (++stage == kAStages) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < 8; ++i) {
+        float4 hi, lo;
+        split4(v[i], hi, lo);
+        const uint32_t off = sw128(r0 + 16 * i, chunk);
+        *reinterpret_cast<float4*>(dst + off) = hi;
+        *reinterpret_cast<float4*>(dst + kTileM * 128 + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * stage);
+    };
+    float4 va[8], vb[8];
+    float da[8][2], db[8][2];
+    if (n_it > 0) load(0, va, da);
+    for (int64_t it = 0; it < n_it; it += 2) {
+      if (it + 1 < n_it) load(it + 1, vb, db);
+      store(it, va, da);
+      if (it + 1 < n_it) {
+        if (it + 2 < n_it) load(it + 2, va, da);
+        store(it + 1, vb, db);
       }
     }
   } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
@@ -484,28 +498,40 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_bf16_kernel(HParams p) {
   if (warp < kFwdProducerWarps) {
     const int t = threadIdx.x;
     const int chunk = t & 7, r0 = t >> 3;
-    uint32_t stage = 0, phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * kTileM;
-      for (int kb = 0; kb < kK / kHKB; ++kb) {
-        float4 v[8][2];
+    constexpr int KB = kK / kHKB;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_it = my_tiles * KB;
+    auto load = [&](int64_t it, float4(&v)[8][2]) {
+      const int64_t row0 = (blockIdx.x + (it / KB) * gridDim.x) * kTileM;
+      const int kb = (int)(it % KB);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t row = row0 + r0 + 16 * i;
-          if (row < p.n_rows) {
-            v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
-            v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
-          } else {
-            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + r0 + 16 * i;
+        if (row < p.n_rows) {
+          v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
+          v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
+        } else {
+          v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        uint8_t* dst = sm + kHBImageBytes + stage * kHAStageBytes;
+      }
+    };
+    auto store = [&](int64_t it, float4(&v)[8][2]) {
+      const uint32_t stage = (uint32_t)(it % kHStages), phase = (uint32_t)((it / kHStages) & 1);
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+      uint8_t* dst = sm + kHBImageBytes + stage * kHAStageBytes;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 16 * i, chunk)) = pack8_bf16(v[i][0], v[i][1]);
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * stage);
-        if (++stage == kHStages) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 16 * i, chunk)) = pack8_bf16(v[i][0], v[i][1]);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * stage);
+    };
+    float4 va[8][2], vb[8][2];
+    if (n_it > 0) load(0, va);
+    for (int64_t it = 0; it < n_it; it += 2) {
+      if (it + 1 < n_it) load(it + 1, vb);
+      store(it, va);
+      if (it + 1 < n_it) {
+        if (it + 2 < n_it) load(it + 2, va);
+        store(it + 1, vb);
       }
     }
   } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
@@ -653,48 +679,58 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
     const float4 as = *reinterpret_cast<const float4*>(att + c4 * 4);
     const float4 ad = *reinterpret_cast<const float4*>(att + kTileN + c4 * 4);
     float4 vs = make_float4(0.f, 0.f, 0.f, 0.f), vd = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < n_stages_total; ++it) {
+    struct Ld { float4 g[4], xv[4]; float d0[4], d1[4]; };
+    auto load = [&](int it, Ld& L) {
       const int64_t row0 = r_begin + (int64_t)it * kDwRows;
-      float4 g[4], xv[4];
-      float d0[4], d1[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {             // warp w handles rows w, w+8, w+16, w+24 of the stage
         const int64_t row = row0 + warp + 8 * i;
         if (row < r_end) {
-          g[i] = ld_stream4(p.dh + row * 128 + c4 * 4);
-          xv[i] = ld_stream4(p.x + row * 128 + c4 * 4);
-          d0[i] = p.ds ? __ldg(p.ds + row * 2) : 0.f;
-          d1[i] = p.ds ? __ldg(p.ds + row * 2 + 1) : 0.f;
+          L.g[i] = ld_stream4(p.dh + row * 128 + c4 * 4);
+          L.xv[i] = ld_stream4(p.x + row * 128 + c4 * 4);
+          L.d0[i] = p.ds ? __ldg(p.ds + row * 2) : 0.f;
+          L.d1[i] = p.ds ? __ldg(p.ds + row * 2 + 1) : 0.f;
         } else {
-          g[i] = xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          d0[i] = d1[i] = 0.f;
+          L.g[i] = L.xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          L.d0[i] = L.d1[i] = 0.f;
         }
       }
+    };
+    auto store = [&](int it, Ld& L) {
+      const uint32_t stage = (uint32_t)(it % kDwStages), phase = (uint32_t)((it / kDwStages) & 1);
       mbar_wait(bar_empty + 8 * stage, phase ^ 1);
       uint8_t* dA = sm + stage * kDwStageBytes;
       uint8_t* dB = dA + kDwOperandBytes;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 a = g[i];
-        a.x += d0[i] * as.x + d1[i] * ad.x;
-        a.y += d0[i] * as.y + d1[i] * ad.y;
-        a.z += d0[i] * as.z + d1[i] * ad.z;
-        a.w += d0[i] * as.w + d1[i] * ad.w;
-        vs = fma4(d0[i], xv[i], vs);
-        vd = fma4(d1[i], xv[i], vd);
+        float4 a = L.g[i];
+        a.x += L.d0[i] * as.x + L.d1[i] * ad.x;
+        a.y += L.d0[i] * as.y + L.d1[i] * ad.y;
+        a.z += L.d0[i] * as.z + L.d1[i] * ad.z;
+        a.w += L.d0[i] * as.w + L.d1[i] * ad.w;
+        vs = fma4(L.d0[i], L.xv[i], vs);
+        vd = fma4(L.d1[i], L.xv[i], vd);
         float4 hi, lo;
         const uint32_t off = mn_off(warp + 8 * i, c4);
         split4(a, hi, lo);
         *reinterpret_cast<float4*>(dA + off) = hi;
         *reinterpret_cast<float4*>(dA + kDwRows * 512 + off) = lo;
-        split4(xv[i], hi, lo);
+        split4(L.xv[i], hi, lo);
         *reinterpret_cast<float4*>(dB + off) = hi;
         *reinterpret_cast<float4*>(dB + kDwRows * 512 + off) = lo;
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * stage);
-      if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+    };
+    Ld la, lb;
+    if (n_stages_total > 0) load(0, la);
+    for (int it = 0; it < n_stages_total; it += 2) {
+      if (it + 1 < n_stages_total) load(it + 1, lb);
+      store(it, la);
+      if (it + 1 < n_stages_total) {
+        if (it + 2 < n_stages_total) load(it + 2, la);
+        store(it + 1, lb);
+      }
     }
     // park the side sums; reduced after the block barrier below
     // (the MMA pipeline may still be reading the stages: wait until the accumulator is published)

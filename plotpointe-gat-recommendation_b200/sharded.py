@@ -100,8 +100,12 @@ class ShardedGAT:
 
     def __init__(self, kind: str, n_users: int, n_items: int, item_feats: torch.Tensor, edge_index: torch.Tensor,
                  hidden: int = 128, layers: int = 2, heads: int = 1, attn_dropout: float = 0.1, seed: int = 42,
-                 lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None):
+                 lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None,
+                 feature_dtype=torch.float32):
         from . import _lib
+        if feature_dtype not in (torch.float32, torch.bfloat16):
+            raise NotImplementedError("feature_dtype must be float32 or bfloat16")
+        self.bf16 = feature_dtype == torch.bfloat16   # bf16 projection: h and the gathered dout travel (and are stored) as bf16
         from .graph import build_graph
         from .modules import CustomGAT, PyGGAT
         self._lib = _lib
@@ -158,9 +162,9 @@ class ShardedGAT:
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
-    def _rows(self, *shape):
+    def _rows(self, *shape, dtype=torch.float32):
         """Buffer for a tensor that is exchanged: padded to n_max rows (kernels fill the first n_loc)."""
-        return torch.empty((self.n_max,) + shape, dtype=torch.float32, device=self.dev)
+        return torch.empty((self.n_max,) + shape, dtype=dtype, device=self.dev)
 
     def _layer_seed(self, layer: int) -> int:
         return (self.seed * 1_000_003 + self.step_no * 101 + layer) & (2 ** 62 - 1)
@@ -179,10 +183,10 @@ class ShardedGAT:
         p = self.p_drop if self.training else 0.0
         for l in range(self.n_layers):
             f_in = x.shape[1]
-            h_loc, s_loc = self._rows(H * C), self._rows(2 * H)
+            h_loc, s_loc = self._rows(H * C, dtype=torch.bfloat16 if self.bf16 else torch.float32), self._rows(2 * H)
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
-            lib.call("b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+            lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), lib.ptr(dws), dwb, st)
             h_full = all_gather_rows(h_loc, self.world)
             s_full = all_gather_rows(s_loc, self.world)
@@ -191,7 +195,8 @@ class ShardedGAT:
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
             sf = self.sched_fwd
-            lib.call("b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(sf.sched), sf.n_sched, lib.ptr(sf.table),
+            lib.call("b200gat_edge_fwd_bf16" if self.bf16 else "b200gat_edge_fwd_f32", lib.ptr(h_full), lib.ptr(s_full),
+                     lib.ptr(sf.sched), sf.n_sched, lib.ptr(sf.table),
                      sf.n_long, lib.ptr(sf.partial(H * (C + 4))), lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.plan.lo,
                      H, C, self.policy, 0.2, lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
             self.saved.append((x, h_full, s_full, rowstat, out if H == 1 else out_heads, p, seed))
@@ -223,16 +228,18 @@ class ShardedGAT:
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
+            dout_g = self._rows(C, dtype=torch.bfloat16) if self.bf16 else None
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
-                     None, lib.ptr(dws), dwb, st)
-            dout_full = all_gather_rows(dout, self.world)
+                     lib.ptr(dout_g), lib.ptr(dws), dwb, st)
+            dout_full = all_gather_rows(dout_g if self.bf16 else dout, self.world)
             nodestat_full = all_gather_rows(nodestat, self.world)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
             sb = self.sched_bwd
-            lib.call("b200gat_edge_bwd_f32", lib.ptr(h_full), lib.ptr(s_full), lib.ptr(dout_full), lib.ptr(nodestat_full),
+            lib.call("b200gat_edge_bwd_bf16" if self.bf16 else "b200gat_edge_bwd_f32", lib.ptr(h_full), lib.ptr(s_full),
+                     lib.ptr(dout_full), lib.ptr(nodestat_full),
                      lib.ptr(sb.sched), sb.n_sched, lib.ptr(sb.table), sb.n_long, lib.ptr(sb.partial(H * C + 4)),
                      lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh),
                      lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
@@ -294,7 +301,9 @@ def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
     nu, ni, n_inter, k = synth.CONFIGS[args.workload]
     ei, feats = synth.make_graph(nu, ni, n_inter, k)
     e = int(ei.shape[1])
-    tr = ShardedGAT("pyg", nu, ni, feats, ei, hidden=B.HIDDEN, layers=B.LAYERS, heads=B.HEADS, attn_dropout=0.1, device=dev)
+    bf16 = getattr(args, "tier", "f32") == "bf16"
+    tr = ShardedGAT("pyg", nu, ni, feats, ei, hidden=B.HIDDEN, layers=B.LAYERS, heads=B.HEADS, attn_dropout=0.1, device=dev,
+                    feature_dtype=torch.bfloat16 if bf16 else torch.float32)
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
@@ -332,7 +341,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
         print(json.dumps({
             "metric": B.METRIC, "value": e * B.LAYERS / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{B.LAYERS}, d={B.HIDDEN}, heads={B.HEADS}, BPR on "
                                    f"{B.S_TRIPLES} triples, train mode, Adam step; {e} edges", "n_nodes": nu + ni, "n_edges": e,
                        "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs (round-robin node blocks), NCCL all-gather per layer",

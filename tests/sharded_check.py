@@ -69,6 +69,21 @@ def main(kind):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # bf16 tier: sharded equals the single-GPU bf16 modules (same kernels, same rounding points)
+    trb = sharded.ShardedGAT(kind, nu, ni, feats, ei, hidden=128, layers=2, heads=heads, attn_dropout=0.1, seed=7, device=dev,
+                             feature_dtype=torch.bfloat16)
+    trb.training = False
+    zb = trb.forward()
+    lb = trb.loss_and_backward(zb, u, i, j, "bpr")
+    torch.manual_seed(7)
+    mb = (b200gat.CustomGAT(nu, ni, 128, 128, 2, feature_dtype=torch.bfloat16) if kind == "custom"
+          else b200gat.PyGGAT(nu, ni, 128, 128, 2, heads, 0.1, feature_dtype=torch.bfloat16)).to(dev).eval()
+    zmb = mb(feats.to(dev), eid)
+    lmb = b200gat.bpr_loss(zmb, nu, u, i, j)
+    lmb.backward()
+    close(zb[:trb.n_loc], zmb[trb.plan.local_nodes], "z bf16", 1e-4)
+    close(lb, lmb, "loss bf16", 1e-5)
+    close(trb.W[0].grad, (mb.layers if kind == "custom" else mb.convs)[0].lin.weight.grad, "dW0 bf16", 1e-3)
     if rank == 0:
         print("SHARDED_OK", float(loss), float(l_train))
 

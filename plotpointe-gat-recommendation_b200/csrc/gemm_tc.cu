@@ -181,7 +181,8 @@ __global__ void build_b_image_kernel(const float* __restrict__ w, int64_t ldn, i
 // ------------------------------------------------------------------------------------------------
 // proj_fwd / proj_dx
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdProducerWarps = 4, kFwdEpiWarps = 4;
+constexpr int kFwdProducerWarps = 8, kFwdEpiWarps = 4;
+constexpr int kProdRows = kTileM / (kFwdProducerWarps * 4);   // rows per producer thread and k-block (4)
 constexpr int kFwdThreads = (kFwdProducerWarps + kFwdEpiWarps + 1) * 32;  // + MMA warp
 constexpr int kAStages = 2;
 constexpr int kAStageBytes = 2 * kTileM * 128;                 // hi + lo of one 32-wide k block (32 KB)
@@ -256,63 +257,66 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
   if (warp < kFwdProducerWarps) {
     // =========================== producers: A tiles =============================================
     // Software pipelined: the global loads of k-block it+1 are in flight while k-block it is split and stored.
-    const int t = threadIdx.x;          // 0..127
-    const int chunk = t & 7, r0 = t >> 3;
+    const int t = threadIdx.x;          // 0..255
+    const int chunk = t & 7, r0 = t >> 3;   // rows r0, r0+32, r0+64, r0+96 of the tile
     constexpr int KB = kK / kKB;
+    constexpr int R = kProdRows;
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_it = my_tiles * KB;
-    auto load = [&](int64_t it, float4(&v)[8], float(&dsv)[8][2]) {
+    struct Ld { float4 v[R]; float ds[R][2]; };
+    auto load = [&](int64_t it, Ld& L) {
       const int64_t row0 = (blockIdx.x + (it / KB) * gridDim.x) * kTileM;
       const int kb = (int)(it % KB);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + r0 + 16 * i;
+      for (int i = 0; i < R; ++i) {
+        const int64_t row = row0 + r0 + 32 * i;
         if (row < p.n_rows) {
-          v[i] = ld_stream4(p.a + row * p.lda + kb * kKB + chunk * 4);
-          if (DX) { dsv[i][0] = __ldg(p.ds + row * 2); dsv[i][1] = __ldg(p.ds + row * 2 + 1); }
+          L.v[i] = ld_stream4(p.a + row * p.lda + kb * kKB + chunk * 4);
+          if (DX) { L.ds[i][0] = __ldg(p.ds + row * 2); L.ds[i][1] = __ldg(p.ds + row * 2 + 1); }
         } else {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (DX) dsv[i][0] = dsv[i][1] = 0.f;
+          L.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (DX) L.ds[i][0] = L.ds[i][1] = 0.f;
         }
       }
     };
-    auto store = [&](int64_t it, float4(&v)[8], float(&dsv)[8][2]) {
+    auto store = [&](int64_t it, Ld& L) {
       const int kb = (int)(it % KB);
       const uint32_t stage = (uint32_t)(it % kAStages), phase = (uint32_t)((it / kAStages) & 1);
       if (DX) {  // dh_full = dh + ds_src * a_src + ds_dst * a_dst
         const float4 as = *reinterpret_cast<const float4*>(att + kb * kKB + chunk * 4);
         const float4 ad = *reinterpret_cast<const float4*>(att + kTileN + kb * kKB + chunk * 4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i].x += dsv[i][0] * as.x + dsv[i][1] * ad.x;
-          v[i].y += dsv[i][0] * as.y + dsv[i][1] * ad.y;
-          v[i].z += dsv[i][0] * as.z + dsv[i][1] * ad.z;
-          v[i].w += dsv[i][0] * as.w + dsv[i][1] * ad.w;
+        for (int i = 0; i < R; ++i) {
+          L.v[i].x += L.ds[i][0] * as.x + L.ds[i][1] * ad.x;
+          L.v[i].y += L.ds[i][0] * as.y + L.ds[i][1] * ad.y;
+          L.v[i].z += L.ds[i][0] * as.z + L.ds[i][1] * ad.z;
+          L.v[i].w += L.ds[i][0] * as.w + L.ds[i][1] * ad.w;
         }
       }
       mbar_wait(bar_empty + 8 * stage, phase ^ 1);
       uint8_t* dst = sm + kBImageBytes + stage * kAStageBytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < R; ++i) {
         float4 hi, lo;
-        split4(v[i], hi, lo);
-        const uint32_t off = sw128(r0 + 16 * i, chunk);
+        split4(L.v[i], hi, lo);
+        const uint32_t off = sw128(r0 + 32 * i, chunk);
         *reinterpret_cast<float4*>(dst + off) = hi;
         *reinterpret_cast<float4*>(dst + kTileM * 128 + off) = lo;
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * stage);
     };
-    float4 va[8], vb[8];
-    float da[8][2], db[8][2];
-    if (n_it > 0) load(0, va, da);
-    for (int64_t it = 0; it < n_it; it += 2) {
-      if (it + 1 < n_it) load(it + 1, vb, db);
-      store(it, va, da);
-      if (it + 1 < n_it) {
-        if (it + 2 < n_it) load(it + 2, va, da);
-        store(it + 1, vb, db);
-      }
+    // four k-blocks of loads in flight per thread (64 KB per SM)
+    Ld l0, l1, l2, l3;
+    if (0 < n_it) load(0, l0);
+    if (1 < n_it) load(1, l1);
+    if (2 < n_it) load(2, l2);
+    for (int64_t it = 0; it < n_it; it += 4) {
+      if (it + 3 < n_it) load(it + 3, l3);
+      store(it, l0);
+      if (it + 1 < n_it) { if (it + 4 < n_it) load(it + 4, l0); store(it + 1, l1); }
+      if (it + 2 < n_it) { if (it + 5 < n_it) load(it + 5, l1); store(it + 2, l2); }
+      if (it + 3 < n_it) { if (it + 6 < n_it) load(it + 6, l2); store(it + 3, l3); }
     }
   } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
     // =========================== MMA issuer ======================================================
@@ -499,40 +503,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_bf16_kernel(HParams p) {
     const int t = threadIdx.x;
     const int chunk = t & 7, r0 = t >> 3;
     constexpr int KB = kK / kHKB;
+    constexpr int R = kProdRows;
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_it = my_tiles * KB;
-    auto load = [&](int64_t it, float4(&v)[8][2]) {
+    struct Ld { float4 v[R][2]; };
+    auto load = [&](int64_t it, Ld& L) {
       const int64_t row0 = (blockIdx.x + (it / KB) * gridDim.x) * kTileM;
       const int kb = (int)(it % KB);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + r0 + 16 * i;
+      for (int i = 0; i < R; ++i) {
+        const int64_t row = row0 + r0 + 32 * i;
         if (row < p.n_rows) {
-          v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
-          v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
+          L.v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
+          L.v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
         } else {
-          v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          L.v[i][0] = L.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
-    auto store = [&](int64_t it, float4(&v)[8][2]) {
+    auto store = [&](int64_t it, Ld& L) {
       const uint32_t stage = (uint32_t)(it % kHStages), phase = (uint32_t)((it / kHStages) & 1);
       mbar_wait(bar_empty + 8 * stage, phase ^ 1);
       uint8_t* dst = sm + kHBImageBytes + stage * kHAStageBytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 16 * i, chunk)) = pack8_bf16(v[i][0], v[i][1]);
+      for (int i = 0; i < R; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 32 * i, chunk)) = pack8_bf16(L.v[i][0], L.v[i][1]);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * stage);
     };
-    float4 va[8][2], vb[8][2];
-    if (n_it > 0) load(0, va);
+    Ld l0, l1;   // two k-blocks (64 KB per SM) of loads in flight
+    if (0 < n_it) load(0, l0);
     for (int64_t it = 0; it < n_it; it += 2) {
-      if (it + 1 < n_it) load(it + 1, vb);
-      store(it, va);
-      if (it + 1 < n_it) {
-        if (it + 2 < n_it) load(it + 2, va);
-        store(it + 1, vb);
-      }
+      if (it + 1 < n_it) load(it + 1, l1);
+      store(it, l0);
+      if (it + 1 < n_it) { if (it + 2 < n_it) load(it + 2, l0); store(it + 1, l1); }
     }
   } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
     if (lane == 0) {
@@ -722,15 +725,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * stage);
     };
-    Ld la, lb;
-    if (n_stages_total > 0) load(0, la);
+    Ld l0, l1;   // two stages (64 KB per SM) of loads in flight
+    if (0 < n_stages_total) load(0, l0);
     for (int it = 0; it < n_stages_total; it += 2) {
-      if (it + 1 < n_stages_total) load(it + 1, lb);
-      store(it, la);
-      if (it + 1 < n_stages_total) {
-        if (it + 2 < n_stages_total) load(it + 2, la);
-        store(it + 1, lb);
-      }
+      if (it + 1 < n_stages_total) load(it + 1, l1);
+      store(it, l0);
+      if (it + 1 < n_stages_total) { if (it + 2 < n_stages_total) load(it + 2, l0); store(it + 1, l1); }
     }
     // park the side sums; reduced after the block barrier below
     // (the MMA pipeline may still be reading the stages: wait until the accumulator is published)

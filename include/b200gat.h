@@ -171,8 +171,8 @@ int b200gat_edge_bwd_bf16(const void* h_bf16, const float* s, const void* dout_b
                           float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset, int heads,
                           int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
                           int ld_ds, float p_drop, uint64_t seed, void* stream);
-int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int heads,
-                       float* ds_dst, int ld_ds, void* stream);
+int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows, int64_t n_edges,
+                       int heads, float* ds_dst, int ld_ds, void* stream);
 
 /* ---- (5) fused ranking loss ---------------------------------------------------------------------
  * Replaces train_gat_custom.py:350-359: pos/neg dot products of gathered rows of Z, BPR
@@ -183,7 +183,8 @@ int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* cs
  *   same workspace to the backward.  grad_out : device float[1].  The backward writes the gradient
  *   rows of nodes [node_begin, node_begin+node_count) -- or of the nodes listed in node_list
  *   [node_count] when it is not NULL -- into dz [node_count, channels] (a row shard; 0 / n_users+n_items
- *   = everything); every row written (rows without triples = 0); no atomics, bitwise reproducible.
+ *   = everything; node_list entries < 0 are padding rows and get zeros); every row written (rows without
+ *   triples = 0); no atomics, bitwise reproducible.  dz_bf16 (nullable): a bf16 copy of dz for the bf16 tier.
  *   node_map (nullable, int32 [n_users+n_items]): row of z that holds node v (a row-sharded z is stored
  *   block-permuted); NULL = identity.
  */
@@ -195,7 +196,8 @@ int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_t n_items, 
 int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
                               const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
                               int loss_kind, const float* grad_out, const int32_t* node_list, int64_t node_begin,
-                              int64_t node_count, float* dz, void* workspace, size_t workspace_bytes, void* stream);
+                              int64_t node_count, float* dz, void* dz_bf16, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 #ifdef __cplusplus
 }

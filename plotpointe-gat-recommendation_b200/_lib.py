@@ -54,12 +54,12 @@ _SIGS = {
     "b200gat_build_schedule": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int,
                                      c_float, _P, _P, _P, c_int, c_float, c_uint64, _P]),
-    "b200gat_ds_dst_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P]),
+    "b200gat_ds_dst_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, c_int, _P]),
     "b200gat_loss_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_rank_loss_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P,
                                           c_size_t, _P]),
     "b200gat_rank_loss_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, _P, c_int, _P, _P, c_int64,
-                                          c_int64, _P, _P, c_size_t, _P]),
+                                          c_int64, _P, _P, _P, c_size_t, _P]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

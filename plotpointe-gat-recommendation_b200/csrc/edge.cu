@@ -603,6 +603,26 @@ __global__ void __launch_bounds__(128) ds_dst_kernel(const float* __restrict__ d
   }
 }
 
+// thread-per-row variant for short rows (average degree < 8, e.g. one rank's slice of the backward graph)
+template <int H>
+__global__ void __launch_bounds__(256) ds_dst_thread_kernel(const float* __restrict__ de, const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ csr2csc, int n_rows,
+                                                            float* __restrict__ ds_dst, int ld_ds) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int beg = rowptr[r], end = rowptr[r + 1];
+  float a[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) a[hh] = 0.f;
+  for (int e = beg; e < end; ++e) {
+    const size_t q = (size_t)csr2csc[e];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) a[hh] += de[q * H + hh];
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) ds_dst[(size_t)r * ld_ds + hh] = a[hh];
+}
+
 // ---- dispatch helpers ---------------------------------------------------------------------------
 #define B200GAT_DISPATCH_HC(H_, CV_, ...)                                        \
   if (H_ == 1 && CV_ == 1) { constexpr int kH = 1, kCV = 1; __VA_ARGS__; }        \
@@ -812,9 +832,19 @@ extern "C" int b200gat_edge_bwd_bf16(const void* h_bf16, const float* s, const v
 }
 
 extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const int32_t* csr2csc, int64_t n_rows,
-                                  int heads, float* ds_dst, int ld_ds, void* stream) {
+                                  int64_t n_edges, int heads, float* ds_dst, int ld_ds, void* stream) {
   B200GAT_CHECK_ARG(rowptr && ds_dst && ld_ds >= heads, "null pointer / bad ld");
   if (n_rows == 0) return kOk;
+  if (n_edges < 8 * n_rows) {   // short rows: one thread per row (the per-row sums stay in edge order: same result)
+    cudaStream_t st2 = (cudaStream_t)stream;
+    const int g2 = ceil_div(n_rows, 256);
+    if (heads == 1) count_launch(), ds_dst_thread_kernel<1><<<g2, 256, 0, st2>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+    else if (heads == 2) count_launch(), ds_dst_thread_kernel<2><<<g2, 256, 0, st2>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+    else if (heads == 4) count_launch(), ds_dst_thread_kernel<4><<<g2, 256, 0, st2>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+    else { set_error("unsupported heads=%d", heads); return kErrUnsupported; }
+    B200GAT_LAUNCH_CHECK();
+    return kOk;
+  }
   const int grid = ceil_div(n_rows * 32, 128);
   cudaStream_t st = (cudaStream_t)stream;
   if (heads == 1) count_launch(), ds_dst_kernel<1><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);

@@ -7,6 +7,8 @@
 // backward: the 3S (node, triple) incidences are stably sorted by node once per triple set
 //           (radix sort from graph.cu); a warp per node then accumulates its incidences in that
 //           order -> dZ[N, C] without atomics, every row written exactly once.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/b200gat.h"
 
@@ -105,12 +107,14 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ ids, const float* __restrict__ grad_out,
                                                        float scale, const int32_t* __restrict__ node_list, int64_t node_begin,
                                                        int64_t node_count, const int32_t* __restrict__ node_map,
-                                                       float* __restrict__ dz /*[node_count, C]*/) {
+                                                       float* __restrict__ dz /*[node_count, C]*/,
+                                                       __nv_bfloat16* __restrict__ dz_bf16 /*optional bf16 copy*/) {
   const int lane = threadIdx.x & 31;
   const int64_t local = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (local >= node_count) return;
   const int64_t n = node_list ? (int64_t)node_list[local] : node_begin + local;
-  const int beg = ptr[n], end = ptr[n + 1];
+  const bool real = n >= 0;                      // node_list entries < 0 are padding rows: written as zeros
+  const int beg = real ? ptr[n] : 0, end = real ? ptr[n + 1] : 0;
   const float g = grad_out[0] * scale;
   const int64_t n_items = n_nodes - n_users;
   auto safe = [](int64_t v, int64_t lim) { return (v < 0 || v >= lim) ? (int64_t)0 : v; };
@@ -130,6 +134,13 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
     }
     acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
     *reinterpret_cast<float4*>(dz + local * C + c) = acc;
+    if (dz_bf16) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dz_bf16 + local * C + c) = pk;
+    }
   }
 }
 
@@ -208,8 +219,8 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
 extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* u,
                                          const int64_t* i, const int64_t* j, int64_t n_triples, const int32_t* node_map,
                                          int loss_kind, const float* grad_out, const int32_t* node_list, int64_t node_begin,
-                                         int64_t node_count, float* dz, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         int64_t node_count, float* dz, void* dz_bf16, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
   B200GAT_CHECK_ARG(z && grad_out && dz && workspace && u && i && j, "null pointer");
   B200GAT_CHECK_ARG(loss_kind == kBpr || loss_kind == kBce, "bad loss kind %d", loss_kind);
   size_t need;
@@ -223,7 +234,8 @@ extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_
   LossWs w = carve(workspace, N, S);
   const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
   count_launch(), loss_bwd_kernel<<<ceil_div(node_count * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids,
-                                                                 grad_out, scale, node_list, node_begin, node_count, node_map, dz);
+                                                                 grad_out, scale, node_list, node_begin, node_count, node_map, dz,
+                                                                 (__nv_bfloat16*)dz_bf16);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -87,7 +87,7 @@ class GATLayerFunction(torch.autograd.Function):
                       _lib.ptr(sb.sched), sb.n_sched, _lib.ptr(sb.table), sb.n_long,
                       _lib.ptr(sb.partial(heads * channels + 4)), _lib.ptr(g.row), _lib.ptr(g.perm_csc), 0, heads, channels,
                       policy, negative_slope, _lib.ptr(dh), _lib.ptr(de), _lib.ptr(ds), 2 * heads, p_drop, seed, st)
-            _lib.call("b200gat_ds_dst_f32", _lib.ptr(de), _lib.ptr(g.rowptr), _lib.ptr(g.csr2csc), n, heads,
+            _lib.call("b200gat_ds_dst_f32", _lib.ptr(de), _lib.ptr(g.rowptr), _lib.ptr(g.csr2csc), n, g.n_edges, heads,
                       _lib.ptr(ds, heads), 2 * heads, st)
             del de
             dx = _empty((n, f_in), x) if ctx.needs_input_grad[0] else None
@@ -192,7 +192,7 @@ class RankLossFunction(torch.autograd.Function):
         dz = torch.empty_like(z)
         with torch.cuda.device(z.device):
             _lib.call("b200gat_rank_loss_bwd_f32", _lib.ptr(z), n_users, n_items, c, _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), s,
-                      None, kind, _lib.ptr(go), None, 0, n_users + n_items, _lib.ptr(dz), _lib.ptr(ws), ws_bytes,
+                      None, kind, _lib.ptr(go), None, 0, n_users + n_items, _lib.ptr(dz), None, _lib.ptr(ws), ws_bytes,
                       _lib.stream())
         return dz, None, None, None, None, None
 

@@ -135,6 +135,11 @@ class ShardedGAT:
         self.sched_bwd = _lib.make_schedule(self.g_bwd.colptr, plan.lo, self.n_loc, self.g_bwd.n_edges + 1)
         self.node_map = plan.perm_map.to(torch.int32).contiguous()
         self.node_list = plan.local_nodes.to(torch.int32).contiguous()
+        # node id of every gathered row (-1 for the padding rows): the loss gradient is evaluated for ALL rows on every
+        # rank (0.2 ms of redundant work) so that the last layer's dout needs no 354 MB all-gather
+        row_nodes = torch.full((self.n_pad,), -1, dtype=torch.int32, device=self.dev)
+        row_nodes[plan.perm_map] = torch.arange(self.n, dtype=torch.int32, device=self.dev)
+        self.row_nodes = row_nodes
         del ei, ei_p
 
         torch.manual_seed(seed)
@@ -215,10 +220,20 @@ class ShardedGAT:
         lib.call("b200gat_rank_loss_fwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
                  lib.ptr(self.node_map), kind, 1, lib.ptr(loss), lib.ptr(ws), ws_bytes, st)
         one = torch.ones(1, dtype=torch.float32, device=self.dev)
-        dout = self._rows(C)
-        lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                 lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.node_list), 0, self.n_loc, lib.ptr(dout), lib.ptr(ws),
-                 ws_bytes, st)
+        if self.world > 1:
+            dout_all = self._empty(self.n_pad, C)
+            dout_all_g = torch.empty((self.n_pad, C), dtype=torch.bfloat16, device=self.dev) if self.bf16 else None
+            lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
+                     lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.row_nodes), 0, self.n_pad, lib.ptr(dout_all),
+                     lib.ptr(dout_all_g), lib.ptr(ws), ws_bytes, st)
+            dout = dout_all[self.plan.lo:self.plan.lo + self.n_max]
+            pre_gathered = (dout_all_g if self.bf16 else dout_all)
+        else:
+            dout = self._rows(C)
+            lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
+                     lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.node_list), 0, self.n_loc, lib.ptr(dout), None,
+                     lib.ptr(ws), ws_bytes, st)
+            pre_gathered = None
         del z_full
         grads = {}
         for l in reversed(range(self.n_layers)):
@@ -228,11 +243,12 @@ class ShardedGAT:
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
-            dout_g = self._rows(C, dtype=torch.bfloat16) if self.bf16 else None
+            have_full = pre_gathered is not None and l == self.n_layers - 1
+            dout_g = self._rows(C, dtype=torch.bfloat16) if (self.bf16 and not have_full) else None
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
                      lib.ptr(dout_g), lib.ptr(dws), dwb, st)
-            dout_full = all_gather_rows(dout_g if self.bf16 else dout, self.world)
+            dout_full = pre_gathered if have_full else all_gather_rows(dout_g if self.bf16 else dout, self.world)
             nodestat_full = all_gather_rows(nodestat, self.world)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
@@ -244,7 +260,8 @@ class ShardedGAT:
                      lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh),
                      lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
             ds_dst = self._empty(self.n_pad, H)                              # partial sums over this rank's edges
-            lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad, H,
+            lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad,
+                     self.g_bwd.n_edges, H,
                      lib.ptr(ds_dst), H, st)
             if self.world > 1:
                 dist.all_reduce(ds_dst)

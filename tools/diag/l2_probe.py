@@ -1,6 +1,6 @@
 """Diagnostic (not a test): how fast is the forward edge kernel when the gathered rows fit in L2?"""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import b200gat
 from b200gat import synth, _lib
 dev = torch.device("cuda:0")

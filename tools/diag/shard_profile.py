@@ -1,6 +1,6 @@
 """Diagnostic (not a test): per-phase CUDA-event timing of the row-sharded step. Run under torchrun."""
 import os, sys, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist
 

@@ -1,6 +1,6 @@
 """Diagnostic (not a test): step time and per-entry-point breakdown of the fp32 and bf16 tiers on config 2."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import b200gat
 from b200gat import synth, _lib
 dev = torch.device("cuda:0")

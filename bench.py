@@ -120,7 +120,7 @@ def run_ours(args):
     bf16 = args.tier == "bf16"
     model = b200gat.PyGGAT(nu, ni, 128, HIDDEN, LAYERS, heads=HEADS, attn_dropout=0.1,
                            feature_dtype=torch.bfloat16 if bf16 else torch.float32).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    opt = b200gat.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)   # same rule as the reference torch.optim.Adam
     eid, fd = ei.to(dev), feats.to(dev)
     u, i, j = synth.make_triples(nu, ni, S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))

@@ -199,6 +199,20 @@ int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, 
                               int64_t node_count, float* dz, void* dz_bf16, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* ---- callers either side of the path ---------------------------------
+ * adam_step : one step of torch.optim.Adam(lr, weight_decay=l2) exactly as the reference builds it
+ *   (scripts/train_gat_custom.py:335,362): g += wd*p; m, v moments; bias-corrected update.  step counts from 1.
+ * eval_ranks: inner loop of eval_sampled (scripts/train_gat_custom.py:200-206).  candidates [n_eval, n_candidates]
+ *   int64 item ids, column 0 = the held-out positive, the rest the sampled negatives; ranks[q] =
+ *   (scores > scores[0]).sum() + 1 with scores = I[candidates[q]] @ U[users[q]].  n_bad: device int32 count of
+ *   out-of-range ids (those are scored against row 0).  Recall@k / NDCG@k follow on the host as at :207-209.
+ */
+int b200gat_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* users,
+                           const int64_t* candidates, int64_t n_eval, int n_candidates, int32_t* ranks, int32_t* n_bad,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,11 @@ Pinning status
   reference makes (scripts/train_gat_pyg.py:77,87).  PARITY UNPINNED for this dialect: the only
   anchor is the cross-check against the pinned custom dialect on inputs where both coincide
   (``tests/test_oracle_golden.py::test_gatconv_matches_custom_when_unclamped``).
-* ``build_ii_knn``: restated from graphs/build_ii_knn.py:56-99; checked in the container against
-  the reference's own arithmetic re-run by ``make_golden.py``.
+* ``eval_ranks`` / ``ranking_metrics`` / ``sample_eval_candidates`` (next row f2): PINNED.  ``make_golden.py`` runs
+  the reference's own ``eval_sampled`` (scripts/train_gat_custom.py:184-210) under a fixed numpy seed and stores its
+  metrics; the test replays the same numpy stream through ``sample_eval_candidates`` and must reproduce them.
+* ``build_ii_knn`` (next row f1): restated from graphs/build_ii_knn.py:56-99, which only exists inside a ``main()`` that
+  talks to GCS, so it cannot be imported: PARITY UNPINNED (sanity-checked against a brute-force top-k only).
 
 All functions are dtype-generic (float32 or float64) and differentiable through torch autograd,
 which is exactly how the reference obtains its gradients (``loss.backward()``,
@@ -245,3 +248,48 @@ def build_ii_knn(embeddings: np.ndarray, k: int = 20, min_similarity: float = 0.
             cols.extend(top.tolist())
             sims.extend(ts.tolist())
     return np.asarray(rows, np.int32), np.asarray(cols, np.int32), np.asarray(sims, np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# f2 / f3 (next rows): sampled evaluation and the optimizer step
+# --------------------------------------------------------------------------------------
+
+
+def eval_ranks(z: torch.Tensor, n_users: int, users: torch.Tensor, candidates: torch.Tensor):
+    """Inner loop of eval_sampled, scripts/train_gat_custom.py:200-206: per evaluated user the scores of
+    [positive] + negatives, ``i_emb @ u_emb``, and ``rank = (scores > scores[0]).sum() + 1``.  Returns (ranks, scores)."""
+    U, I = z[:n_users], z[n_users:]
+    scores = torch.einsum("qkc,qc->qk", I[candidates], U[users])
+    ranks = (scores > scores[:, :1]).sum(dim=1) + 1
+    return ranks, scores
+
+
+def sample_eval_candidates(train_pos_idx, eval_pos, n_items: int, neg_k: int):
+    """Candidate lists of eval_sampled, scripts/train_gat_custom.py:190-199: for each evaluated user, in dict order, the
+    positive followed by ``neg_k`` negatives drawn one ``np.random.randint`` at a time and rejected while they are in the
+    user's training positives or equal the positive.  Consumes the global numpy stream exactly like the reference."""
+    user_pos_sets = {u: set(pos) for u, pos in train_pos_idx.items()}
+    users, cands = [], []
+    for u, pos_i in eval_pos.items():
+        avoid = user_pos_sets.get(u, set()) | {pos_i}
+        negs = []
+        while len(negs) < neg_k:
+            cand = np.random.randint(0, n_items)
+            if cand not in avoid:
+                negs.append(cand)
+        users.append(u)
+        cands.append([pos_i] + negs)
+    return torch.tensor(users, dtype=torch.long), torch.tensor(cands, dtype=torch.long).reshape(len(users), neg_k + 1)
+
+
+def ranking_metrics(ranks, Ks=(10, 20)):
+    """scripts/train_gat_custom.py:206-210."""
+    import math
+    out = {f"recall@{k}": [] for k in Ks}
+    out.update({f"ndcg@{k}": [] for k in Ks})
+    for rank in ranks.tolist():
+        for k in Ks:
+            hit = 1.0 if rank <= k else 0.0
+            out[f"recall@{k}"].append(hit)
+            out[f"ndcg@{k}"].append((1.0 / math.log2(rank + 1)) if hit else 0.0)
+    return {m: float(np.mean(v)) if v else 0.0 for m, v in out.items()}

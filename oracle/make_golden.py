@@ -117,6 +117,35 @@ def model_case(ref, seed, n_users, n_items, feat_dim, hidden, layers, n_inter, n
     return out
 
 
+def eval_case(ref, seed):
+    """The reference's own eval_sampled (scripts/train_gat_custom.py:184-210) on a small model, fixed numpy seed."""
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    nu, ni, hidden = 30, 50, 128
+    train_pos = {u: rng.integers(0, ni, size=int(rng.integers(1, 6))) for u in range(nu)}
+    eval_pos = {int(u): int(rng.integers(0, ni)) for u in rng.permutation(nu)[:20]}
+    ei = ref.build_edge_index(nu, ni, train_pos)
+    feats = torch.nn.functional.normalize(torch.randn(ni, 128), dim=1)
+    model = ref.CustomGAT(nu, ni, 128, hidden, 2).eval()
+    with torch.no_grad():
+        model.user_emb.weight.mul_(5.0)        # spread the scores so that ranks are not all ties
+    cfg = ref.Config("p", "r", "s", "g", "e", "m", eval_neg_k=25)
+    np.random.seed(1234)
+    metrics = ref.eval_sampled(model, cfg, feats, ei, train_pos, eval_pos)
+    out = {"n_users": np.int64(nu), "n_items": np.int64(ni), "neg_k": np.int64(25), "np_seed": np.int64(1234),
+           "edge_index": ei.numpy(), "item_feats": feats.numpy(),
+           "train_users": np.concatenate([np.full(len(v), k) for k, v in train_pos.items()]),
+           "train_items": np.concatenate(list(train_pos.values())),
+           "eval_users": np.array(list(eval_pos.keys())), "eval_items": np.array(list(eval_pos.values()))}
+    for k, v in model.state_dict().items():
+        out["param:" + k] = v.numpy()
+    for k, v in metrics.items():
+        out["metric:" + k] = np.float64(v)
+    with torch.no_grad():
+        out["z"] = model(feats, ei).numpy()
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -125,6 +154,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "custom_model.npz"),
                         **model_case(ref, 3, n_users=40, n_items=70, feat_dim=128, hidden=128, layers=2,
                                      n_inter=300, n_triples=256))
+    np.savez_compressed(os.path.join(OUT, "eval_sampled.npz"), **eval_case(ref, 4))
     # edge-list builder: dict order, array order, duplicates
     tp = {3: np.array([5, 1, 5]), 0: np.array([2]), 7: np.array([0, 9, 9, 4])}
     np.savez_compressed(os.path.join(OUT, "edge_index_small.npz"), edge_index=ref.build_edge_index(8, 10, tp).numpy(),

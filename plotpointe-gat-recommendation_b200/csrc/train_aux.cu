@@ -1,0 +1,111 @@
+// The two callers either side of the hot path:
+//   adam_step  : torch.optim.Adam(lr, weight_decay) as the reference constructs it (scripts/train_gat_custom.py:335,362),
+//                one fused elementwise kernel per parameter tensor (L2-in-gradient weight decay, bias correction).
+//   eval_ranks : the inner loop of eval_sampled (scripts/train_gat_custom.py:200-206): for each evaluated user, the
+//                scores of 1 positive + K sampled negatives, i_emb @ u_emb, and rank = (scores > scores[0]).sum() + 1.
+#include "common.cuh"
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n, float lr, float b1, float b2, float eps, float wd, float inv_bc1, float inv_sqrt_bc2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = g[i] + wd * pi;                       // weight decay enters the gradient (Adam, not AdamW)
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);      // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - (lr * inv_bc1) * (mi / denom);
+  }
+}
+
+constexpr int kEvalThreads = 128;
+constexpr int kEvalU = 4;   // candidate rows in flight per warp
+
+__global__ void __launch_bounds__(kEvalThreads) eval_ranks_kernel(const float* __restrict__ z, int64_t n_users, int64_t n_items, int C,
+                                                                  const int64_t* __restrict__ users,
+                                                                  const int64_t* __restrict__ cand, int64_t n_eval, int K1,
+                                                                  int32_t* __restrict__ rank_out, int32_t* __restrict__ n_bad) {
+  __shared__ float s_pos;
+  __shared__ int s_cnt[kEvalThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x;
+  if (q >= n_eval) return;
+  int64_t u = users[q];
+  if (u < 0 || u >= n_users) { u = 0; if (threadIdx.x == 0) atomicAdd(n_bad, 1); }
+  const int64_t* cq = cand + q * K1;
+  // this lane's slice of the user row (C <= 512: up to 4 chunks of 128 channels)
+  float4 ur[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ur[k] = (k * 128 + lane * 4 < C) ? ldg4(z + u * C + k * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  auto score = [&](int64_t item) {
+    if (item < 0 || item >= n_items) { item = 0; if (lane == 0) atomicAdd(n_bad, 1); }
+    const float* r = z + (n_users + item) * C;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k * 128 + lane * 4 < C) d += dot4(ur[k], ldg4(r + k * 128 + lane * 4));
+    return d;
+  };
+  if (warp == 0) {
+    const float d = warp_sum(score(cq[0]));
+    if (lane == 0) s_pos = d;
+  }
+  __syncthreads();
+  const float pos = s_pos;
+  int cnt = 0;
+  for (int c0 = 1 + warp * kEvalU; c0 < K1; c0 += (kEvalThreads / 32) * kEvalU) {
+    float d[kEvalU];
+#pragma unroll
+    for (int k = 0; k < kEvalU; ++k) d[k] = (c0 + k < K1) ? score(cq[c0 + k]) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kEvalU; ++k) {
+      const float t = warp_sum(d[k]);
+      cnt += (c0 + k < K1 && t > pos) ? 1 : 0;
+    }
+  }
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < kEvalThreads / 32; ++w) total += s_cnt[w];
+    rank_out[q] = total + 1;     // (scores > scores[0]).sum() + 1
+  }
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" int b200gat_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+  B200GAT_CHECK_ARG(n == 0 || (param && grad && exp_avg && exp_avg_sq), "null pointer");
+  B200GAT_CHECK_ARG(step >= 1, "step counts from 1");
+  if (n == 0) return kOk;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int64_t want = (n + 255) / 256, cap = (int64_t)kNumSMs * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  count_launch(), adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                          weight_decay, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)));
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* users,
+                                      const int64_t* candidates, int64_t n_eval, int n_candidates, int32_t* ranks,
+                                      int32_t* n_bad, void* stream) {
+  B200GAT_CHECK_ARG(z && ranks && n_bad && (n_eval == 0 || (users && candidates)), "null pointer");
+  B200GAT_CHECK_ARG(channels % 4 == 0 && channels > 0 && channels <= 512, "channels must be a multiple of 4, at most 512");
+  B200GAT_CHECK_ARG(n_candidates >= 1, "need at least the positive candidate");
+  B200GAT_CHECK_ARG(n_eval < 2147483647LL, "too many evaluated users");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200GAT_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(int32_t), st));
+  if (n_eval == 0) return kOk;
+  count_launch(), eval_ranks_kernel<<<(unsigned)n_eval, kEvalThreads, 0, st>>>(z, n_users, n_items, channels, users, candidates, n_eval,
+                                                                              n_candidates, ranks, n_bad);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

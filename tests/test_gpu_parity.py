@@ -466,3 +466,59 @@ def test_bf16_projection_tier(dev, kind, heads):
     m32.load_state_dict(m.state_dict())
     z32 = m32(feats.to(dev), ei.to(dev))
     assert (z32 - z).abs().max() > 1e-6 * z32.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ next rows f2 / f3
+def test_eval_ranks_against_oracle_and_reference_metrics(dev, golden_dir):
+    import b200gat
+    g = np.load(os.path.join(golden_dir, "eval_sampled.npz"))
+    nu, ni, neg_k = int(g["n_users"]), int(g["n_items"]), int(g["neg_k"])
+    train_pos = {}
+    for u, it in zip(g["train_users"], g["train_items"]):
+        train_pos.setdefault(int(u), []).append(int(it))
+    eval_pos = {int(u): int(i) for u, i in zip(g["eval_users"], g["eval_items"])}
+    np.random.seed(int(g["np_seed"]))
+    users, cands = O.sample_eval_candidates({u: np.array(v) for u, v in train_pos.items()}, eval_pos, ni, neg_k)
+    m = b200gat.CustomGAT(nu, ni, 128, 128, 2).to(dev).eval()
+    m.load_state_dict({k[len("param:"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param:")})
+    got = b200gat.eval_sampled(m, torch.from_numpy(g["item_feats"]).to(dev), torch.from_numpy(g["edge_index"]).to(dev), users, cands)
+    for k in ("recall@10", "recall@20", "ndcg@10", "ndcg@20"):
+        assert abs(got[k] - float(g["metric:" + k])) < 1e-9, (k, got[k], float(g["metric:" + k]))
+    # larger random case against the fp64 oracle: ranks are integers, identical except where a negative's score is within
+    # fp32 rounding of the positive's
+    torch.manual_seed(0)
+    nu, ni, c, q, k1 = 500, 3000, 128, 2000, 1001
+    z = torch.randn(nu + ni, c)
+    users = torch.randint(0, nu, (q,)); cands = torch.randint(0, ni, (q, k1))
+    ranks = b200gat.eval_ranks(z.to(dev), nu, users, cands).cpu().long()
+    ref_ranks, scores = O.eval_ranks(z.double(), nu, users, cands)
+    near = ((scores - scores[:, :1]).abs() < 1e-4).sum(1) - 1            # negatives that tie the positive within rounding
+    assert bool(((ranks - ref_ranks).abs() <= near).all())
+    assert float((ranks == ref_ranks).float().mean()) > 0.99
+    met, ref_met = b200gat.ranking_metrics(ranks), O.ranking_metrics(ref_ranks)
+    for k in met:
+        assert abs(met[k] - ref_met[k]) < 2e-3
+    with pytest.raises(IndexError):
+        b200gat.eval_ranks(z.to(dev), nu, torch.tensor([nu]), torch.zeros(1, 3, dtype=torch.long))
+
+
+def test_adam_matches_torch(dev):
+    """Same update rule as torch.optim.Adam(lr, weight_decay) (the reference's optimizer, train_gat_custom.py:335)."""
+    import b200gat
+    torch.manual_seed(0)
+    shapes = [(1000, 128), (128,), (1, 4, 128), (0, 128), (7,)]
+    p_ours = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes]
+    p_ref = [p.detach().clone().requires_grad_(True) for p in p_ours]
+    o_ours = b200gat.Adam(p_ours, lr=1e-3, weight_decay=1e-4)
+    o_ref = torch.optim.Adam(p_ref, lr=1e-3, weight_decay=1e-4)
+    for step in range(25):
+        for a, b in zip(p_ours, p_ref):
+            gr = torch.randn_like(a) * (10.0 if step % 5 == 0 else 0.1)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_ours.step(); o_ref.step()
+    for a, b in zip(p_ours, p_ref):
+        if a.numel():
+            np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    with pytest.raises(RuntimeError):
+        cpu_p = torch.randn(3, requires_grad=True); cpu_p.grad = torch.ones(3)
+        b200gat.Adam([cpu_p]).step()

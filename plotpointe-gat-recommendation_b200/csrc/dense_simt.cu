@@ -194,7 +194,7 @@ size_t tc_workspace_bytes(int heads);
 int tc_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int heads,
                    float* h, float* s, void* workspace, cudaStream_t st);
 int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
-                   int64_t n_rows, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st);
+                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st);
 int tc_linear_fwd(const float* x, const float* W, const float* bias, int64_t n_rows, float* out, int64_t ldo, void* workspace,
                   cudaStream_t st);
 int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, void* workspace, cudaStream_t st);
@@ -246,8 +246,8 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const int HC = heads * channels, F = in_features, H2 = 2 * heads;
-  if (n_rows > 0 && heads == 1 && tc_supported(in_features, heads, channels))
-    return tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, dx, dW, da_src, da_dst, workspace, st);
+  if (n_rows > 0 && tc_supported(in_features, heads, channels))
+    return tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, heads, dx, dW, da_src, da_dst, workspace, st);
   float* part = (float*)workspace;                       // [kSlabs, HC + 2H, F]
   float* v = part + (size_t)kSlabs * (HC + H2) * F + (size_t)kSlabs * channels;  // [2H, F]
   if (n_rows == 0) {

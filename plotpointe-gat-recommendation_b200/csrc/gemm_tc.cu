@@ -201,8 +201,10 @@ struct FwdParams {
   const float* att_src;   // [heads, 128]
   const float* att_dst;
   float* s;               // [n_rows, 2*heads]
-  const float* ds;        // [n_rows, 2] (ds_src, ds_dst), DX flavour (heads == 1)
+  const float* ds;        // DX flavour: [n_rows, ds_ld] logit gradients; this launch uses columns ds_src_col / ds_dst_col
   int heads;
+  int ds_ld, ds_src_col, ds_dst_col;
+  int accumulate;         // DX flavour, heads > 1: out += result (one launch per head, the contraction runs over all heads)
 };
 
 // FLAVOR 0: logits epilogue (projection forward); 1: A corrected on the fly (dx); 2: bias added in the epilogue (plain Linear)
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
         const int64_t row = row0 + r0 + 32 * i;
         if (row < p.n_rows) {
           L.v[i] = ld_stream4(p.a + row * p.lda + kb * kKB + chunk * 4);
-          if (DX) { L.ds[i][0] = __ldg(p.ds + row * 2); L.ds[i][1] = __ldg(p.ds + row * 2 + 1); }
+          if (DX) { L.ds[i][0] = __ldg(p.ds + row * p.ds_ld + p.ds_src_col); L.ds[i][1] = __ldg(p.ds + row * p.ds_ld + p.ds_dst_col); }
         } else {
           L.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (DX) L.ds[i][0] = L.ds[i][1] = 0.f;
@@ -387,9 +389,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = (lane >> 3) + 4 * i, ch = lane & 7;
-          const float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + (((ch ^ r) & 7) << 4));
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + (((ch ^ r) & 7) << 4));
           const int64_t row = row0 + r;
-          if (row < p.n_rows) st_stream4(p.out + row * p.ldo + head * kTileN + c * 32 + ch * 4, o);
+          if (row < p.n_rows) {
+            float* dst = p.out + row * p.ldo + head * kTileN + c * 32 + ch * 4;
+            if (DX && p.accumulate) {
+              const float4 prev = ld_stream4(dst);
+              o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+            }
+            st_stream4(dst, o);
+          }
         }
         __syncwarp();
       }
@@ -619,8 +628,10 @@ constexpr int kDwGroup = 8;
 constexpr int kDwSmem = 1024 + kDwStages * kDwStageBytes + kDwEpiWarps * 32 * 128 + 2 * kTileN * 4 + 256;
 
 struct DwParams {
-  const float* dh;   // [n_rows, 128] aggregation part of dh
-  const float* ds;   // [n_rows, 2]
+  const float* dh;   // [n_rows, ld_dh] aggregation part of dh (this head's 128 columns)
+  int64_t ld_dh;
+  const float* ds;   // [n_rows, ds_ld], columns ds_src_col / ds_dst_col
+  int ds_ld, ds_src_col, ds_dst_col;
   const float* x;    // [n_rows, 128]
   const float* att_src;
   const float* att_dst;
@@ -689,10 +700,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
       for (int i = 0; i < 4; ++i) {             // warp w handles rows w, w+8, w+16, w+24 of the stage
         const int64_t row = row0 + warp + 8 * i;
         if (row < r_end) {
-          L.g[i] = ld_stream4(p.dh + row * 128 + c4 * 4);
+          L.g[i] = ld_stream4(p.dh + row * p.ld_dh + c4 * 4);
           L.xv[i] = ld_stream4(p.x + row * 128 + c4 * 4);
-          L.d0[i] = p.ds ? __ldg(p.ds + row * 2) : 0.f;
-          L.d1[i] = p.ds ? __ldg(p.ds + row * 2 + 1) : 0.f;
+          L.d0[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_src_col) : 0.f;
+          L.d1[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_dst_col) : 0.f;
         } else {
           L.g[i] = L.xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           L.d0[i] = L.d1[i] = 0.f;
@@ -905,35 +916,42 @@ int tc_project_fwd(const float* x, const float* W, const float* a_src, const flo
   return kOk;
 }
 
-// heads == 1:  dx = dh_full W;  dW = dh_full^T x;  da_src/da_dst.  dh is NOT modified (the correction is applied on the fly).
+// dx = dh_full W;  dW = dh_full^T x;  da_src/da_dst  (per head: 128-column slices of dh, rows of W).  dh is NOT modified
+// (the logit-gradient correction is applied on the fly).  heads > 1: dx accumulates over one launch per head.
 int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
-                   int64_t n_rows, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st) {
+                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st) {
   int rc = ensure_attrs();
   if (rc) return rc;
   float* image = (float*)workspace;
   float* part_dw = image + tc::kBImageBytes / 4;
   float* part_v = part_dw + (size_t)kNumSMs * 128 * 128;
   float* v = part_v + (size_t)kNumSMs * 2 * 128;
-  if (dx) {
-    // B(n = f, k = c) = W[c, f]  ->  ldn = 1, ldk = 128
-    count_launch(), tc::build_b_image_kernel<<<ceil_div(128 * 128 / 4, 256), 256, 0, st>>>(W, 1, 128, image);
-    tc::FwdParams p{};
-    p.a = dh; p.lda = 128; p.b_images = image; p.out = dx; p.ldo = 128; p.n_rows = n_rows;
-    p.att_src = a_src; p.att_dst = a_dst; p.s = nullptr; p.ds = ds; p.heads = 1;
-    const int64_t n_tiles = (n_rows + 127) / 128;
-    count_launch(), tc::proj_kernel<1><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
-  }
-  tc::DwParams q{};
-  q.dh = dh; q.ds = ds; q.x = x; q.att_src = a_src; q.att_dst = a_dst; q.n_rows = n_rows;
+  const int64_t n_tiles = (n_rows + 127) / 128;
   int64_t per = (n_rows + kNumSMs - 1) / kNumSMs;
   per = (per + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
-  q.rows_per_cta = per;
   const int grid = (int)((n_rows + per - 1) / per);
-  q.part_dw = part_dw; q.part_v = part_v;
-  count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
-  count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128, dW);
-  count_launch(), tc::reduce_parts_kernel<<<1, 256, 0, st>>>(part_v, grid, 256, 256, v);
-  count_launch(), tc::att_grad_tc_kernel<<<ceil_div(128 * 32, 128), 128, 0, st>>>(W, v, da_src, da_dst);
+  for (int hh = 0; hh < heads; ++hh) {
+    const float* Wh = W + (size_t)hh * 128 * 128;
+    if (dx) {
+      // B(n = f, k = c) = W_h[c, f]  ->  ldn = 1, ldk = 128
+      count_launch(), tc::build_b_image_kernel<<<ceil_div(128 * 128 / 4, 256), 256, 0, st>>>(Wh, 1, 128, image);
+      tc::FwdParams p{};
+      p.a = dh + hh * 128; p.lda = (int64_t)heads * 128; p.b_images = image; p.out = dx; p.ldo = 128; p.n_rows = n_rows;
+      p.att_src = a_src + hh * 128; p.att_dst = a_dst + hh * 128; p.s = nullptr; p.ds = ds; p.heads = 1;
+      p.ds_ld = 2 * heads; p.ds_src_col = hh; p.ds_dst_col = heads + hh; p.accumulate = hh > 0;
+      count_launch(), tc::proj_kernel<1><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
+    }
+    tc::DwParams q{};
+    q.dh = dh + hh * 128; q.ld_dh = (int64_t)heads * 128; q.ds = ds; q.ds_ld = 2 * heads; q.ds_src_col = hh; q.ds_dst_col = heads + hh;
+    q.x = x; q.att_src = a_src + hh * 128; q.att_dst = a_dst + hh * 128; q.n_rows = n_rows;
+    q.rows_per_cta = per;
+    q.part_dw = part_dw; q.part_v = part_v;
+    count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
+    count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128,
+                                                                                      dW + (size_t)hh * 128 * 128);
+    count_launch(), tc::reduce_parts_kernel<<<1, 256, 0, st>>>(part_v, grid, 256, 256, v);
+    count_launch(), tc::att_grad_tc_kernel<<<ceil_div(128 * 32, 128), 128, 0, st>>>(Wh, v, da_src + hh * 128, da_dst + hh * 128);
+  }
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
@@ -960,7 +978,8 @@ int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, voi
   if (rc) return rc;
   float* part_dw = (float*)workspace + tc::kBImageBytes / 4;
   tc::DwParams q{};
-  q.dh = dy; q.ds = nullptr; q.x = x; q.att_src = nullptr; q.att_dst = nullptr; q.n_rows = n_rows;
+  q.dh = dy; q.ld_dh = 128; q.ds = nullptr; q.ds_ld = 0; q.ds_src_col = 0; q.ds_dst_col = 0;
+  q.x = x; q.att_src = nullptr; q.att_dst = nullptr; q.n_rows = n_rows;
   int64_t per = (n_rows + kNumSMs - 1) / kNumSMs;
   per = (per + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
   q.rows_per_cta = per;

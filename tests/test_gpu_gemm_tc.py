@@ -81,3 +81,39 @@ def test_projection_backward(n):
     for name, a, b, r in zip(("dx", "dW", "da_src", "da_dst"), out_tc, out_32, ref):
         assert _err(b, r) < 1e-5, (name, "fp32", _err(b, r))
         assert _err(a, r) < 1e-5, (name, "tc", _err(a, r))
+
+
+@pytest.mark.parametrize("n", [129, 20011])
+@pytest.mark.parametrize("heads", [2, 4])
+def test_projection_backward_multi_head(n, heads):
+    """heads > 1: one tensor-core launch per head, dx accumulated over heads."""
+    from b200gat import _lib as lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(n + heads)
+    x = torch.randn(n, 128, device=dev)
+    W = torch.randn(heads * 128, 128, device=dev) * 0.1
+    a_s, a_d = torch.randn(heads, 128, device=dev), torch.randn(heads, 128, device=dev)
+    dh = torch.randn(n, heads * 128, device=dev)
+    ds = torch.randn(n, 2 * heads, device=dev)
+    outs = {}
+    try:
+        for mode in (lib.GEMM_TF32X3, lib.GEMM_FP32):
+            lib.set_gemm_mode(mode)
+            dx = torch.empty(n, 128, device=dev)
+            dW, da_s, da_d = torch.empty_like(W), torch.empty_like(a_s), torch.empty_like(a_d)
+            wsb = lib.dense_workspace_bytes(heads, 128, 128)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(W), lib.ptr(a_s), lib.ptr(a_d), lib.ptr(dh.clone()), lib.ptr(ds), n,
+                     128, heads, 128, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d), lib.ptr(ws), wsb, lib.stream())
+            torch.cuda.synchronize()
+            outs[mode] = (dx, dW, da_s, da_d)
+    finally:
+        lib.set_gemm_mode(lib.GEMM_TF32X3)
+    x64, W64, dh64, ds64 = (t.double().cpu() for t in (x, W, dh, ds))
+    a_s64, a_d64 = a_s.double().cpu(), a_d.double().cpu()
+    dhf = dh64.view(n, heads, 128) + ds64[:, :heads, None] * a_s64 + ds64[:, heads:, None] * a_d64
+    h64 = (x64 @ W64.t()).view(n, heads, 128)
+    ref = (dhf.reshape(n, -1) @ W64, dhf.reshape(n, -1).t() @ x64, (h64 * ds64[:, :heads, None]).sum(0), (h64 * ds64[:, heads:, None]).sum(0))
+    for name, a, b, r in zip(("dx", "dW", "da_src", "da_dst"), outs[lib.GEMM_TF32X3], outs[lib.GEMM_FP32], ref):
+        assert _err(b, r) < 1e-5, (name, "fp32", _err(b, r))
+        assert _err(a, r) < 1e-5, (name, "tc", _err(a, r))

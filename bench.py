@@ -195,6 +195,7 @@ def run_ours(args):
         except Exception:
             pass
 
+    extras = next_row_extras(model, fd, eid, nu, ni, dev)
     cpu = cpu_baseline(args, nu, ni, ei, feats, (u, i, j)) if not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": e * LAYERS / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -210,8 +211,43 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "epoch_time_ms": ms_step, "graph_build_ms": round(graph_build_ms, 2), "loss": lv,
         "breakdown_ms_per_step": {k_: round(v["ms_per_step"], 4) for k_, v in sorted(per_call.items())},
+        "next_rows": extras,
     }
     print(json.dumps(line))
+
+
+def next_row_extras(model, fd, eid, nu, ni, dev, n_eval=20000, neg_k=1000):
+    """Measurement of the widened rows: sampled-evaluation ranks, 1 positive + 1000 negatives per user
+    as in the reference's eval_sampled (eval_neg_k = 1000), device time with CUDA events; the oracle on a small sample."""
+    import b200gat
+    from oracle import gat_oracle as O
+    g = torch.Generator().manual_seed(7)
+    users = torch.randint(0, nu, (n_eval,), generator=g)
+    cands = torch.randint(0, ni, (n_eval, neg_k + 1), generator=g)
+    model.eval()
+    with torch.no_grad():
+        z = model(fd, eid)
+    model.train()
+    ud, cd = users.to(dev), cands.to(dev)
+    b200gat.eval_ranks(z, nu, ud, cd)
+    torch.cuda.synchronize()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        ranks = b200gat.eval_ranks(z, nu, ud, cd)
+    b_.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b_) / 3
+    zc = z.cpu()
+    ns = 500
+    t0 = time.perf_counter()
+    ref_ranks, _ = O.eval_ranks(zc, nu, users[:ns], cands[:ns])
+    cpu_s = time.perf_counter() - t0
+    agree = float((ranks[:ns].cpu().long() == ref_ranks).float().mean())
+    gather_bytes = n_eval * (neg_k + 2) * z.shape[1] * 4
+    return {"eval_ranks": {"users_per_s": n_eval / (ms * 1e-3), "ms": round(ms, 3), "n_users": n_eval, "candidates": neg_k + 1,
+                           "achieved_gbs": round(gather_bytes / (ms * 1e-3) / 1e9, 1),
+                           "cpu_oracle_users_per_s": round(ns / cpu_s, 1), "rank_agreement_with_oracle": agree}}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms

@@ -1,0 +1,315 @@
+// Item-Item cosine kNN on the GPU -- replaces graphs/build_ii_knn.py:56-99, which computes
+// sklearn's cosine_similarity in 1000-row batches on the CPU (O(n^2 d), 78-100 s for 63k items in the reference's report)
+// and keeps the k best neighbours of every item.
+//
+// Three passes:
+//   1. prepare   : the reference's two normalisations (x / (|x| + 1e-8), then sklearn's row normalisation) in fp32;
+//                  writes the normalised fp32 rows and a bf16 image of them, already laid out the way the UMMA wants
+//                  its shared-memory operands (128-row blocks, 128-byte swizzle), so that a whole operand tile is ONE
+//                  contiguous 32 KB bulk copy (TMA unit).
+//   2. candidates: bf16 tcgen05 GEMM of the image against itself.  A CTA keeps a 256-row block of A resident and streams
+//                  every 128-row block of B through a 3-deep ring of bulk copies; accumulators live in TMEM (2 row
+//                  blocks x 2 stages x 128 columns = all 512 columns); 8 epilogue warps read them back (tcgen05.ld) and
+//                  keep, per row, the 64 best APPROXIMATE similarities seen so far (threshold compare, rare insertion).
+//   3. re-rank   : exact fp32 dot products for the 64 candidates of every row (warp per row), top-k selection in
+//                  descending order, min_similarity filter.  The final similarities are plain fp32 like the reference's;
+//                  the bf16 pass only decides WHICH 64 columns get the exact treatment, and a per-row guard counts the
+//                  rows where the approximate margin would not have been safe.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+namespace knn {
+
+using namespace tc;
+
+constexpr int kD = 128;                    // embedding width handled by the tensor-core path
+constexpr int kBlk = 128;                  // rows per image block
+constexpr int kBlkBytes = kBlk * kD * 2;   // 32 KB: [kb 2][128 rows][128 B swizzled]
+constexpr int kCand = 64;                  // approximate candidates kept per row
+constexpr int kBStages = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA warp + producer warp
+constexpr int kSmem = 1024 + 2 * kBlkBytes + kBStages * kBlkBytes + 256;
+constexpr float kApproxErr = 2e-3f;        // bound on |bf16 similarity - exact| used by the safety guard (unit rows, d = 128)
+
+// ---- 1. prepare -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prepare_kernel(const float* __restrict__ emb, int64_t n, int64_t n_pad,
+                                                      float* __restrict__ en, uint8_t* __restrict__ image) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_pad) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < n) {
+    v = ldg4(emb + r * kD + lane * 4);
+    const float nrm = sqrtf(warp_sum(dot4(v, v)));                 // np.linalg.norm(embeddings, axis=1)
+    const float s1 = 1.f / (nrm + 1e-8f);                          // embeddings / (norms + 1e-8)      (:56-57)
+    v.x *= s1; v.y *= s1; v.z *= s1; v.w *= s1;
+    float n2 = sqrtf(warp_sum(dot4(v, v)));                        // sklearn cosine_similarity normalises again (:76)
+    if (n2 == 0.f) n2 = 1.f;
+    const float s2 = 1.f / n2;
+    v.x *= s2; v.y *= s2; v.z *= s2; v.w *= s2;
+  }
+  *reinterpret_cast<float4*>(en + r * kD + lane * 4) = v;
+  // bf16 image: block = r / 128, row in block = r % 128, k-block = (lane*4) / 64, 16-byte chunk = ((lane*4) % 64) / 8
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  const int rb = (int)(r % kBlk), kb = lane >> 4, e = (lane & 15) * 4;   // e: element offset inside the 64-wide k-block
+  uint8_t* dst = image + (r / kBlk) * kBlkBytes + kb * (kBlk * 128) + sw128(rb, e >> 3) + (e & 7) * 2;
+  *reinterpret_cast<uint2*>(dst) = pk;
+}
+
+// ---- 2. candidates --------------------------------------------------------------------------------------------------
+// insert (v, col) into the descending list; rare once the threshold has warmed up, so it is kept out of line
+__device__ __noinline__ float list_insert(float* cs, int* ci, float v, int col) {
+  int p = kCand - 1;
+  while (p > 0 && cs[p - 1] < v) { cs[p] = cs[p - 1]; ci[p] = ci[p - 1]; --p; }
+  cs[p] = v;
+  ci[p] = col;
+  return cs[kCand - 1];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks,
+                                                                 float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + 2 * kBlkBytes, sBar = sB + kBStages * kBlkBytes;
+  const uint32_t bar_afull = sBar, bar_aempty = sBar + 8, bar_bfull = sBar + 16, bar_bempty = sBar + 48, bar_tfull = sBar + 80,
+                 bar_tempty = sBar + 96;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_super = (n_blocks + 1) / 2;      // 256-row super blocks
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aempty, 1);
+    for (int i = 0; i < kBStages; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == kEpiWarps + 1) {
+    // =============================== producer: bulk copies through the TMA unit ===============================
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0, aph = 0;
+      for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+        mbar_wait(bar_aempty, aph ^ 1);
+        mbar_expect_tx(bar_afull, 2 * kBlkBytes);
+        const int a0 = 2 * sb, a1 = min(2 * sb + 1, n_blocks - 1);     // a1 clamps on an odd tail: its rows are ignored
+        bulk_g2s(sA, image + (size_t)a0 * kBlkBytes, kBlkBytes, bar_afull);
+        bulk_g2s(sA + kBlkBytes, image + (size_t)a1 * kBlkBytes, kBlkBytes, bar_afull);
+        for (int j = 0; j < n_blocks; ++j) {
+          mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+          mbar_expect_tx(bar_bfull + 8 * bs, kBlkBytes);
+          bulk_g2s(sB + bs * kBlkBytes, image + (size_t)j * kBlkBytes, kBlkBytes, bar_bfull + 8 * bs);
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        }
+        aph ^= 1;
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // =============================== MMA issuer ===============================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      uint32_t bs = 0, bph = 0, ts = 0, tph = 0, aph = 0;
+      for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+        mbar_wait(bar_afull, aph);
+        for (int j = 0; j < n_blocks; ++j) {
+          mbar_wait(bar_tempty + 8 * ts, tph ^ 1);
+          mbar_wait(bar_bfull + 8 * bs, bph);
+          tc_fence_after();
+          const uint32_t b0 = sB + bs * kBlkBytes;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint32_t d = tmem_base + (ts * 2 + a) * 128, a0 = sA + a * kBlkBytes;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d, make_desc(a0 + kb * (kBlk * 128) + k * 32, 16, 1024), make_desc(b0 + kb * (kBlk * 128) + k * 32, 16, 1024),
+                          idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_bempty + 8 * bs);
+          umma_commit(bar_tfull + 8 * ts);
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+          if (++ts == 2) { ts = 0; tph ^= 1; }
+        }
+        umma_commit(bar_aempty);
+        aph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue: running top-64 per row ==========================================
+    const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
+    float cs[kCand];
+    int ci[kCand];
+    uint32_t ts = 0, tph = 0;
+    for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+      const int64_t row = ((int64_t)(2 * sb + a)) * kBlk + q * 32 + lane;
+      const bool live = (2 * sb + a) < n_blocks && row < n;
+#pragma unroll 1
+      for (int k = 0; k < kCand; ++k) { cs[k] = -INFINITY; ci[k] = -1; }
+      float thr = live ? -INFINITY : INFINITY;      // padding rows never insert
+      for (int j = 0; j < n_blocks; ++j) {
+        mbar_wait(bar_tfull + 8 * ts, tph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (ts * 2 + a) * 128 + c * 32, v);
+          const int64_t col0 = (int64_t)j * kBlk + c * 32;
+          if ((row >= col0 && row < col0 + 32) || col0 + 32 > n) {   // chunk holds the diagonal or runs past the last item
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (v[t] > thr && col0 + t != row && col0 + t < n) thr = list_insert(cs, ci, v[t], (int)(col0 + t));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (v[t] > thr) thr = list_insert(cs, ci, v[t], (int)(col0 + t));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * ts);
+        if (++ts == 2) { ts = 0; tph ^= 1; }
+      }
+      if (live) {
+#pragma unroll 1
+        for (int k = 0; k < kCand; ++k) {
+          cand_sim[row * kCand + k] = cs[k];
+          cand_idx[row * kCand + k] = ci[k];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kEpiWarps) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- 3. exact re-rank ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ en, int64_t n, const float* __restrict__ cand_sim,
+                                                     const int32_t* __restrict__ cand_idx, int k, float min_similarity,
+                                                     int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
+                                                     int32_t* __restrict__ counts, int32_t* __restrict__ n_unsafe) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const float4 u = ldg4(en + r * kD + lane * 4);
+  // lane l owns candidates l and l + 32
+  int id[2] = {cand_idx[r * kCand + lane], cand_idx[r * kCand + 32 + lane]};
+  float ex[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    for (int c0 = 0; c0 < 32; c0 += 4) {
+      float d[4];
+      int cid[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        cid[t] = __shfl_sync(kFull, id[half], c0 + t);
+        d[t] = cid[t] >= 0 ? dot4(u, ldg4(en + (size_t)cid[t] * kD + lane * 4)) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float s = warp_sum(d[t]);
+        if (lane == c0 + t && cid[t] >= 0) ex[half] = s;
+      }
+    }
+  }
+  const float approx_last = cand_sim[r * kCand + kCand - 1];   // smallest approximate similarity that made the list
+  // k rounds of warp arg-max over the 64 exact similarities (ties: lower candidate slot first)
+  float kth = -INFINITY;
+  int valid = 0;
+  for (int round = 0; round < k; ++round) {
+    float best = ex[0];
+    int slot = lane;
+    if (ex[1] > best) { best = ex[1]; slot = lane + 32; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(kFull, best, o);
+      const int os = __shfl_xor_sync(kFull, slot, o);
+      if (ob > best || (ob == best && os < slot)) { best = ob; slot = os; }
+    }
+    const int wid = __shfl_sync(kFull, id[slot >> 5], slot & 31);
+    if (lane == (slot & 31)) ex[slot >> 5] = -INFINITY;           // consumed
+    const bool ok = best > -INFINITY && best >= min_similarity;  // the list is descending: once false, always false
+    if (lane == 0) {
+      nbr_sim[r * k + round] = best > -INFINITY ? best : 0.f;
+      nbr_idx[r * k + round] = best > -INFINITY ? wid : -1;
+    }
+    valid += ok ? 1 : 0;
+    kth = best;
+  }
+  if (lane == 0) {
+    counts[r] = valid;
+    // guard: a column outside the 64 candidates has approximate similarity <= approx_last, hence exact similarity
+    // <= approx_last + err; the selection is provably the exact top-k iff the exact k-th beats that bound
+    if (n - 1 > kCand && kth > -INFINITY && !(kth > approx_last + kApproxErr)) atomicAdd(n_unsafe, 1);
+  }
+}
+
+}  // namespace knn
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* bytes) {
+  B200GAT_CHECK_ARG(bytes && n_items >= 0, "bad args");
+  if (dim != knn::kD) {
+    set_error("cosine kNN: embedding width %d is not supported on the tensor-core path (128 only)", dim);
+    return kErrUnsupported;
+  }
+  const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
+  *bytes = (size_t)n_pad * knn::kD * 4 /*en*/ + (size_t)n_pad * knn::kD * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ + 1024;
+  return kOk;
+}
+
+// nbr_idx / nbr_sim [n, k]: the k most similar other items of every item, descending (unused slots: -1 / 0);
+// counts[n]: how many of them pass `>= min_similarity` (they are a prefix).  n_unsafe: device int32, number of rows
+// whose bf16 candidate margin was too thin to prove exactness (0 in every test so far; callers should check it).
+extern "C" int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim, int k, float min_similarity,
+                                      int32_t* nbr_idx, float* nbr_sim, int32_t* counts, int32_t* n_unsafe, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(emb && nbr_idx && nbr_sim && counts && n_unsafe && workspace, "null pointer");
+  B200GAT_CHECK_ARG(k >= 1 && k <= 32, "k=%d must be in [1, 32]", k);
+  size_t need;
+  int rc = b200gat_knn_workspace_bytes(n_items, dim, &need);
+  if (rc) return rc;
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  B200GAT_CHECK_ARG(n_items < 2147483647LL, "too many items");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200GAT_CUDA(cudaMemsetAsync(n_unsafe, 0, sizeof(int32_t), st));
+  if (n_items == 0) return kOk;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, knn::kSmem));
+    attr_done = true;
+  }
+  const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
+  const int n_blocks = (int)(n_pad / knn::kBlk);
+  char* p = (char*)workspace;
+  float* en = (float*)p;                                p += (size_t)n_pad * knn::kD * 4;
+  uint8_t* image = (uint8_t*)p;                         p += (size_t)n_pad * knn::kD * 2;
+  float* cand_sim = (float*)p;                          p += (size_t)n_pad * knn::kCand * 4;
+  int32_t* cand_idx = (int32_t*)p;
+  count_launch(), knn::prepare_kernel<<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
+  const int n_super = (n_blocks + 1) / 2;
+  count_launch(), knn::candidates_kernel<<<n_super < kNumSMs ? n_super : kNumSMs, knn::kThreads, knn::kSmem, st>>>(image, n_items, n_blocks,
+                                                                                                                  cand_sim, cand_idx);
+  count_launch(), knn::rerank_kernel<<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
+                                                                                  nbr_idx, nbr_sim, counts, n_unsafe);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

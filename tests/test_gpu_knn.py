@@ -1,0 +1,64 @@
+"""GPU: the cosine kNN builder (next row f1) against the oracle's restatement of graphs/build_ii_knn.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gat_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, seed, clustered):
+    rng = np.random.default_rng(seed)
+    if clustered:
+        centers = rng.standard_normal((max(n // 40, 2), 128))
+        x = centers[rng.integers(0, len(centers), n)] + 0.6 * rng.standard_normal((n, 128))
+    else:
+        x = rng.standard_normal((n, 128))
+    return (x * rng.uniform(0.5, 3.0, size=(n, 1))).astype(np.float32)     # un-normalised rows, like raw embeddings
+
+
+@pytest.mark.parametrize("n,clustered,k,min_sim", [(50, False, 20, -1.0), (129, True, 20, 0.3), (3000, True, 20, 0.3),
+                                                   (2049, False, 5, -1.0), (5000, True, 20, 0.5)])
+def test_knn_matches_oracle(n, clustered, k, min_sim):
+    import b200gat
+    emb = _data(n, n, clustered)
+    rows, cols, sims = O.build_ii_knn(emb, k=min(k, n - 1), min_similarity=min_sim, batch_size=1000)
+    r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=min(k, n - 1), min_similarity=min_sim)
+    r, c, s = r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
+    assert r.dtype == np.int32 and c.dtype == np.int32 and s.dtype == np.float32
+    # exact dense similarities (fp64) to judge near-ties
+    en = emb.astype(np.float64)
+    en /= np.linalg.norm(en, axis=1, keepdims=True)
+    full = en @ en.T
+    np.fill_diagonal(full, -np.inf)
+    # every emitted pair carries its true similarity (fp32 rounding), rows ascending, similarities descending inside a row
+    np.testing.assert_allclose(s, full[r, c], rtol=0, atol=3e-6)
+    assert np.all(np.diff(r) >= 0) and np.all((np.diff(s) <= 1e-6) | (np.diff(r) > 0))
+    assert np.all(r != c) and np.all(s >= min_sim - 3e-6)
+    # same edge count per row as the reference arithmetic, up to pairs that sit within rounding of the k-th value or of
+    # the min_similarity cut
+    cnt_ref = np.bincount(rows, minlength=n)
+    cnt = np.bincount(r, minlength=n)
+    kk = min(k, n - 1)
+    kth = -np.sort(-full, axis=1)[:, kk - 1]
+    near_cut = ((np.abs(full - min_sim) < 5e-6).sum(1) > 0)
+    assert np.all((cnt == cnt_ref) | near_cut)
+    # the neighbour sets agree except for columns within rounding of the k-th best
+    ref_sets = [set() for _ in range(n)]
+    for a, b in zip(rows, cols):
+        ref_sets[a].add(int(b))
+    bad = 0
+    for a, b in zip(r, c):
+        if int(b) not in ref_sets[a] and abs(full[a, b] - max(kth[a], min_sim)) > 5e-6:
+            bad += 1
+    assert bad == 0
+    assert len(r) >= 0.999 * len(rows)
+
+
+def test_knn_rejects_unsupported(monkeypatch):
+    import b200gat
+    with pytest.raises(RuntimeError):
+        b200gat.build_ii_knn(torch.randn(10, 128))                 # CPU tensor
+    with pytest.raises(RuntimeError, match="128"):
+        b200gat.build_ii_knn(torch.randn(10, 384).cuda())          # the text embeddings (384-d) are not supported yet

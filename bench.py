@@ -245,7 +245,29 @@ def next_row_extras(model, fd, eid, nu, ni, dev, n_eval=20000, neg_k=1000):
     cpu_s = time.perf_counter() - t0
     agree = float((ranks[:ns].cpu().long() == ref_ranks).float().mean())
     gather_bytes = n_eval * (neg_k + 2) * z.shape[1] * 4
-    return {"eval_ranks": {"users_per_s": n_eval / (ms * 1e-3), "ms": round(ms, 3), "n_users": n_eval, "candidates": neg_k + 1,
+    # f1: cosine kNN (k=20, min_similarity 0.3) at the reference's own item count (63,001 interacted items,
+    # PHASE0_REPORT.md:190-193: 77.91 s on an n1-highmem-8); oracle restatement on a 6,000-item sample
+    gk = torch.Generator().manual_seed(11)
+    nk = 63001
+    centers = torch.randn(nk // 50, 128, generator=gk)
+    emb = centers[torch.randint(0, centers.shape[0], (nk,), generator=gk)] + 0.7 * torch.randn(nk, 128, generator=gk)
+    embd = emb.to(dev)
+    b200gat.knn_neighbors(embd, 20, 0.3)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(3):
+        _, _, counts = b200gat.knn_neighbors(embd, 20, 0.3)
+    b_.record()
+    torch.cuda.synchronize()
+    knn_ms = a.elapsed_time(b_) / 3
+    t0 = time.perf_counter()
+    O.build_ii_knn(emb[:6000].numpy(), 20, 0.3)
+    knn_cpu_s = time.perf_counter() - t0
+    knn = {"items": nk, "k": 20, "ms": round(knn_ms, 2), "item_pairs_per_s": nk * nk / (knn_ms * 1e-3),
+           "tflops_bf16_equivalent": round(2.0 * nk * nk * 128 / (knn_ms * 1e-3) / 1e12, 1), "edges": int(counts.sum()),
+           "cpu_oracle_item_pairs_per_s": round(6000 * 6000 / knn_cpu_s, 1), "cpu_sample": "first 6000 items, numpy restatement",
+           "reference_published_s": 77.91}
+    return {"knn": knn, "eval_ranks": {"users_per_s": n_eval / (ms * 1e-3), "ms": round(ms, 3), "n_users": n_eval, "candidates": neg_k + 1,
                            "achieved_gbs": round(gather_bytes / (ms * 1e-3) / 1e9, 1),
                            "cpu_oracle_users_per_s": round(ns / cpu_s, 1), "rank_agreement_with_oracle": agree}}
 

@@ -10,10 +10,10 @@
 //   2. candidates: bf16 tcgen05 GEMM of the image against itself.  A CTA keeps a 256-row block of A resident and streams
 //                  every 128-row block of B through a 3-deep ring of bulk copies; accumulators live in TMEM (2 row
 //                  blocks x 2 stages x 128 columns = all 512 columns); 8 epilogue warps read them back (tcgen05.ld) and
-//                  keep, per row, the 64 best APPROXIMATE similarities seen so far (threshold compare, rare insertion).
-//   3. re-rank   : exact fp32 dot products for the 64 candidates of every row (warp per row), top-k selection in
+//                  keep, per row, the 48 best APPROXIMATE similarities seen so far in a register-resident list.
+//   3. re-rank   : exact fp32 dot products for the 48 candidates of every row (warp per row), top-k selection in
 //                  descending order, min_similarity filter.  The final similarities are plain fp32 like the reference's;
-//                  the bf16 pass only decides WHICH 64 columns get the exact treatment, and a per-row guard counts the
+//                  the bf16 pass only decides WHICH 48 columns get the exact treatment, and a per-row guard counts the
 //                  rows where the approximate margin would not have been safe.
 #include <cuda_bf16.h>
 
@@ -29,7 +29,7 @@ using namespace tc;
 constexpr int kD = 128;                    // embedding width handled by the tensor-core path
 constexpr int kBlk = 128;                  // rows per image block
 constexpr int kBlkBytes = kBlk * kD * 2;   // 32 KB: [kb 2][128 rows][128 B swizzled]
-constexpr int kCand = 64;                  // approximate candidates kept per row
+constexpr int kCand = 48;                  // approximate candidates kept per row (register-resident list)
 constexpr int kBStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA warp + producer warp
@@ -65,14 +65,29 @@ __global__ void __launch_bounds__(128) prepare_kernel(const float* __restrict__ 
 }
 
 // ---- 2. candidates --------------------------------------------------------------------------------------------------
-// insert (v, col) into the descending list; rare once the threshold has warmed up, so it is kept out of line
-__device__ __noinline__ float list_insert(float* cs, int* ci, float v, int col) {
-  int p = kCand - 1;
-  while (p > 0 && cs[p - 1] < v) { cs[p] = cs[p - 1]; ci[p] = ci[p - 1]; --p; }
-  cs[p] = v;
-  ci[p] = col;
-  return cs[kCand - 1];
-}
+// The running top-64 of a row lives in REGISTERS as a descending list.  Insertion is a fully unrolled bubble pass
+// (compare, conditional swap) -- no local memory, no dependent address chain; lanes that have nothing to insert carry
+// v = -inf through the pass and leave their list untouched, so the pass runs once per warp per accepted column.
+struct TopList {
+  float s[kCand];
+  int i[kCand];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) { s[k] = -INFINITY; i[k] = -1; }
+  }
+  __device__ __forceinline__ void insert(float v, int col) {
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) {
+      const bool sw = v > s[k];
+      const float ts = s[k];
+      const int ti = i[k];
+      s[k] = sw ? v : ts;
+      i[k] = sw ? col : ti;
+      v = sw ? ts : v;
+      col = sw ? ti : col;
+    }
+  }
+};
 
 __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks,
                                                                  float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx) {
@@ -153,14 +168,12 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
   } else {
     // =============================== epilogue: running top-64 per row ==========================================
     const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
-    float cs[kCand];
-    int ci[kCand];
+    TopList top;
     uint32_t ts = 0, tph = 0;
     for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
       const int64_t row = ((int64_t)(2 * sb + a)) * kBlk + q * 32 + lane;
       const bool live = (2 * sb + a) < n_blocks && row < n;
-#pragma unroll 1
-      for (int k = 0; k < kCand; ++k) { cs[k] = -INFINITY; ci[k] = -1; }
+      top.reset();
       float thr = live ? -INFINITY : INFINITY;      // padding rows never insert
       for (int j = 0; j < n_blocks; ++j) {
         mbar_wait(bar_tfull + 8 * ts, tph);
@@ -170,14 +183,23 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (ts * 2 + a) * 128 + c * 32, v);
           const int64_t col0 = (int64_t)j * kBlk + c * 32;
-          if ((row >= col0 && row < col0 + 32) || col0 + 32 > n) {   // chunk holds the diagonal or runs past the last item
+          // Per lane: bit mask of the columns of this chunk that beat the row's current threshold; then ONE copy of
+          // the insertion pass in a loop -- each lane feeds its own next pending column, so the loop runs
+          // max-over-lanes(popcount) times (usually 0 or 1) and the code stays a few KB (a pass per column position was
+          // 170 KB of SASS and instruction-fetch bound).
+          unsigned pend = 0;
 #pragma unroll
-            for (int t = 0; t < 32; ++t)
-              if (v[t] > thr && col0 + t != row && col0 + t < n) thr = list_insert(cs, ci, v[t], (int)(col0 + t));
-          } else {
+          for (int t = 0; t < 32; ++t) pend |= (v[t] > thr ? 1u : 0u) << t;
+          if ((row >= col0 && row < col0 + 32)) pend &= ~(1u << (int)(row - col0));          // the diagonal
+          if (col0 + 32 > n) pend &= (col0 < n) ? ((1u << (int)(n - col0)) - 1u) : 0u;          // past the last item
+          while (__any_sync(kFull, pend != 0)) {
+            const int t = pend ? (__ffs(pend) - 1) : 0;
+            float sel = v[0];
 #pragma unroll
-            for (int t = 0; t < 32; ++t)
-              if (v[t] > thr) thr = list_insert(cs, ci, v[t], (int)(col0 + t));
+            for (int k = 1; k < 32; ++k) sel = (t == k) ? v[k] : sel;
+            top.insert(pend ? sel : -INFINITY, (int)(col0 + t));
+            pend &= pend - 1;
+            if (live) thr = top.s[kCand - 1];
           }
         }
         tc_fence_before();
@@ -185,10 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
         if (++ts == 2) { ts = 0; tph ^= 1; }
       }
       if (live) {
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < kCand; ++k) {
-          cand_sim[row * kCand + k] = cs[k];
-          cand_idx[row * kCand + k] = ci[k];
+          cand_sim[row * kCand + k] = top.s[k];
+          cand_idx[row * kCand + k] = top.i[k];
         }
       }
     }
@@ -208,8 +230,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const float4 u = ldg4(en + r * kD + lane * 4);
-  // lane l owns candidates l and l + 32
-  int id[2] = {cand_idx[r * kCand + lane], cand_idx[r * kCand + 32 + lane]};
+  // lane l owns candidates l and l + 32 (kCand <= 64)
+  static_assert(kCand > 32 && kCand <= 64, "rerank lane mapping");
+  int id[2] = {cand_idx[r * kCand + lane], (32 + lane < kCand) ? cand_idx[r * kCand + 32 + lane] : -1};
   float ex[2] = {-INFINITY, -INFINITY};
 #pragma unroll
   for (int half = 0; half < 2; ++half) {

@@ -209,6 +209,13 @@ int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, 
  */
 int b200gat_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+/* sample_bpr (row f4): the per-epoch triple sampler, scripts/train_gat_custom.py:213-224 -- uniform user among those
+ * with positives, uniform positive, uniform non-positive item by rejection.  The user's positives are the out-edges of
+ * the user node in the CSC of b200gat_build_graph (colptr/row; row holds n_users + item).  Counter-based RNG keyed on
+ * (seed, sample index): distribution-level parity with the reference's Python `random` stream.  n_fail: device int32,
+ * samples for which no user / negative was found within the attempt budget (0 unless the graph is degenerate). */
+int b200gat_sample_bpr(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
+                       uint64_t seed, int64_t* u, int64_t* i, int64_t* j, int32_t* n_fail, void* stream);
 int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* users,
                            const int64_t* candidates, int64_t n_eval, int n_candidates, int32_t* ranks, int32_t* n_bad,
                            void* stream);

@@ -109,3 +109,75 @@ extern "C" int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
+
+// ---- f4: BPR triple sampler (scripts/train_gat_custom.py:213-224) ---------------------------------------------------
+// The reference draws, per sample, a uniform user among those with training positives, a uniform positive of that user
+// and a uniform item that is not one of the user's positives (rejection).  Python's `random` stream cannot be replayed on
+// a GPU, so parity is distributional; the draws come from Philox-4x32-10 keyed on (seed, sample, attempt).  The user's
+// positives are read from the graph's CSC (out-edges of a user node are exactly its items).
+namespace b200gat {
+__device__ __forceinline__ void philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t (&out)[4]) {
+  uint32_t c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// unbiased integer in [0, n): 64-bit multiply-shift on 32 random bits is biased by < n / 2^32 (< 2e-4 here), as is
+// Python's own randrange for non powers of two before its rejection step; good to distribution-level parity
+__device__ __forceinline__ int64_t bounded(uint32_t r, int64_t n) { return (int64_t)(((uint64_t)r * (uint64_t)n) >> 32); }
+
+__global__ void sample_bpr_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ row, int64_t n_users,
+                                  int64_t n_items, int64_t n_samples, uint64_t seed, int64_t* __restrict__ u_out,
+                                  int64_t* __restrict__ i_out, int64_t* __restrict__ j_out, int32_t* __restrict__ n_fail) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_samples) return;
+  uint32_t r[4];
+  int64_t u = 0;
+  int beg = 0, deg = 0;
+  uint32_t attempt = 0;
+  for (; attempt < 64; ++attempt) {              // users without positives are not in the reference's dict: redraw
+    philox4(seed, (uint32_t)t, ((uint32_t)(t >> 32) << 8) | attempt, r);
+    u = bounded(r[0], n_users);
+    beg = colptr[u];
+    deg = colptr[u + 1] - beg;
+    if (deg > 0) break;
+  }
+  if (deg <= 0) { atomicAdd(n_fail, 1); u_out[t] = 0; i_out[t] = 0; j_out[t] = 0; return; }
+  const int64_t i = (int64_t)row[beg + (int)bounded(r[1], deg)] - n_users;
+  int64_t j = -1;
+  uint32_t rr[4] = {r[2], r[3], 0, 0};
+  int next = 0, avail = 2;                          // two words are left over from the first draw
+  for (uint32_t a2 = 0; a2 < 256 && j < 0; ++a2) {
+    if (next == avail) { philox4(seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)t, ((uint32_t)(t >> 32) << 8) | (a2 & 0xff), rr); next = 0; avail = 4; }
+    const uint32_t word = next == 0 ? rr[0] : (next == 1 ? rr[1] : (next == 2 ? rr[2] : rr[3]));
+    const int64_t cand = bounded(word, n_items);
+    ++next;
+    bool in = false;
+    for (int q = beg; q < beg + deg; ++q) in |= ((int64_t)row[q] - n_users == cand);
+    if (!in) j = cand;
+  }
+  if (j < 0) { atomicAdd(n_fail, 1); j = 0; }
+  u_out[t] = u;
+  i_out[t] = i;
+  j_out[t] = j;
+}
+}  // namespace b200gat
+
+extern "C" int b200gat_sample_bpr(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
+                                  uint64_t seed, int64_t* u, int64_t* i, int64_t* j, int32_t* n_fail, void* stream) {
+  B200GAT_CHECK_ARG(colptr && row && n_fail && (n_samples == 0 || (u && i && j)), "null pointer");
+  B200GAT_CHECK_ARG(n_users > 0 && n_items > 0 && n_samples >= 0, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200GAT_CUDA(cudaMemsetAsync(n_fail, 0, sizeof(int32_t), st));
+  if (n_samples == 0) return kOk;
+  count_launch(), sample_bpr_kernel<<<ceil_div(n_samples, 256), 256, 0, st>>>(colptr, row, n_users, n_items, n_samples, seed, u, i, j,
+                                                                             n_fail);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}

@@ -46,6 +46,24 @@ class Adam(torch.optim.Optimizer):
         return loss
 
 
+def sample_bpr_epoch(graph, n_users: int, n_items: int, samples: int, seed: int):
+    """Device version of ``sample_bpr_epoch`` (scripts/train_gat_custom.py:213-224): ``samples`` triples (u, i, j) with u
+    uniform over users that have training positives, i a uniform positive of u, j a uniform item u has not interacted with.
+    ``graph`` is the :class:`GraphStructure` of the training ``edge_index`` (a user's positives are its out-edges).  Returns
+    int64 CUDA tensors; same distribution as the reference, not the same stream (Python's ``random`` cannot be replayed)."""
+    dev = graph.colptr.device
+    u = torch.empty(samples, dtype=torch.int64, device=dev)
+    i = torch.empty_like(u)
+    j = torch.empty_like(u)
+    n_fail = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("b200gat_sample_bpr", _lib.ptr(graph.colptr), _lib.ptr(graph.row), n_users, n_items, samples, int(seed) & (2 ** 64 - 1),
+                  _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), _lib.ptr(n_fail), _lib.stream())
+    if int(n_fail.item()):
+        raise RuntimeError("sample_bpr_epoch: could not draw a user with positives / a negative item for some samples")
+    return u, i, j
+
+
 def eval_ranks(z: torch.Tensor, n_users: int, users: torch.Tensor, candidates: torch.Tensor) -> torch.Tensor:
     """ranks[q] = (scores > scores[0]).sum() + 1 for scores = I[candidates[q]] @ U[users[q]]
     (scripts/train_gat_custom.py:200-206).  ``candidates`` [n_eval, 1+K] int64 item ids, column 0 = the positive."""

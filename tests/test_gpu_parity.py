@@ -527,3 +527,48 @@ def test_adam_matches_torch(dev):
     with pytest.raises(RuntimeError):
         cpu_p = torch.randn(3, requires_grad=True); cpu_p.grad = torch.ones(3)
         b200gat.Adam([cpu_p]).step()
+
+
+def test_bpr_sampler_distribution(dev):
+    """Row f4: the device sampler draws from the same distribution as sample_bpr_epoch (train_gat_custom.py:213-224):
+    u uniform over users with positives, i one of u's positives (uniform over the list, duplicates counted), j uniform
+    over the items u has NOT interacted with.  Python's `random` stream cannot be replayed, so the check is statistical."""
+    import b200gat
+    from b200gat import synth
+    nu, ni = 200, 300
+    rng = np.random.default_rng(0)
+    train_pos = {u: rng.integers(0, ni, size=int(rng.integers(1, 12))) for u in range(nu) if u % 10 != 3}   # some users absent
+    ei = b200gat.build_edge_index(nu, ni, train_pos)
+    g = b200gat.build_graph(ei.to(dev), nu + ni)
+    s = 400_000
+    u, i, j = b200gat.sample_bpr_epoch(g, nu, ni, s, seed=123)
+    u2, i2, j2 = b200gat.sample_bpr_epoch(g, nu, ni, s, seed=123)
+    assert torch.equal(u, u2) and torch.equal(i, i2) and torch.equal(j, j2)          # reproducible per seed
+    u3, _, _ = b200gat.sample_bpr_epoch(g, nu, ni, s, seed=124)
+    assert not torch.equal(u, u3)
+    u, i, j = u.cpu().numpy(), i.cpu().numpy(), j.cpu().numpy()
+    pos = {k: set(v.tolist()) for k, v in train_pos.items()}
+    assert set(np.unique(u)) == set(train_pos.keys())                                  # only users that have positives
+    assert all(int(ii) in pos[int(uu)] for uu, ii in zip(u[:20000], i[:20000]))
+    assert not any(int(jj) in pos[int(uu)] for uu, jj in zip(u[:20000], j[:20000]))
+    # uniform over the eligible users (5 sigma)
+    cnt = np.bincount(u, minlength=nu)[list(train_pos.keys())]
+    exp = s / len(train_pos)
+    assert np.abs(cnt - exp).max() < 5 * np.sqrt(exp)
+    # for one busy user: positives drawn proportionally to their multiplicity, negatives uniform over the complement
+    uu = max(train_pos, key=lambda k: len(train_pos[k]))
+    sel = u == uu
+    vals, mult = np.unique(train_pos[uu], return_counts=True)
+    got = np.array([(i[sel] == v).sum() for v in vals])
+    np.testing.assert_allclose(got / sel.sum(), mult / mult.sum(), atol=5 * np.sqrt(0.25 / sel.sum()))
+    neg_cnt = np.bincount(j[sel], minlength=ni)
+    comp = np.array([k not in pos[uu] for k in range(ni)])
+    assert neg_cnt[~comp].sum() == 0
+    e = sel.sum() / comp.sum()
+    assert np.abs(neg_cnt[comp] - e).max() < 6 * np.sqrt(e) + 3
+    # the reference's sampler has the same first moments
+    import random
+    random.seed(0)
+    users = list(train_pos.keys())
+    ref_u = np.array([random.choice(users) for _ in range(50000)])
+    assert abs(ref_u.mean() - u.mean()) < 1.0

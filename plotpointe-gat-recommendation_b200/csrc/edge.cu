@@ -142,7 +142,7 @@ __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float 
 }
 
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : 1) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? 4 : 2)) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ col,
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : 1) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? 4 : 2)) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const T* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
                                                                 const int4* __restrict__ sched,

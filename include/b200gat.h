@@ -224,7 +224,8 @@ int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int
  * emb [n_items, 128] fp32.  Normalisation as the reference (x/(|x|+1e-8), then sklearn's row normalisation), bf16
  * tcgen05 pass that selects 64 candidate columns per row, exact fp32 re-rank.  Outputs: nbr_idx / nbr_sim
  * [n_items, k] descending (self excluded; unused slots -1 / 0), counts[n_items] = how many pass >= min_similarity
- * (a prefix of the row).  n_unsafe: device int32, rows whose candidate margin could not prove exactness (check == 0).
+ * (a prefix of the row).  n_unsafe: device int32, rows whose bf16 candidate margin could not prove the selection exact
+ * and were therefore recomputed with exact fp32 dots against all columns (informational).
  * The COO triple of the reference (:103-111) is (row = item, col = nbr_idx[item, :counts[item]], sim). */
 int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* bytes /*host*/);
 int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim, int k, float min_similarity, int32_t* nbr_idx,

@@ -12,8 +12,10 @@
 //          de per edge (E*H floats, the only E-sized scratch) and ds_src; a scalar CSR pass then
 //          reduces de per destination into ds_dst.
 //
-// Row width is H*C floats with C a multiple of 128 (lane l owns channels [4l,4l+4) of every
-// 128-wide chunk), H in {1,2,4}.
+// Row width is H*C elements with C a multiple of 128 (lane l owns channels [4l,4l+4) of every
+// 128-wide chunk), H in {1,2,4}; the gathered matrix is fp32 or bf16 (template parameter T),
+// accumulation is always fp32.  Rows come from a descending-degree schedule; rows longer than
+// 128 edges arrive as segments whose partial states a small combine kernel merges in order.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -68,10 +70,6 @@ __device__ __forceinline__ float4 to_f4(uint2 v) {   // bf16 -> fp32 is a 16-bit
                      __uint_as_float(v.y & 0xffff0000u));
 }
 
-template <int H, int CV>
-struct Unroll {
-  static constexpr int value = (H * CV >= 8) ? 1 : (H * CV >= 4 ? 2 : (H * CV >= 2 ? 4 : 8));
-};
 
 // --------------------------------------------------------------------------------------------
 // row schedule: rows in descending-degree order, one int4 (row, beg, end, 0) each.  Persistent warps walk

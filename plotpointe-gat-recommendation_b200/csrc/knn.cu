@@ -13,8 +13,9 @@
 //                  keep, per row, the 48 best APPROXIMATE similarities seen so far in a register-resident list.
 //   3. re-rank   : exact fp32 dot products for the 48 candidates of every row (warp per row), top-k selection in
 //                  descending order, min_similarity filter.  The final similarities are plain fp32 like the reference's;
-//                  the bf16 pass only decides WHICH 48 columns get the exact treatment, and a per-row guard counts the
-//                  rows where the approximate margin would not have been safe.
+//                  the bf16 pass only decides WHICH 48 columns get the exact treatment, and a per-row guard lists the
+//                  rows where the approximate margin cannot prove the selection exact (dense near-duplicates);
+//   4. exact     : those rows are redone with exact fp32 dots against ALL columns.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
 __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ en, int64_t n, const float* __restrict__ cand_sim,
                                                      const int32_t* __restrict__ cand_idx, int k, float min_similarity,
                                                      int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
-                                                     int32_t* __restrict__ counts, int32_t* __restrict__ n_unsafe) {
+                                                     int32_t* __restrict__ counts, int32_t* __restrict__ n_unsafe,
+                                                     int32_t* __restrict__ unsafe_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
@@ -279,7 +281,100 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
     counts[r] = valid;
     // guard: a column outside the 64 candidates has approximate similarity <= approx_last, hence exact similarity
     // <= approx_last + err; the selection is provably the exact top-k iff the exact k-th beats that bound
-    if (n - 1 > kCand && kth > -INFINITY && !(kth > approx_last + kApproxErr)) atomicAdd(n_unsafe, 1);
+    if (n - 1 > kCand && kth > -INFINITY && !(kth > approx_last + kApproxErr)) unsafe_rows[atomicAdd(n_unsafe, 1)] = (int32_t)r;
+  }
+}
+
+
+// ---- 4. exact path for the rows the guard could not clear -------------------------------------------------------------
+// One block per such row (grid-stride over the list): every warp scans a stripe of ALL columns with exact fp32 dots and
+// keeps its own top-k (lane l holds entry l, replacement of the current minimum); the 8 per-warp lists are merged by
+// warp 0.  255 MB of reads per row at 498k items, so this is only meant for the few rows with dense near-duplicates.
+__global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict__ en, int64_t n, const int32_t* __restrict__ unsafe_rows,
+                                                         const int32_t* __restrict__ n_unsafe, int k, float min_similarity,
+                                                         int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
+                                                         int32_t* __restrict__ counts) {
+  __shared__ float s_sim[8][32];
+  __shared__ int s_idx[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int total = *n_unsafe;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    const int64_t r = unsafe_rows[u];
+    const float4 q = ldg4(en + r * kD + lane * 4);
+    float my = -INFINITY;       // lane l < k holds one entry of this warp's top-k
+    int my_i = -1;
+    float wmin = -INFINITY;     // smallest entry of the warp's list (valid once the list is full)
+    int filled = 0;
+    for (int64_t c0 = warp; c0 < n; c0 += 8 * 4) {
+      float d[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t c = c0 + 8 * t;
+        d[t] = (c < n && c != r) ? dot4(q, ldg4(en + c * kD + lane * 4)) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t c = c0 + 8 * t;
+        const float sc = warp_sum(d[t]);
+        if (c >= n || c == r) continue;                       // warp-uniform
+        if (filled < k) {
+          if (lane == filled) { my = sc; my_i = (int)c; }
+          ++filled;
+          if (filled == k) {                                  // list full: find its minimum
+            float m = lane < k ? my : INFINITY;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(kFull, m, o));
+            wmin = m;
+          }
+        } else if (sc > wmin) {
+          // replace (one of) the minimum entries, then recompute the minimum
+          const unsigned holders = __ballot_sync(kFull, lane < k && my == wmin);
+          if (lane == __ffs(holders) - 1) { my = sc; my_i = (int)c; }
+          float m = lane < k ? my : INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(kFull, m, o));
+          wmin = m;
+        }
+      }
+    }
+    s_sim[warp][lane] = lane < k ? my : -INFINITY;
+    s_idx[warp][lane] = lane < k ? my_i : -1;
+    __syncthreads();
+    if (warp == 0) {
+      // 8 lists x 32 slots = 256 candidates, 8 per lane; k rounds of arg-max (ties: lower column index first)
+      float cs[8];
+      int ci[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { cs[w] = s_sim[w][lane]; ci[w] = s_idx[w][lane]; }
+      int valid = 0;
+      for (int round = 0; round < k; ++round) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff, bw = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          if (cs[w] > best || (cs[w] == best && ci[w] >= 0 && ci[w] < bi)) { best = cs[w]; bi = ci[w] >= 0 ? ci[w] : 0x7fffffff; bw = w; }
+        float gb = best;
+        int gi = bi, gl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(kFull, gb, o);
+          const int oi = __shfl_xor_sync(kFull, gi, o), ol = __shfl_xor_sync(kFull, gl, o);
+          if (ob > gb || (ob == gb && oi < gi)) { gb = ob; gi = oi; gl = ol; }
+        }
+        if (lane == gl) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w)
+            if (w == bw) cs[w] = -INFINITY;                   // consumed
+        }
+        if (lane == 0) {
+          nbr_sim[r * k + round] = gb > -INFINITY ? gb : 0.f;
+          nbr_idx[r * k + round] = gb > -INFINITY ? gi : -1;
+        }
+        valid += (gb > -INFINITY && gb >= min_similarity) ? 1 : 0;
+      }
+      if (lane == 0) counts[r] = valid;
+    }
+    __syncthreads();
   }
 }
 
@@ -295,13 +390,14 @@ extern "C" int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* byt
     return kErrUnsupported;
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
-  *bytes = (size_t)n_pad * knn::kD * 4 /*en*/ + (size_t)n_pad * knn::kD * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ + 1024;
+  *bytes = (size_t)n_pad * knn::kD * 4 /*en*/ + (size_t)n_pad * knn::kD * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ +
+           (size_t)n_pad * 4 /*unsafe row list*/ + 1024;
   return kOk;
 }
 
 // nbr_idx / nbr_sim [n, k]: the k most similar other items of every item, descending (unused slots: -1 / 0);
 // counts[n]: how many of them pass `>= min_similarity` (they are a prefix).  n_unsafe: device int32, number of rows
-// whose bf16 candidate margin was too thin to prove exactness (0 in every test so far; callers should check it).
+// whose bf16 candidate margin was too thin to prove exactness; those rows were recomputed by the exact path.
 extern "C" int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim, int k, float min_similarity,
                                       int32_t* nbr_idx, float* nbr_sim, int32_t* counts, int32_t* n_unsafe, void* workspace,
                                       size_t workspace_bytes, void* stream) {
@@ -326,13 +422,17 @@ extern "C" int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim
   float* en = (float*)p;                                p += (size_t)n_pad * knn::kD * 4;
   uint8_t* image = (uint8_t*)p;                         p += (size_t)n_pad * knn::kD * 2;
   float* cand_sim = (float*)p;                          p += (size_t)n_pad * knn::kCand * 4;
-  int32_t* cand_idx = (int32_t*)p;
+  int32_t* cand_idx = (int32_t*)p;                      p += (size_t)n_pad * knn::kCand * 4;
+  int32_t* unsafe_rows = (int32_t*)p;
   count_launch(), knn::prepare_kernel<<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
   const int n_super = (n_blocks + 1) / 2;
   count_launch(), knn::candidates_kernel<<<n_super < kNumSMs ? n_super : kNumSMs, knn::kThreads, knn::kSmem, st>>>(image, n_items, n_blocks,
                                                                                                                   cand_sim, cand_idx);
   count_launch(), knn::rerank_kernel<<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
-                                                                                  nbr_idx, nbr_sim, counts, n_unsafe);
+                                                                                  nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows);
+  // rows whose bf16 margin was too thin: exact scan of all columns (no-op when the list is empty)
+  count_launch(), knn::exact_rows_kernel<<<kNumSMs * 2, 256, 0, st>>>(en, n_items, unsafe_rows, n_unsafe, k, min_similarity, nbr_idx,
+                                                                     nbr_sim, counts);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

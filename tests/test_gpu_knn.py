@@ -62,3 +62,30 @@ def test_knn_rejects_unsupported(monkeypatch):
         b200gat.build_ii_knn(torch.randn(10, 128))                 # CPU tensor
     with pytest.raises(RuntimeError, match="128"):
         b200gat.build_ii_knn(torch.randn(10, 384).cuda())          # the text embeddings (384-d) are not supported yet
+
+
+def test_knn_dense_duplicates_take_the_exact_path():
+    """Rows whose 48 bf16 candidates cannot prove the top-k (clusters of >48 near-identical items) are redone exactly."""
+    import b200gat
+    rng = np.random.default_rng(5)
+    centers = rng.standard_normal((5, 128))
+    dup = np.repeat(centers, 120, axis=0) + 1e-4 * rng.standard_normal((600, 128))        # 5 clumps of 120 near-duplicates
+    emb = np.concatenate([dup, rng.standard_normal((424, 128))]).astype(np.float32)
+    n, k = emb.shape[0], 20
+    idx, sim, counts = b200gat.knn_neighbors(torch.from_numpy(emb).cuda(), k, 0.3)
+    assert int(b200gat.knn_neighbors.last_exact_rows.item()) >= 600
+    idx, sim, counts = idx.cpu().numpy(), sim.cpu().numpy(), counts.cpu().numpy()
+    en = emb.astype(np.float64)
+    en /= np.linalg.norm(en, axis=1, keepdims=True)
+    full = en @ en.T
+    np.fill_diagonal(full, -np.inf)
+    kth = -np.sort(-full, axis=1)[:, k - 1]
+    for r in range(n):
+        c = idx[r]
+        assert len(set(c.tolist())) == k and r not in c
+        np.testing.assert_allclose(sim[r], full[r, c], rtol=0, atol=3e-6)
+        assert np.all(np.diff(sim[r]) <= 1e-6)
+        assert np.all(full[r, c] >= kth[r] - 5e-6)                # every neighbour is a true top-k member up to rounding
+    assert np.all(counts[:600] == k)
+    rows, cols, sims = O.build_ii_knn(emb, k=k, min_similarity=0.3)
+    np.testing.assert_array_equal(np.bincount(rows, minlength=n), counts)

@@ -221,8 +221,9 @@ int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int
                            void* stream);
 
 /* ---- next row f1: Item-Item cosine kNN (graphs/build_ii_knn.py:56-99) ------------------------------------------
- * emb [n_items, 128] fp32.  Normalisation as the reference (x/(|x|+1e-8), then sklearn's row normalisation), bf16
- * tcgen05 pass that selects 64 candidate columns per row, exact fp32 re-rank.  Outputs: nbr_idx / nbr_sim
+ * emb [n_items, dim] fp32, dim = 128 (fused features) or 384 (text embeddings).  Normalisation as the reference
+ * (x/(|x|+1e-8), then sklearn's row normalisation), bf16 tcgen05 pass that selects 48 candidate columns per row, exact
+ * fp32 re-rank.  Outputs: nbr_idx / nbr_sim
  * [n_items, k] descending (self excluded; unused slots -1 / 0), counts[n_items] = how many pass >= min_similarity
  * (a prefix of the row).  n_unsafe: device int32, rows whose bf16 candidate margin could not prove the selection exact
  * and were therefore recomputed with exact fp32 dots against all columns (informational).

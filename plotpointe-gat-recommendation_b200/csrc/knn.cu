@@ -2,15 +2,16 @@
 // sklearn's cosine_similarity in 1000-row batches on the CPU (O(n^2 d), 78-100 s for 63k items in the reference's report)
 // and keeps the k best neighbours of every item.
 //
-// Three passes:
+// Four passes:
 //   1. prepare   : the reference's two normalisations (x / (|x| + 1e-8), then sklearn's row normalisation) in fp32;
 //                  writes the normalised fp32 rows and a bf16 image of them, already laid out the way the UMMA wants
 //                  its shared-memory operands (128-row blocks, 128-byte swizzle), so that a whole operand tile is ONE
 //                  contiguous 32 KB bulk copy (TMA unit).
-//   2. candidates: bf16 tcgen05 GEMM of the image against itself.  A CTA keeps a 256-row block of A resident and streams
-//                  every 128-row block of B through a 3-deep ring of bulk copies; accumulators live in TMEM (2 row
-//                  blocks x 2 stages x 128 columns = all 512 columns); 8 epilogue warps read them back (tcgen05.ld) and
-//                  keep, per row, the 48 best APPROXIMATE similarities seen so far in a register-resident list.
+//   2. candidates: bf16 tcgen05 GEMM of the image against itself.  A CTA keeps a 256-row block of A resident (128 rows
+//                  for 384-d) and streams every 128-row block of B, one 128-wide K chunk at a time, through a 3-deep
+//                  ring of bulk copies; accumulators live in TMEM (2 row blocks x 2 stages x 128 columns = all 512
+//                  columns); 8 epilogue warps read them back (tcgen05.ld) and keep, per row, the 48 best APPROXIMATE
+//                  similarities seen so far in a register-resident list.
 //   3. re-rank   : exact fp32 dot products for the 48 candidates of every row (warp per row), top-k selection in
 //                  descending order, min_similarity filter.  The final similarities are plain fp32 like the reference's;
 //                  the bf16 pass only decides WHICH 48 columns get the exact treatment, and a per-row guard lists the
@@ -27,42 +28,67 @@ namespace knn {
 
 using namespace tc;
 
-constexpr int kD = 128;                    // embedding width handled by the tensor-core path
-constexpr int kBlk = 128;                  // rows per image block
-constexpr int kBlkBytes = kBlk * kD * 2;   // 32 KB: [kb 2][128 rows][128 B swizzled]
+// The embedding width is KC chunks of 128 (KC = 1: the fused 128-d features, KC = 3: the 384-d text embeddings).
+constexpr int kChunkD = 128;
+constexpr int kBlk = 128;                       // rows per image block
+constexpr int kChunkBytes = kBlk * kChunkD * 2; // 32 KB: [kb 2][128 rows][128 B swizzled]; a block is KC consecutive chunks
 constexpr int kCand = 48;                  // approximate candidates kept per row (register-resident list)
 constexpr int kBStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA warp + producer warp
-constexpr int kSmem = 1024 + 2 * kBlkBytes + kBStages * kBlkBytes + 256;
-constexpr float kApproxErr = 2e-3f;        // bound on |bf16 similarity - exact| used by the safety guard (unit rows, d = 128)
+template <int KC> struct Cfg {
+  static constexpr int kNA = KC == 1 ? 2 : 1;                       // A row blocks resident per CTA
+  static constexpr int kD = KC * kChunkD;
+  static constexpr int kBlkBytes = KC * kChunkBytes;
+  static constexpr int kSmem = 1024 + kNA * kBlkBytes + kBStages * kChunkBytes + 256;
+};
+// Bound on |bf16 similarity - exact| used by the safety guard: both operands are rounded to nearest (u = 2^-9), so the
+// error is at most (2u + u^2) * sum|a_i b_i| <= 3.91e-3 for unit rows of any width; fp32 accumulation adds ~1e-6.
+constexpr float kApproxErr = 4e-3f;
 
 // ---- 1. prepare -----------------------------------------------------------------------------------------------------
+template <int KC>
 __global__ void __launch_bounds__(128) prepare_kernel(const float* __restrict__ emb, int64_t n, int64_t n_pad,
                                                       float* __restrict__ en, uint8_t* __restrict__ image) {
+  constexpr int D = KC * kChunkD;
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n_pad) return;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v[KC];
+#pragma unroll
+  for (int kc = 0; kc < KC; ++kc) v[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (r < n) {
-    v = ldg4(emb + r * kD + lane * 4);
-    const float nrm = sqrtf(warp_sum(dot4(v, v)));                 // np.linalg.norm(embeddings, axis=1)
-    const float s1 = 1.f / (nrm + 1e-8f);                          // embeddings / (norms + 1e-8)      (:56-57)
-    v.x *= s1; v.y *= s1; v.z *= s1; v.w *= s1;
-    float n2 = sqrtf(warp_sum(dot4(v, v)));                        // sklearn cosine_similarity normalises again (:76)
+    float ss = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      v[kc] = ldg4(emb + r * D + kc * kChunkD + lane * 4);
+      ss += dot4(v[kc], v[kc]);
+    }
+    const float s1 = 1.f / (sqrtf(warp_sum(ss)) + 1e-8f);          // embeddings / (norms + 1e-8)      (:56-57)
+    ss = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      v[kc].x *= s1; v[kc].y *= s1; v[kc].z *= s1; v[kc].w *= s1;
+      ss += dot4(v[kc], v[kc]);
+    }
+    float n2 = sqrtf(warp_sum(ss));                                // sklearn cosine_similarity normalises again (:76)
     if (n2 == 0.f) n2 = 1.f;
     const float s2 = 1.f / n2;
-    v.x *= s2; v.y *= s2; v.z *= s2; v.w *= s2;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) { v[kc].x *= s2; v[kc].y *= s2; v[kc].z *= s2; v[kc].w *= s2; }
   }
-  *reinterpret_cast<float4*>(en + r * kD + lane * 4) = v;
-  // bf16 image: block = r / 128, row in block = r % 128, k-block = (lane*4) / 64, 16-byte chunk = ((lane*4) % 64) / 8
-  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  // bf16 image: block = r / 128, then chunk kc, k-block = (lane*4) / 64, 16-byte piece = ((lane*4) % 64) / 8
   const int rb = (int)(r % kBlk), kb = lane >> 4, e = (lane & 15) * 4;   // e: element offset inside the 64-wide k-block
-  uint8_t* dst = image + (r / kBlk) * kBlkBytes + kb * (kBlk * 128) + sw128(rb, e >> 3) + (e & 7) * 2;
-  *reinterpret_cast<uint2*>(dst) = pk;
+#pragma unroll
+  for (int kc = 0; kc < KC; ++kc) {
+    *reinterpret_cast<float4*>(en + r * D + kc * kChunkD + lane * 4) = v[kc];
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[kc].x, v[kc].y), hi = __floats2bfloat162_rn(v[kc].z, v[kc].w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    uint8_t* dst = image + ((r / kBlk) * KC + kc) * (size_t)kChunkBytes + kb * (kBlk * 128) + sw128(rb, e >> 3) + (e & 7) * 2;
+    *reinterpret_cast<uint2*>(dst) = pk;
+  }
 }
 
 // ---- 2. candidates --------------------------------------------------------------------------------------------------
@@ -90,23 +116,26 @@ struct TopList {
   }
 };
 
+template <int KC>
 __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks,
                                                                  float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx) {
+  constexpr int NA = Cfg<KC>::kNA;
+  constexpr int kBlkBytes = Cfg<KC>::kBlkBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + 2 * kBlkBytes, sBar = sB + kBStages * kBlkBytes;
+  const uint32_t sA = base, sB = base + NA * kBlkBytes, sBar = sB + kBStages * kChunkBytes;
   const uint32_t bar_afull = sBar, bar_aempty = sBar + 8, bar_bfull = sBar + 16, bar_bempty = sBar + 48, bar_tfull = sBar + 80,
                  bar_tempty = sBar + 96;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_super = (n_blocks + 1) / 2;      // 256-row super blocks
+  const int n_super = (n_blocks + NA - 1) / NA;      // NA*128-row super blocks
 
   if (threadIdx.x == 0) {
     mbar_init(bar_afull, 1);
     mbar_init(bar_aempty, 1);
     for (int i = 0; i < kBStages; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, NA * 128); }
     fence_barrier_init();
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
@@ -121,15 +150,22 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
       uint32_t bs = 0, bph = 0, aph = 0;
       for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
         mbar_wait(bar_aempty, aph ^ 1);
-        mbar_expect_tx(bar_afull, 2 * kBlkBytes);
-        const int a0 = 2 * sb, a1 = min(2 * sb + 1, n_blocks - 1);     // a1 clamps on an odd tail: its rows are ignored
-        bulk_g2s(sA, image + (size_t)a0 * kBlkBytes, kBlkBytes, bar_afull);
-        bulk_g2s(sA + kBlkBytes, image + (size_t)a1 * kBlkBytes, kBlkBytes, bar_afull);
+        mbar_expect_tx(bar_afull, NA * kBlkBytes);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const int ab = min(NA * sb + a, n_blocks - 1);                 // clamps on a ragged tail: those rows are ignored
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc)
+            bulk_g2s(sA + a * kBlkBytes + kc * kChunkBytes, image + ((size_t)ab * KC + kc) * kChunkBytes, kChunkBytes, bar_afull);
+        }
         for (int j = 0; j < n_blocks; ++j) {
-          mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
-          mbar_expect_tx(bar_bfull + 8 * bs, kBlkBytes);
-          bulk_g2s(sB + bs * kBlkBytes, image + (size_t)j * kBlkBytes, kBlkBytes, bar_bfull + 8 * bs);
-          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+#pragma unroll 1
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+            mbar_expect_tx(bar_bfull + 8 * bs, kChunkBytes);
+            bulk_g2s(sB + bs * kChunkBytes, image + ((size_t)j * KC + kc) * kChunkBytes, kChunkBytes, bar_bfull + 8 * bs);
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
+          }
         }
         aph ^= 1;
       }
@@ -143,22 +179,25 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
         mbar_wait(bar_afull, aph);
         for (int j = 0; j < n_blocks; ++j) {
           mbar_wait(bar_tempty + 8 * ts, tph ^ 1);
-          mbar_wait(bar_bfull + 8 * bs, bph);
-          tc_fence_after();
-          const uint32_t b0 = sB + bs * kBlkBytes;
+#pragma unroll 1
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar_bfull + 8 * bs, bph);
+            tc_fence_after();
+            const uint32_t b0 = sB + bs * kChunkBytes;
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint32_t d = tmem_base + (ts * 2 + a) * 128, a0 = sA + a * kBlkBytes;
+            for (int a = 0; a < NA; ++a) {
+              const uint32_t d = tmem_base + (ts * 2 + a) * 128, a0 = sA + a * kBlkBytes + kc * kChunkBytes;
 #pragma unroll
-            for (int kb = 0; kb < 2; ++kb)
+              for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d, make_desc(a0 + kb * (kBlk * 128) + k * 32, 16, 1024), make_desc(b0 + kb * (kBlk * 128) + k * 32, 16, 1024),
-                          idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d, make_desc(a0 + kb * (kBlk * 128) + k * 32, 16, 1024),
+                            make_desc(b0 + kb * (kBlk * 128) + k * 32, 16, 1024), idesc, (kc | kb | k) != 0);
+            }
+            umma_commit(bar_bempty + 8 * bs);
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
-          umma_commit(bar_bempty + 8 * bs);
           umma_commit(bar_tfull + 8 * ts);
-          if (++bs == kBStages) { bs = 0; bph ^= 1; }
           if (++ts == 2) { ts = 0; tph ^= 1; }
         }
         umma_commit(bar_aempty);
@@ -166,14 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
       }
     }
     __syncwarp();
-  } else {
-    // =============================== epilogue: running top-64 per row ==========================================
+  } else if ((warp >> 2) < NA) {
+    // =============================== epilogue: running top-48 per row ==========================================
     const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
     TopList top;
     uint32_t ts = 0, tph = 0;
     for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
-      const int64_t row = ((int64_t)(2 * sb + a)) * kBlk + q * 32 + lane;
-      const bool live = (2 * sb + a) < n_blocks && row < n;
+      const int64_t row = ((int64_t)(NA * sb + a)) * kBlk + q * 32 + lane;
+      const bool live = (NA * sb + a) < n_blocks && row < n;
       top.reset();
       float thr = live ? -INFINITY : INFINITY;      // padding rows never insert
       for (int j = 0; j < n_blocks; ++j) {
@@ -223,15 +262,25 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
 }
 
 // ---- 3. exact re-rank ------------------------------------------------------------------------------------------------
+template <int KC>
 __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ en, int64_t n, const float* __restrict__ cand_sim,
                                                      const int32_t* __restrict__ cand_idx, int k, float min_similarity,
                                                      int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
                                                      int32_t* __restrict__ counts, int32_t* __restrict__ n_unsafe,
                                                      int32_t* __restrict__ unsafe_rows) {
+  constexpr int D = KC * kChunkD;
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
-  const float4 u = ldg4(en + r * kD + lane * 4);
+  float4 u[KC];
+#pragma unroll
+  for (int kc = 0; kc < KC; ++kc) u[kc] = ldg4(en + r * D + kc * kChunkD + lane * 4);
+  auto dot_row = [&](int64_t c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) acc += dot4(u[kc], ldg4(en + c * D + kc * kChunkD + lane * 4));
+    return acc;
+  };
   // lane l owns candidates l and l + 32 (kCand <= 64)
   static_assert(kCand > 32 && kCand <= 64, "rerank lane mapping");
   int id[2] = {cand_idx[r * kCand + lane], (32 + lane < kCand) ? cand_idx[r * kCand + 32 + lane] : -1};
@@ -244,7 +293,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         cid[t] = __shfl_sync(kFull, id[half], c0 + t);
-        d[t] = cid[t] >= 0 ? dot4(u, ldg4(en + (size_t)cid[t] * kD + lane * 4)) : 0.f;
+        d[t] = cid[t] >= 0 ? dot_row(cid[t]) : 0.f;
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -279,7 +328,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
   }
   if (lane == 0) {
     counts[r] = valid;
-    // guard: a column outside the 64 candidates has approximate similarity <= approx_last, hence exact similarity
+    // guard: a column outside the 48 candidates has approximate similarity <= approx_last, hence exact similarity
     // <= approx_last + err; the selection is provably the exact top-k iff the exact k-th beats that bound
     if (n - 1 > kCand && kth > -INFINITY && !(kth > approx_last + kApproxErr)) unsafe_rows[atomicAdd(n_unsafe, 1)] = (int32_t)r;
   }
@@ -290,6 +339,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
 // One block per such row (grid-stride over the list): every warp scans a stripe of ALL columns with exact fp32 dots and
 // keeps its own top-k (lane l holds entry l, replacement of the current minimum); the 8 per-warp lists are merged by
 // warp 0.  255 MB of reads per row at 498k items, so this is only meant for the few rows with dense near-duplicates.
+template <int KC>
 __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict__ en, int64_t n, const int32_t* __restrict__ unsafe_rows,
                                                          const int32_t* __restrict__ n_unsafe, int k, float min_similarity,
                                                          int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
@@ -299,8 +349,11 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int total = *n_unsafe;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    constexpr int D = KC * kChunkD;
     const int64_t r = unsafe_rows[u];
-    const float4 q = ldg4(en + r * kD + lane * 4);
+    float4 q[KC];
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) q[kc] = ldg4(en + r * D + kc * kChunkD + lane * 4);
     float my = -INFINITY;       // lane l < k holds one entry of this warp's top-k
     int my_i = -1;
     float wmin = -INFINITY;     // smallest entry of the warp's list (valid once the list is full)
@@ -310,7 +363,12 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int64_t c = c0 + 8 * t;
-        d[t] = (c < n && c != r) ? dot4(q, ldg4(en + c * kD + lane * 4)) : 0.f;
+        float acc = 0.f;
+        if (c < n && c != r) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) acc += dot4(q[kc], ldg4(en + c * D + kc * kChunkD + lane * 4));
+        }
+        d[t] = acc;
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -383,14 +441,44 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict
 
 using namespace b200gat;
 
+template <int KC>
+static int knn_run(const float* emb, int64_t n_items, int k, float min_similarity, int32_t* nbr_idx, float* nbr_sim, int32_t* counts,
+                   int32_t* n_unsafe, void* workspace, cudaStream_t st) {
+  using C = knn::Cfg<KC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_done = true;
+  }
+  const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
+  const int n_blocks = (int)(n_pad / knn::kBlk);
+  char* p = (char*)workspace;
+  float* en = (float*)p;                                p += (size_t)n_pad * C::kD * 4;
+  uint8_t* image = (uint8_t*)p;                         p += (size_t)n_pad * C::kD * 2;
+  float* cand_sim = (float*)p;                          p += (size_t)n_pad * knn::kCand * 4;
+  int32_t* cand_idx = (int32_t*)p;                      p += (size_t)n_pad * knn::kCand * 4;
+  int32_t* unsafe_rows = (int32_t*)p;
+  count_launch(), knn::prepare_kernel<KC><<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
+  const int n_super = (n_blocks + C::kNA - 1) / C::kNA;
+  count_launch(), knn::candidates_kernel<KC><<<n_super < kNumSMs ? n_super : kNumSMs, knn::kThreads, C::kSmem, st>>>(
+      image, n_items, n_blocks, cand_sim, cand_idx);
+  count_launch(), knn::rerank_kernel<KC><<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
+                                                                                      nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows);
+  // rows whose bf16 margin was too thin: exact scan of all columns (no-op when the list is empty)
+  count_launch(), knn::exact_rows_kernel<KC><<<kNumSMs * 2, 256, 0, st>>>(en, n_items, unsafe_rows, n_unsafe, k, min_similarity, nbr_idx,
+                                                                         nbr_sim, counts);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
 extern "C" int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* bytes) {
   B200GAT_CHECK_ARG(bytes && n_items >= 0, "bad args");
-  if (dim != knn::kD) {
-    set_error("cosine kNN: embedding width %d is not supported on the tensor-core path (128 only)", dim);
+  if (dim != 128 && dim != 384) {
+    set_error("cosine kNN: embedding width %d is not supported on the tensor-core path (128 or 384)", dim);
     return kErrUnsupported;
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
-  *bytes = (size_t)n_pad * knn::kD * 4 /*en*/ + (size_t)n_pad * knn::kD * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ +
+  *bytes = (size_t)n_pad * dim * 4 /*en*/ + (size_t)n_pad * dim * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ +
            (size_t)n_pad * 4 /*unsafe row list*/ + 1024;
   return kOk;
 }
@@ -411,28 +499,6 @@ extern "C" int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim
   cudaStream_t st = (cudaStream_t)stream;
   B200GAT_CUDA(cudaMemsetAsync(n_unsafe, 0, sizeof(int32_t), st));
   if (n_items == 0) return kOk;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, knn::kSmem));
-    attr_done = true;
-  }
-  const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
-  const int n_blocks = (int)(n_pad / knn::kBlk);
-  char* p = (char*)workspace;
-  float* en = (float*)p;                                p += (size_t)n_pad * knn::kD * 4;
-  uint8_t* image = (uint8_t*)p;                         p += (size_t)n_pad * knn::kD * 2;
-  float* cand_sim = (float*)p;                          p += (size_t)n_pad * knn::kCand * 4;
-  int32_t* cand_idx = (int32_t*)p;                      p += (size_t)n_pad * knn::kCand * 4;
-  int32_t* unsafe_rows = (int32_t*)p;
-  count_launch(), knn::prepare_kernel<<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
-  const int n_super = (n_blocks + 1) / 2;
-  count_launch(), knn::candidates_kernel<<<n_super < kNumSMs ? n_super : kNumSMs, knn::kThreads, knn::kSmem, st>>>(image, n_items, n_blocks,
-                                                                                                                  cand_sim, cand_idx);
-  count_launch(), knn::rerank_kernel<<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
-                                                                                  nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows);
-  // rows whose bf16 margin was too thin: exact scan of all columns (no-op when the list is empty)
-  count_launch(), knn::exact_rows_kernel<<<kNumSMs * 2, 256, 0, st>>>(en, n_items, unsafe_rows, n_unsafe, k, min_similarity, nbr_idx,
-                                                                     nbr_sim, counts);
-  B200GAT_LAUNCH_CHECK();
-  return kOk;
+  if (dim == 128) return knn_run<1>(emb, n_items, k, min_similarity, nbr_idx, nbr_sim, counts, n_unsafe, workspace, st);
+  return knn_run<3>(emb, n_items, k, min_similarity, nbr_idx, nbr_sim, counts, n_unsafe, workspace, st);
 }

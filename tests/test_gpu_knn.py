@@ -8,21 +8,25 @@ from oracle import gat_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _data(n, seed, clustered):
+def _data(n, seed, clustered, d=128):
     rng = np.random.default_rng(seed)
     if clustered:
-        centers = rng.standard_normal((max(n // 40, 2), 128))
-        x = centers[rng.integers(0, len(centers), n)] + 0.6 * rng.standard_normal((n, 128))
+        centers = rng.standard_normal((max(n // 40, 2), d))
+        x = centers[rng.integers(0, len(centers), n)] + 0.6 * rng.standard_normal((n, d))
     else:
-        x = rng.standard_normal((n, 128))
+        x = rng.standard_normal((n, d))
     return (x * rng.uniform(0.5, 3.0, size=(n, 1))).astype(np.float32)     # un-normalised rows, like raw embeddings
 
 
-@pytest.mark.parametrize("n,clustered,k,min_sim", [(50, False, 20, -1.0), (129, True, 20, 0.3), (3000, True, 20, 0.3),
-                                                   (2049, False, 5, -1.0), (5000, True, 20, 0.5)])
-def test_knn_matches_oracle(n, clustered, k, min_sim):
+@pytest.mark.parametrize("n,clustered,k,min_sim,d", [(50, False, 20, -1.0, 128), (129, True, 20, 0.3, 128),
+                                                     (3000, True, 20, 0.3, 128), (2049, False, 5, -1.0, 128),
+                                                     (5000, True, 20, 0.5, 128),
+                                                     # the 384-d text embeddings (embeddings/embed_text.py -> build_ii_knn.py)
+                                                     (130, False, 20, -1.0, 384), (3000, True, 20, 0.3, 384),
+                                                     (4100, True, 10, 0.5, 384)])
+def test_knn_matches_oracle(n, clustered, k, min_sim, d):
     import b200gat
-    emb = _data(n, n, clustered)
+    emb = _data(n, n, clustered, d)
     rows, cols, sims = O.build_ii_knn(emb, k=min(k, n - 1), min_similarity=min_sim, batch_size=1000)
     r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=min(k, n - 1), min_similarity=min_sim)
     r, c, s = r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
@@ -60,17 +64,18 @@ def test_knn_rejects_unsupported(monkeypatch):
     import b200gat
     with pytest.raises(RuntimeError):
         b200gat.build_ii_knn(torch.randn(10, 128))                 # CPU tensor
-    with pytest.raises(RuntimeError, match="128"):
-        b200gat.build_ii_knn(torch.randn(10, 384).cuda())          # the text embeddings (384-d) are not supported yet
+    with pytest.raises(RuntimeError, match="128 or 384"):
+        b200gat.build_ii_knn(torch.randn(10, 512).cuda())          # widths other than fused (128) / text (384)
 
 
-def test_knn_dense_duplicates_take_the_exact_path():
+@pytest.mark.parametrize("d", [128, 384])
+def test_knn_dense_duplicates_take_the_exact_path(d):
     """Rows whose 48 bf16 candidates cannot prove the top-k (clusters of >48 near-identical items) are redone exactly."""
     import b200gat
     rng = np.random.default_rng(5)
-    centers = rng.standard_normal((5, 128))
-    dup = np.repeat(centers, 120, axis=0) + 1e-4 * rng.standard_normal((600, 128))        # 5 clumps of 120 near-duplicates
-    emb = np.concatenate([dup, rng.standard_normal((424, 128))]).astype(np.float32)
+    centers = rng.standard_normal((5, d))
+    dup = np.repeat(centers, 120, axis=0) + 1e-4 * rng.standard_normal((600, d))          # 5 clumps of 120 near-duplicates
+    emb = np.concatenate([dup, rng.standard_normal((424, d))]).astype(np.float32)
     n, k = emb.shape[0], 20
     idx, sim, counts = b200gat.knn_neighbors(torch.from_numpy(emb).cuda(), k, 0.3)
     assert int(b200gat.knn_neighbors.last_exact_rows.item()) >= 600

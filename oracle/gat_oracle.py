@@ -22,8 +22,10 @@ Pinning status
 * ``eval_ranks`` / ``ranking_metrics`` / ``sample_eval_candidates`` (next row f2): PINNED.  ``make_golden.py`` runs
   the reference's own ``eval_sampled`` (scripts/train_gat_custom.py:184-210) under a fixed numpy seed and stores its
   metrics; the test replays the same numpy stream through ``sample_eval_candidates`` and must reproduce them.
-* ``build_ii_knn`` (next row f1): restated from graphs/build_ii_knn.py:56-99, which only exists inside a ``main()`` that
-  talks to GCS, so it cannot be imported: PARITY UNPINNED (sanity-checked against a brute-force top-k only).
+* ``build_ii_knn`` (next row f1): PINNED.  graphs/build_ii_knn.py:56-99 only exists inside a ``main()`` that talks to
+  GCS, so ``make_golden.py knn`` runs that file AS A SCRIPT (runpy) with a stand-in storage client that hands over a
+  local .npy, and stores the script's own output (``tests/golden/knn_128.npz``, ``knn_384.npz``); the restatement must
+  reproduce the edge list (rows, neighbours, order) exactly and the similarities to fp32 rounding.
 
 All functions are dtype-generic (float32 or float64) and differentiable through torch autograd,
 which is exactly how the reference obtains its gradients (``loss.backward()``,

@@ -8,6 +8,7 @@ reference is copied: its classes are imported, executed on seeded inputs, and on
 tensors are stored.
 
     python oracle/make_golden.py            # rewrites tests/golden/*.npz
+    python oracle/make_golden.py knn        # only the kNN fixtures (runs graphs/build_ii_knn.py as a script)
 """
 from __future__ import annotations
 
@@ -146,9 +147,77 @@ def eval_case(ref, seed):
     return out
 
 
+def knn_case(seed, n, dim, k, min_similarity, batch_size, n_centers):
+    """Run the reference's graphs/build_ii_knn.py AS A SCRIPT (its code lives inside main()): the GCS client is replaced
+    by a stand-in whose download hands over a local .npy and whose upload is a no-op; the script's own ``tmp/<name>.npz``
+    is then read back.  Clustered, un-normalised rows so that the min_similarity filter both keeps and drops edges."""
+    import runpy
+    import shutil
+    import tempfile
+    from scipy.sparse import load_npz
+
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((n_centers, dim))
+    emb = centers[rng.integers(0, len(centers), n)] + 0.8 * rng.standard_normal((n, dim))
+    emb = (emb * rng.uniform(0.5, 3.0, size=(n, 1))).astype(np.float32)
+    work = tempfile.mkdtemp(prefix="b200gat_knn_")
+    src = os.path.join(work, "emb.npy")
+    np.save(src, emb)
+
+    class _Blob:
+        def download_to_filename(self, dst):
+            shutil.copyfile(src, dst)
+
+        def upload_from_filename(self, path):
+            pass
+
+    class _Bucket:
+        def blob(self, path):
+            return _Blob()
+
+    class _Client:
+        def __init__(self, project=None):
+            pass
+
+        def bucket(self, name):
+            return _Bucket()
+
+    for name in ("google", "google.cloud", "google.cloud.storage"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["google.cloud.storage"].Client = _Client
+    sys.modules["google"].cloud = sys.modules["google.cloud"]
+    sys.modules["google.cloud"].storage = sys.modules["google.cloud.storage"]
+    argv, cwd = sys.argv, os.getcwd()
+    try:
+        os.chdir(work)
+        sys.argv = ["build_ii_knn.py", "--project-id", "p", "--embeddings-path", "gs://b/emb.npy", "--output-prefix", "gs://b/out",
+                    "--output-name", "ii", "--k", str(k), "--min-similarity", str(min_similarity), "--batch-size", str(batch_size)]
+        runpy.run_path(os.path.join(REF, "graphs", "build_ii_knn.py"), run_name="__main__")
+        m = load_npz(os.path.join(work, "tmp", "ii.npz"))
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+        sys.modules["google.cloud.storage"].Client = object
+    out = {"embeddings": emb, "k": np.int64(k), "min_similarity": np.float64(min_similarity), "batch_size": np.int64(batch_size),
+           "rows": m.row.astype(np.int32), "cols": m.col.astype(np.int32), "sims": m.data.astype(np.float32)}
+    shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
+def main_knn():
+    os.makedirs(OUT, exist_ok=True)
+    # 128-d (fused features) with several similarity batches and a ragged last one; 384-d (text embeddings)
+    np.savez_compressed(os.path.join(OUT, "knn_128.npz"), **knn_case(11, 333, 128, 20, 0.3, 100, 14))
+    np.savez_compressed(os.path.join(OUT, "knn_384.npz"), **knn_case(12, 150, 384, 10, 0.25, 1000, 12))
+
+
 def main():
+    if sys.argv[1:] == ["knn"]:            # only the kNN fixtures (leaves the others untouched)
+        main_knn()
+        return
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
+    main_knn()
     np.savez_compressed(os.path.join(OUT, "custom_layer_plain.npz"), **layer_case(ref, 1, 160, 1500, 128, 1.0))
     np.savez_compressed(os.path.join(OUT, "custom_layer_clamped.npz"), **layer_case(ref, 2, 120, 1200, 128, 12.0, hub=7))
     np.savez_compressed(os.path.join(OUT, "custom_model.npz"),

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace b200gat {
 
 // ---- error plumbing -------------------------------------------------------------------------
@@ -13,6 +15,19 @@ enum : int { kOk = 0, kErrArg = -1, kErrCuda = -2, kErrUnsupported = -3, kErrWor
 
 void set_error(const char* fmt, ...);
 void count_launch();  // bumps the process-wide kernel launch counter (b200gat_launch_count)
+
+// cudaFuncSetAttribute applies to the CURRENT device only, so "done once" has to be remembered per device.
+// Usage: static DeviceOnce once; if (once.pending()) { ...set attributes...; once.done(); }   (setting twice is harmless)
+struct DeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  static uint64_t bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool pending() const { return !(mask.load(std::memory_order_acquire) & bit()); }
+  void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
 
 #define B200GAT_CHECK_ARG(cond, ...)                    \
   do {                                                  \
@@ -43,6 +58,49 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+// Sums U (power of two <= 32) per-lane values across the warp at once.  A plain butterfly per value costs 5 shuffles each;
+// here every level first halves the number of live values (a lane keeps one half and ships the other half to its
+// partner), so the cost is (U - 1) + (5 - log2 U) shuffles in total.  On return, the total of value u is held by the
+// lanes with (lane >> (5 - log2 U)) == u; v[] is clobbered.
+template <int N, int OFF>
+struct MultiReduce {
+  template <int U>
+  static __device__ __forceinline__ float run(float (&v)[U], int lane) {
+    const bool hi = (lane & OFF) != 0;
+#pragma unroll
+    for (int t = 0; t < N / 2; ++t) {
+      const float keep = hi ? v[N / 2 + t] : v[t];
+      const float send = hi ? v[t] : v[N / 2 + t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+    return MultiReduce<N / 2, OFF / 2>::run(v, lane);
+  }
+};
+template <int OFF>
+struct MultiReduce<1, OFF> {
+  template <int U>
+  static __device__ __forceinline__ float run(float (&v)[U], int) {
+    float x = v[0];
+#pragma unroll
+    for (int o = OFF; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  }
+};
+template <>
+struct MultiReduce<1, 0> {
+  template <int U>
+  static __device__ __forceinline__ float run(float (&v)[U], int) { return v[0]; }
+};
+template <int U>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[U], int lane) {
+  static_assert(U >= 1 && U <= 32 && (U & (U - 1)) == 0, "U must be a power of two <= 32");
+  return MultiReduce<U, 16>::run(v, lane);
+}
+template <int U>
+struct Log2 { static constexpr int value = 1 + Log2<U / 2>::value; };
+template <>
+struct Log2<1> { static constexpr int value = 0; };
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));

@@ -458,11 +458,12 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
       load_group(bufA, i, 0);                      // dout gathers start before the per-edge scalar math
       if (U < cnt) load_group(bufB, i, U);
 
-      float alpha[H], agg[H], gsc[H], tt[H], ks[H], my_de[H];
+      // per lane (= per edge of this chunk): agg = alpha' / H (weight of dout_i in dh_j), and the two coefficients of
+      // de = alpha * (dalpha * keep - t) * slope  written as  de = gA * <dout_i, h_j> - cB
+      float agg[H], gA[H], cB[H], my_de[H];
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) {
-        alpha[hh] = agg[hh] = gsc[hh] = tt[hh] = my_de[hh] = 0.f;
-        ks[hh] = 1.f;
+        agg[hh] = gA[hh] = cB[hh] = my_de[hh] = 0.f;
         if (valid) {
           const float4 st = __ldg(nodestat + (size_t)i * H + hh);  // (s_dst, m, 1/D, t)
           const float z0 = ssj[hh] + st.x;
@@ -472,30 +473,42 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
             zc = fminf(fmaxf(zl, -10.f), 10.f);
             pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;  // clamp passes gradient only inside [-10,10]
           }
-          alpha[hh] = expf(zc - st.y) * st.z;
-          gsc[hh] = (z0 > 0.f ? 1.f : neg_slope) * pass;
-          tt[hh] = st.w;
-          if (DROPOUT) ks[hh] = dropout_scale(seed, (uint32_t)__ldg(perm_csc + q), hh, p_drop, inv_keep);
-          agg[hh] = alpha[hh] * ks[hh] * invH;
+          const float alpha = expf(zc - st.y) * st.z;
+          const float gsc = (z0 > 0.f ? 1.f : neg_slope) * pass;
+          float ks = 1.f;
+          if (DROPOUT) ks = dropout_scale(seed, (uint32_t)__ldg(perm_csc + q), hh, p_drop, inv_keep);
+          agg[hh] = alpha * ks * invH;
+          gA[hh] = agg[hh] * gsc;
+          cB[hh] = alpha * st.w * gsc;
         }
       }
       auto consume = [&](GBuf(&buf)[U], int k) {
+        // dalpha of the U edges of this group: per-lane partial dots first, then ONE multi-value warp reduction per head
+        // (7 shuffles for 4 edges instead of 20), then each edge's owner lane fetches its total.
+        float dsum[H][U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int kk = (k + u) & 31;
 #pragma unroll
           for (int hh = 0; hh < H; ++hh) {
             const float a = __shfl_sync(kFull, agg[hh], kk);
-            float dsum = 0.f;
+            float dp = 0.f;
 #pragma unroll
             for (int cv = 0; cv < CV; ++cv) {
               const float4 gv = to_f4(buf[u].g[cv]);
               acc[hh][cv] = fma4(a, gv, acc[hh][cv]);
-              dsum += dot4(hj[hh][cv], gv);
+              dp += dot4(hj[hh][cv], gv);
             }
-            dsum = warp_sum(dsum) * invH;  // d(out)/d(alpha'_ij) for this head
-            if (lane == kk && k + u < cnt) my_de[hh] = alpha[hh] * (dsum * ks[hh] - tt[hh]) * gsc[hh];
+            dsum[hh][u] = dp;
           }
+        }
+        const int mine = (lane - k) & 31;                   // which edge of the group this lane owns (if < U)
+        const bool owner = mine < U && k + mine < cnt;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+          const float tot = warp_multi_sum<U>(dsum[hh], lane);
+          const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (5 - Log2<U>::value));   // <dout_i, h_j> of my edge
+          if (owner) my_de[hh] = gA[hh] * dot - cB[hh];
         }
       };
       for (int k = 0; k < cnt; k += 2 * U) {

@@ -727,14 +727,14 @@ __global__ void att_grad_tc_kernel(const float* __restrict__ W, const float* __r
 static int g_gemm_mode = B200GAT_GEMM_TF32X3;
 
 static int ensure_attrs() {
-  static bool done = false;
-  if (done) return kOk;
+  static DeviceOnce once;
+  if (!once.pending()) return kOk;
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kHSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDwSmem));
-  done = true;
+  once.done();
   return kOk;
 }
 

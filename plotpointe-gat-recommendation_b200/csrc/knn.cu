@@ -445,10 +445,10 @@ template <int KC>
 static int knn_run(const float* emb, int64_t n_items, int k, float min_similarity, int32_t* nbr_idx, float* nbr_sim, int32_t* counts,
                    int32_t* n_unsafe, void* workspace, cudaStream_t st) {
   using C = knn::Cfg<KC>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce once;        // one per KC instantiation
+  if (once.pending()) {
     B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_done = true;
+    once.done();
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
   const int n_blocks = (int)(n_pad / knn::kBlk);

@@ -2,16 +2,19 @@
 from __future__ import annotations
 
 import ctypes
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
 
 
-def knn_neighbors(embeddings: torch.Tensor, k: int = 20, min_similarity: float = 0.3):
+def knn_neighbors(embeddings: torch.Tensor, k: int = 20, min_similarity: float = 0.3, stats: Optional[dict] = None):
     """Top-k cosine neighbours of every row.  Returns (nbr_idx int32 [n, k], nbr_sim fp32 [n, k], counts int32 [n]):
-    rows are in descending similarity, self excluded; ``counts`` = how many entries pass ``>= min_similarity``."""
+    rows are in descending similarity, self excluded; ``counts`` = how many entries pass ``>= min_similarity``.
+    ``embeddings`` is [n, 128] (fused features) or [n, 384] (text embeddings), fp32, on the GPU.  If ``stats`` is a dict,
+    ``stats["exact_rows"]`` receives a device int32 tensor: how many rows the bf16 candidate pass could not prove exact
+    and were therefore recomputed against all columns (dense clumps of near-duplicates); the result is exact either way."""
     if not embeddings.is_cuda:
         raise RuntimeError("b200gat knn: embeddings must be a CUDA tensor (there is no CPU fallback)")
     emb = _lib._f32(embeddings, "embeddings").contiguous()
@@ -26,7 +29,8 @@ def knn_neighbors(embeddings: torch.Tensor, k: int = 20, min_similarity: float =
     with torch.cuda.device(emb.device):
         _lib.call("b200gat_knn_cosine_f32", _lib.ptr(emb), n, d, k, float(min_similarity), _lib.ptr(idx), _lib.ptr(sim), _lib.ptr(counts),
                   _lib.ptr(unsafe), _lib.ptr(ws), out.value, _lib.stream())
-    knn_neighbors.last_exact_rows = unsafe      # device counter: rows redone by the exact path (dense near-duplicates)
+    if stats is not None:
+        stats["exact_rows"] = unsafe
     return idx, sim, counts
 
 

@@ -77,8 +77,9 @@ def test_knn_dense_duplicates_take_the_exact_path(d):
     dup = np.repeat(centers, 120, axis=0) + 1e-4 * rng.standard_normal((600, d))          # 5 clumps of 120 near-duplicates
     emb = np.concatenate([dup, rng.standard_normal((424, d))]).astype(np.float32)
     n, k = emb.shape[0], 20
-    idx, sim, counts = b200gat.knn_neighbors(torch.from_numpy(emb).cuda(), k, 0.3)
-    assert int(b200gat.knn_neighbors.last_exact_rows.item()) >= 600
+    stats = {}
+    idx, sim, counts = b200gat.knn_neighbors(torch.from_numpy(emb).cuda(), k, 0.3, stats=stats)
+    assert int(stats["exact_rows"].item()) >= 600
     idx, sim, counts = idx.cpu().numpy(), sim.cpu().numpy(), counts.cpu().numpy()
     en = emb.astype(np.float64)
     en /= np.linalg.norm(en, axis=1, keepdims=True)

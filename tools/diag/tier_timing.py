@@ -8,7 +8,8 @@ nu, ni, n_inter, k = synth.CONFIGS["amazon"]
 ei, feats = synth.make_graph(nu, ni, n_inter, k)
 eid, fd = ei.to(dev), feats.to(dev)
 u, i, j = (t.to(dev) for t in synth.make_triples(nu, ni, 200000))
-for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+tiers = os.environ.get("TIERS", "f32,bf16").split(",")
+for name, dt in [t for t in (("f32", torch.float32), ("bf16", torch.bfloat16)) if t[0] in tiers]:
     torch.manual_seed(42)
     m = b200gat.PyGGAT(nu, ni, 128, 128, 2, heads=1, attn_dropout=0.1, feature_dtype=dt).to(dev).train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)

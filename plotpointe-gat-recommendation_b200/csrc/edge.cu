@@ -634,6 +634,286 @@ __global__ void __launch_bounds__(256) ds_dst_thread_kernel(const float* __restr
   for (int hh = 0; hh < H; ++hh) ds_dst[(size_t)r * ld_ds + hh] = a[hh];
 }
 
+// --------------------------------------------------------------------------------------------
+// H * C == 128 (the headline shape): HALF a warp per scheduled row.
+// Rows are short (mean in-degree 19, a third of them below 10), so what bounds the warp-per-row kernels is the
+// number of rows being worked on at once (every row is a chain of dependent loads: schedule entry -> edge ids ->
+// feature rows), not the bytes each warp keeps in flight.  Here a warp carries two neighbouring schedule entries
+// (neighbours in the degree-sorted schedule have almost the same length), 16 lanes each; a lane owns channels
+// [4 sl, 4 sl + 4) and [64 + 4 sl, 64 + 4 sl + 4), so both 128-bit loads of a row stay fully coalesced.  Bytes in
+// flight per warp and registers per lane are unchanged; the number of concurrent row chains doubles.
+// Every shuffle is executed by the full warp (width 16 keeps the data inside each half), so trip counts are the
+// maximum over the two halves and the shorter half is predicated off.
+// --------------------------------------------------------------------------------------------
+#ifndef EDGE_W
+#define EDGE_W 16      // 16: half-warp kernels for H*C == 128; 32: the generic warp-per-row kernels everywhere
+#endif
+// Measured on config 2 (fp32, ms for both layers; generic warp-per-row kernels: fwd 2.63, bwd 3.32):
+//   rows per group 2, 8 blocks/SM: fwd 2.42, bwd 3.33 (bwd spills)      rows per group 1, 8 blocks/SM: fwd 1.93, bwd 2.78
+//   rows per group 1, 9 blocks/SM: fwd 1.94, bwd 2.73                   rows per group 1, 10 blocks/SM: fwd 2.17, bwd 2.92 (spills)
+#ifndef EDGE_U16_FWD
+#define EDGE_U16_FWD 1
+#endif
+#ifndef EDGE_U16_BWD
+#define EDGE_U16_BWD 1
+#endif
+#ifndef EDGE_MINB16_FWD
+#define EDGE_MINB16_FWD 9
+#endif
+#ifndef EDGE_MINB16_BWD
+#define EDGE_MINB16_BWD 9
+#endif
+
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+template <typename T>
+struct HalfRow {
+  typename Raw4<T>::type a, b;
+};
+
+template <typename T, int POLICY, bool DROPOUT>
+__global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_FWD) edge_fwd16_kernel(const T* __restrict__ h, const float* __restrict__ s,
+                                                                            const int4* __restrict__ sched,
+                                                                            const int32_t* __restrict__ col,
+                                                                            const int32_t* __restrict__ perm, int n_rows,
+                                                                            int row_offset, float neg_slope,
+                                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                                            float* __restrict__ out_heads,
+                                                                            float2* __restrict__ rowstat, float* __restrict__ partial,
+                                                                            float p_drop, uint64_t seed) {
+  constexpr int C = 128;
+  constexpr int U = EDGE_U16_FWD * (sizeof(T) == 2 ? 2 : 1);   // rows per load group and half; two groups in flight
+  const int lane = threadIdx.x & 31, sl = lane & 15;
+  const int idx = (blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+  if ((idx & ~1) >= n_rows) return;     // both halves past the end
+  const bool live = idx < n_rows;
+  const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
+  const int4 d = live ? __ldg(sched + idx) : make_int4(0, 0, 0, 0);
+  const int r = d.x, beg = d.y, end = d.z;
+  const int ch0 = sl * 4, ch1 = 64 + sl * 4;
+
+  auto load_group = [&](HalfRow<T>(&buf)[U], int c, int k, int cnt) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ck = __shfl_sync(kFull, c, (k + u) & 15, 16);
+      if (k + u < cnt) {
+        const T* hp = h + (size_t)ck * C;
+        buf[u].a = ld_raw4(hp + ch0);
+        buf[u].b = ld_raw4(hp + ch1);
+      }
+    }
+  };
+
+  const float sd = live ? __ldg(s + (size_t)(row_offset + r) * 2 + 1) : 0.f;
+  float m = POLICY == kPyG ? -INFINITY : 0.f, l = 0.f;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  const int nch_mine = (end - beg + 15) >> 4;
+  const int nch = max(nch_mine, __shfl_xor_sync(kFull, nch_mine, 16));
+  for (int ch = 0; ch < nch; ++ch) {
+    const int base = beg + ch * 16;
+    const int e = base + sl;
+    const bool valid = e < end;
+    const int c = valid ? __ldg(col + e) : 0;
+    const float sv = valid ? __ldg(s + (size_t)c * 2) : 0.f;
+    const int cnt = min(16, end - base);                                  // <= 0 once this half is done
+    const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));           // warp-uniform trip count
+    HalfRow<T> bufA[U], bufB[U];
+    load_group(bufA, c, 0, cnt);                                          // gathers start before the softmax math
+    if (U < cmax) load_group(bufB, c, U, cnt);
+
+    float z = -INFINITY, p;
+    if (valid) z = activate<POLICY>(sv + sd, neg_slope);
+    if (POLICY == kPyG) {
+      const float nm = fmaxf(m, half_max(z));
+      if (nm != m) {   // uniform inside the half
+        const float scale = expf(m - nm);
+        l *= scale;
+        acc0.x *= scale; acc0.y *= scale; acc0.z *= scale; acc0.w *= scale;
+        acc1.x *= scale; acc1.y *= scale; acc1.z *= scale; acc1.w *= scale;
+        m = nm;
+      }
+      p = valid ? expf(z - nm) : 0.f;
+    } else {
+      p = valid ? expf(z) : 0.f;
+    }
+    l += p;   // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
+    if (DROPOUT && valid) p *= dropout_scale(seed, (uint32_t)__ldg(perm + e), 0, p_drop, inv_keep);
+
+    auto consume = [&](HalfRow<T>(&buf)[U], int k) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float pk = __shfl_sync(kFull, p, (k + u) & 15, 16);
+        if (k + u < cnt) {
+          acc0 = fma4(pk, to_f4(buf[u].a), acc0);
+          acc1 = fma4(pk, to_f4(buf[u].b), acc1);
+        }
+      }
+    };
+    for (int k = 0; k < cmax; k += 2 * U) {
+      consume(bufA, k);
+      if (k + 2 * U < cmax) load_group(bufA, c, k + 2 * U, cnt);
+      if (k + U < cmax) {
+        consume(bufB, k + U);
+        if (k + 3 * U < cmax) load_group(bufB, c, k + 3 * U, cnt);
+      }
+    }
+  }
+  const float lt = half_sum(l);
+  if (!live) return;
+  if (d.w > 0) {  // segment of a split (long) row: park the un-normalised state, fwd_combine_kernel finishes the row
+    float* ps = partial + (size_t)(d.w - 1) * (C + 4);
+    if (sl == 0) { ps[0] = m; ps[1] = lt; }
+    *reinterpret_cast<float4*>(ps + 4 + ch0) = acc0;
+    *reinterpret_cast<float4*>(ps + 4 + ch1) = acc1;
+    return;
+  }
+  const float inv = 1.f / (lt + (POLICY == kCustom ? 1e-9f : 1e-16f));
+  if (sl == 0 && rowstat) rowstat[r] = make_float2(beg < end ? m : 0.f, inv);
+  acc0.x *= inv; acc0.y *= inv; acc0.z *= inv; acc0.w *= inv;
+  acc1.x *= inv; acc1.y *= inv; acc1.z *= inv; acc1.w *= inv;
+  if (out_heads) {
+    st_stream4(out_heads + (size_t)r * C + ch0, acc0);
+    st_stream4(out_heads + (size_t)r * C + ch1, acc1);
+  }
+  if (bias) {
+    const float4 b0 = ldg4(bias + ch0), b1 = ldg4(bias + ch1);
+    acc0.x += b0.x; acc0.y += b0.y; acc0.z += b0.z; acc0.w += b0.w;
+    acc1.x += b1.x; acc1.y += b1.y; acc1.z += b1.z; acc1.w += b1.w;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)r * C + ch0) = acc0;
+  *reinterpret_cast<float4*>(out + (size_t)r * C + ch1) = acc1;
+}
+
+template <typename T, int POLICY, bool DROPOUT>
+__global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kernel(const T* __restrict__ h, const float* __restrict__ s,
+                                                                            const T* __restrict__ dout,
+                                                                            const float4* __restrict__ nodestat,
+                                                                            const int4* __restrict__ sched,
+                                                                            const int32_t* __restrict__ row,
+                                                                            const int32_t* __restrict__ perm_csc, int n_rows,
+                                                                            int row_offset, float neg_slope, float* __restrict__ dh,
+                                                                            float* __restrict__ de, float* __restrict__ ds_src,
+                                                                            int ld_ds, float* __restrict__ partial, float p_drop,
+                                                                            uint64_t seed) {
+  constexpr int C = 128;
+  constexpr int U = EDGE_U16_BWD * (sizeof(T) == 2 ? 2 : 1);
+  const int lane = threadIdx.x & 31, sl = lane & 15;
+  const int idx = (blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+  if ((idx & ~1) >= n_rows) return;
+  const bool live = idx < n_rows;
+  const float inv_keep = DROPOUT ? 1.f / (1.f - p_drop) : 1.f;
+  const int4 d = live ? __ldg(sched + idx) : make_int4(0, 0, 0, 0);
+  const int r = d.x, beg = d.y, end = d.z;
+  const int ch0 = sl * 4, ch1 = 64 + sl * 4;
+  const size_t j = (size_t)row_offset + r;
+
+  auto load_group = [&](HalfRow<T>(&buf)[U], int i, int k, int cnt) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ik = __shfl_sync(kFull, i, (k + u) & 15, 16);
+      if (k + u < cnt) {
+        const T* gp = dout + (size_t)ik * C;
+        buf[u].a = ld_raw4(gp + ch0);
+        buf[u].b = ld_raw4(gp + ch1);
+      }
+    }
+  };
+
+  float4 hj0 = make_float4(0.f, 0.f, 0.f, 0.f), hj1 = hj0, acc0 = hj0, acc1 = hj0;
+  float ssj = 0.f, dss = 0.f;
+  if (beg < end) {   // false for the dead half too (beg = end = 0)
+    ssj = __ldg(s + j * 2);
+    hj0 = to_f4(ld_raw4(h + j * C + ch0));
+    hj1 = to_f4(ld_raw4(h + j * C + ch1));
+  }
+  const int nch_mine = (end - beg + 15) >> 4;
+  const int nch = max(nch_mine, __shfl_xor_sync(kFull, nch_mine, 16));
+  for (int ch = 0; ch < nch; ++ch) {
+    const int base = beg + ch * 16;
+    const int q = base + sl;
+    const bool valid = q < end;
+    const int i = valid ? __ldg(row + q) : 0;
+    const int cnt = min(16, end - base);
+    const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
+    HalfRow<T> bufA[U], bufB[U];
+    load_group(bufA, i, 0, cnt);                      // dout gathers start before the per-edge scalar math
+    if (U < cmax) load_group(bufB, i, U, cnt);
+
+    // per lane (= per edge of this chunk): agg = alpha' (weight of dout_i in dh_j), and the two coefficients of
+    // de = alpha * (dalpha * keep - t) * slope  written as  de = gA * <dout_i, h_j> - cB
+    float agg = 0.f, gA = 0.f, cB = 0.f, my_de = 0.f;
+    if (valid) {
+      const float4 st = __ldg(nodestat + i);  // (s_dst, m, 1/D, t)
+      const float z0 = ssj + st.x;
+      const float zl = z0 > 0.f ? z0 : z0 * neg_slope;
+      float zc = zl, pass = 1.f;
+      if (POLICY == kCustom) {
+        zc = fminf(fmaxf(zl, -10.f), 10.f);
+        pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;  // clamp passes gradient only inside [-10,10]
+      }
+      const float alpha = expf(zc - st.y) * st.z;
+      const float gsc = (z0 > 0.f ? 1.f : neg_slope) * pass;
+      float ks = 1.f;
+      if (DROPOUT) ks = dropout_scale(seed, (uint32_t)__ldg(perm_csc + q), 0, p_drop, inv_keep);
+      agg = alpha * ks;
+      gA = agg * gsc;
+      cB = alpha * st.w * gsc;
+    }
+    auto consume = [&](HalfRow<T>(&buf)[U], int k) {
+      float dsum[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float a = __shfl_sync(kFull, agg, (k + u) & 15, 16);
+        dsum[u] = 0.f;
+        if (k + u < cnt) {
+          const float4 g0 = to_f4(buf[u].a), g1 = to_f4(buf[u].b);
+          acc0 = fma4(a, g0, acc0);
+          acc1 = fma4(a, g1, acc1);
+          dsum[u] = dot4(hj0, g0) + dot4(hj1, g1);
+        }
+      }
+      const int mine = (sl - k) & 15;                    // which edge of the group this lane owns (if < U)
+      const bool owner = mine < U && k + mine < cnt;
+      const float tot = MultiReduce<U, 8>::run(dsum, lane);               // total of edge u sits in lanes sl >> (4 - log2 U) == u
+      const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (4 - Log2<U>::value), 16);
+      if (owner) my_de = gA * dot - cB;
+    };
+    for (int k = 0; k < cmax; k += 2 * U) {
+      consume(bufA, k);
+      if (k + 2 * U < cmax) load_group(bufA, i, k + 2 * U, cnt);
+      if (k + U < cmax) {
+        consume(bufB, k + U);
+        if (k + 3 * U < cmax) load_group(bufB, i, k + 3 * U, cnt);
+      }
+    }
+    if (valid) {
+      de[q] = my_de;
+      dss += my_de;
+    }
+  }
+  const float t = half_sum(dss);
+  if (!live) return;
+  if (d.w > 0) {  // segment of a split (long) row: bwd_combine_kernel sums the segments in order
+    float* ps = partial + (size_t)(d.w - 1) * (C + 4);
+    if (sl == 0) ps[0] = t;
+    *reinterpret_cast<float4*>(ps + 4 + ch0) = acc0;
+    *reinterpret_cast<float4*>(ps + 4 + ch1) = acc1;
+    return;
+  }
+  if (sl == 0) ds_src[(size_t)r * ld_ds] = t;
+  *reinterpret_cast<float4*>(dh + (size_t)r * C + ch0) = acc0;
+  *reinterpret_cast<float4*>(dh + (size_t)r * C + ch1) = acc1;
+}
+
 // ---- dispatch helpers ---------------------------------------------------------------------------
 #define B200GAT_DISPATCH_HC(H_, CV_, ...)                                        \
   if (H_ == 1 && CV_ == 1) { constexpr int kH = 1, kCV = 1; __VA_ARGS__; }        \
@@ -719,11 +999,18 @@ static int edge_fwd_impl(const T* h, const float* s, const int32_t* sched, int64
   int grid = 0;
 #define LAUNCH_FWD(P, D)                                                                                                \
   do {                                                                                                                  \
-    rc = persistent_grid(edge_fwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                               \
-    if (rc) return rc;                                                                                                  \
-    count_launch(), edge_fwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                   \
-        h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,        \
-        (float2*)rowstat, partial, p_drop, seed);                                                                       \
+    if (kH * kCV == 1 && EDGE_W == 16) {                                                                                \
+      grid = (int)ceil_div(n_rows, 2 * (kEdgeThreads / 32));                                                            \
+      count_launch(), edge_fwd16_kernel<T, P, D><<<grid, kEdgeThreads, 0, st>>>(                                        \
+          h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,      \
+          (float2*)rowstat, partial, p_drop, seed);                                                                     \
+    } else {                                                                                                            \
+      rc = persistent_grid(edge_fwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                             \
+      if (rc) return rc;                                                                                                \
+      count_launch(), edge_fwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                 \
+          h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,      \
+          (float2*)rowstat, partial, p_drop, seed);                                                                     \
+    }                                                                                                                   \
     if (n_long > 0)                                                                                                     \
       count_launch(), fwd_combine_kernel<P, kH, kCV><<<ceil_div(n_long * 32, kEdgeThreads), kEdgeThreads, 0, st>>>(     \
           partial, (const int4*)long_table, (int)n_long, bias, out, out_heads, (float2*)rowstat);                       \
@@ -803,11 +1090,18 @@ static int edge_bwd_impl(const T* h, const float* s, const T* dout, const float*
   int grid = 0;
 #define LAUNCH_BWD(P, D)                                                                                               \
   do {                                                                                                                 \
-    rc = persistent_grid(edge_bwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                              \
-    if (rc) return rc;                                                                                                 \
-    count_launch(), edge_bwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                  \
-        h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,          \
-        negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                                 \
+    if (kH * kCV == 1 && EDGE_W == 16) {                                                                               \
+      grid = (int)ceil_div(n_rows, 2 * (kEdgeThreads / 32));                                                           \
+      count_launch(), edge_bwd16_kernel<T, P, D><<<grid, kEdgeThreads, 0, st>>>(                                       \
+          h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,        \
+          negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                               \
+    } else {                                                                                                           \
+      rc = persistent_grid(edge_bwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                            \
+      if (rc) return rc;                                                                                               \
+      count_launch(), edge_bwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                \
+          h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,        \
+          negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                               \
+    }                                                                                                                  \
     if (n_long > 0)                                                                                                    \
       count_launch(), bwd_combine_kernel<kH, kCV><<<ceil_div(n_long * 32, kEdgeThreads), kEdgeThreads, 0, st>>>(       \
           partial, (const int4*)long_table, (int)n_long, dh, ds_src, ld_ds);                                           \

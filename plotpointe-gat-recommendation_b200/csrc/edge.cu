@@ -648,20 +648,36 @@ __global__ void __launch_bounds__(256) ds_dst_thread_kernel(const float* __restr
 #ifndef EDGE_W
 #define EDGE_W 16      // 16: half-warp kernels for H*C == 128; 32: the generic warp-per-row kernels everywhere
 #endif
-// Measured on config 2 (fp32, ms for both layers; generic warp-per-row kernels: fwd 2.63, bwd 3.32):
-//   rows per group 2, 8 blocks/SM: fwd 2.42, bwd 3.33 (bwd spills)      rows per group 1, 8 blocks/SM: fwd 1.93, bwd 2.78
-//   rows per group 1, 9 blocks/SM: fwd 1.94, bwd 2.73                   rows per group 1, 10 blocks/SM: fwd 2.17, bwd 2.92 (spills)
+// Tuning knobs, set from A/B builds on config 2 (ms for both layers; generic warp-per-row kernels: fp32 fwd 2.63, bwd 3.32).
+// U = rows per load group and half (x2 for bf16 rows), NB = load groups in flight, MINB = resident blocks per SM.
+//   fp32 fwd: U1 NB2 MINB9 1.93 | U1 NB4 MINB8 1.86 | U1 NB3 MINB9 2.02 | U2 NB2 MINB8 2.42 | U1 NB2 MINB10 2.17 | U1 NB8 MINB6 2.99
+//   fp32 bwd: U1 NB2 MINB9 2.72 | U1 NB1 MINB10 2.65 | U1 NB1 MINB9 2.70 | U1 NB1 MINB12 2.74 | U2 NB2 MINB8 3.33 | U1 NB1 MINB16 3.39
+//   bf16 fwd: U2 NB2 MINB9 1.67 | U2 NB4 MINB8 1.84          bf16 bwd: U2 NB2 MINB9 2.21 | U2 NB1 MINB10 2.03
+// Fewer bytes in flight per row chain and more chains win: the rows are short, and spills or a lower block count cost more
+// than the extra loads in flight buy.
 #ifndef EDGE_U16_FWD
 #define EDGE_U16_FWD 1
 #endif
 #ifndef EDGE_U16_BWD
 #define EDGE_U16_BWD 1
 #endif
+#ifndef EDGE_NB16_FWD
+#define EDGE_NB16_FWD 4
+#endif
+#ifndef EDGE_NB16_FWD_BF16
+#define EDGE_NB16_FWD_BF16 2
+#endif
+#ifndef EDGE_NB16_BWD
+#define EDGE_NB16_BWD 1
+#endif
 #ifndef EDGE_MINB16_FWD
-#define EDGE_MINB16_FWD 9
+#define EDGE_MINB16_FWD 8
+#endif
+#ifndef EDGE_MINB16_FWD_BF16
+#define EDGE_MINB16_FWD_BF16 9
 #endif
 #ifndef EDGE_MINB16_BWD
-#define EDGE_MINB16_BWD 9
+#define EDGE_MINB16_BWD 10
 #endif
 
 __device__ __forceinline__ float half_sum(float v) {
@@ -681,7 +697,7 @@ struct HalfRow {
 };
 
 template <typename T, int POLICY, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_FWD) edge_fwd16_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD_BF16 : EDGE_MINB16_FWD) edge_fwd16_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                             const int4* __restrict__ sched,
                                                                             const int32_t* __restrict__ col,
                                                                             const int32_t* __restrict__ perm, int n_rows,
@@ -726,9 +742,12 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_FWD) edge_fwd16_kern
     const float sv = valid ? __ldg(s + (size_t)c * 2) : 0.f;
     const int cnt = min(16, end - base);                                  // <= 0 once this half is done
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));           // warp-uniform trip count
-    HalfRow<T> bufA[U], bufB[U];
-    load_group(bufA, c, 0, cnt);                                          // gathers start before the softmax math
-    if (U < cmax) load_group(bufB, c, U, cnt);
+    constexpr int NB = sizeof(T) == 2 ? EDGE_NB16_FWD_BF16 : EDGE_NB16_FWD;
+    HalfRow<T> buf[NB][U];
+    load_group(buf[0], c, 0, cnt);                                        // gathers start before the softmax math
+#pragma unroll
+    for (int b = 1; b < NB; ++b)
+      if (b * U < cmax) load_group(buf[b], c, b * U, cnt);
 
     float z = -INFINITY, p;
     if (valid) z = activate<POLICY>(sv + sd, neg_slope);
@@ -758,12 +777,15 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_FWD) edge_fwd16_kern
         }
       }
     };
-    for (int k = 0; k < cmax; k += 2 * U) {
-      consume(bufA, k);
-      if (k + 2 * U < cmax) load_group(bufA, c, k + 2 * U, cnt);
-      if (k + U < cmax) {
-        consume(bufB, k + U);
-        if (k + 3 * U < cmax) load_group(bufB, c, k + 3 * U, cnt);
+    for (int k = 0; k < cmax; k += NB * U) {
+      consume(buf[0], k);
+      if (k + NB * U < cmax) load_group(buf[0], c, k + NB * U, cnt);
+#pragma unroll
+      for (int b = 1; b < NB; ++b) {
+        if (k + b * U < cmax) {                                           // warp-uniform
+          consume(buf[b], k + b * U);
+          if (k + (b + NB) * U < cmax) load_group(buf[b], c, k + (b + NB) * U, cnt);
+        }
       }
     }
   }
@@ -844,9 +866,12 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
     const int i = valid ? __ldg(row + q) : 0;
     const int cnt = min(16, end - base);
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
-    HalfRow<T> bufA[U], bufB[U];
-    load_group(bufA, i, 0, cnt);                      // dout gathers start before the per-edge scalar math
-    if (U < cmax) load_group(bufB, i, U, cnt);
+    constexpr int NB = EDGE_NB16_BWD;
+    HalfRow<T> buf[NB][U];
+    load_group(buf[0], i, 0, cnt);                    // dout gathers start before the per-edge scalar math
+#pragma unroll
+    for (int b = 1; b < NB; ++b)
+      if (b * U < cmax) load_group(buf[b], i, b * U, cnt);
 
     // per lane (= per edge of this chunk): agg = alpha' (weight of dout_i in dh_j), and the two coefficients of
     // de = alpha * (dalpha * keep - t) * slope  written as  de = gA * <dout_i, h_j> - cB
@@ -887,12 +912,15 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
       const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (4 - Log2<U>::value), 16);
       if (owner) my_de = gA * dot - cB;
     };
-    for (int k = 0; k < cmax; k += 2 * U) {
-      consume(bufA, k);
-      if (k + 2 * U < cmax) load_group(bufA, i, k + 2 * U, cnt);
-      if (k + U < cmax) {
-        consume(bufB, k + U);
-        if (k + 3 * U < cmax) load_group(bufB, i, k + 3 * U, cnt);
+    for (int k = 0; k < cmax; k += NB * U) {
+      consume(buf[0], k);
+      if (k + NB * U < cmax) load_group(buf[0], i, k + NB * U, cnt);
+#pragma unroll
+      for (int b = 1; b < NB; ++b) {
+        if (k + b * U < cmax) {                       // warp-uniform
+          consume(buf[b], k + b * U);
+          if (k + (b + NB) * U < cmax) load_group(buf[b], i, k + (b + NB) * U, cnt);
+        }
       }
     }
     if (valid) {

@@ -734,11 +734,13 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
   const int nch_mine = (end - beg + 15) >> 4;
   const int nch = max(nch_mine, __shfl_xor_sync(kFull, nch_mine, 16));
+  int c_next = (beg + sl < end) ? __ldg(col + beg + sl) : 0;
   for (int ch = 0; ch < nch; ++ch) {
     const int base = beg + ch * 16;
     const int e = base + sl;
     const bool valid = e < end;
-    const int c = valid ? __ldg(col + e) : 0;
+    const int c = c_next;
+    if (ch + 1 < nch) c_next = (e + 16 < end) ? __ldg(col + e + 16) : 0;   // next chunk's ids: one load latency off the chain
     const float sv = valid ? __ldg(s + (size_t)c * 2) : 0.f;
     const int cnt = min(16, end - base);                                  // <= 0 once this half is done
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));           // warp-uniform trip count
@@ -859,11 +861,13 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
   }
   const int nch_mine = (end - beg + 15) >> 4;
   const int nch = max(nch_mine, __shfl_xor_sync(kFull, nch_mine, 16));
+  int i_next = (beg + sl < end) ? __ldg(row + beg + sl) : 0;
   for (int ch = 0; ch < nch; ++ch) {
     const int base = beg + ch * 16;
     const int q = base + sl;
     const bool valid = q < end;
-    const int i = valid ? __ldg(row + q) : 0;
+    const int i = i_next;
+    if (ch + 1 < nch) i_next = (q + 16 < end) ? __ldg(row + q + 16) : 0;   // next chunk's ids: one load latency off the chain
     const int cnt = min(16, end - base);
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
     constexpr int NB = EDGE_NB16_BWD;

@@ -8,17 +8,49 @@
 
 namespace b200gat {
 
-__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 int64_t n, float lr, float b1, float b2, float eps, float wd, float inv_bc1, float inv_sqrt_bc2) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float pi = p[i];
-    const float gi = g[i] + wd * pi;                       // weight decay enters the gradient (Adam, not AdamW)
-    const float mi = m[i] + (gi - m[i]) * (1.f - b1);      // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] = pi - (lr * inv_bc1) * (mi / denom);
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float lr_c, float b1, float b2, float eps,
+                                            float wd, float inv_sqrt_bc2) {
+  const float gi = g + wd * p;                         // weight decay enters the gradient (Adam, not AdamW)
+  m = m + (gi - m) * (1.f - b1);                       // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * b2 + (1.f - b2) * gi * gi;                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+  p = p - lr_c * (m / denom);
+}
+
+// 128-bit accesses, two independent float4 groups per thread and iteration (7 streams: p, g, m, v in; p, m, v out)
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                        float wd, float inv_bc1, float inv_sqrt_bc2, int vec_ok) {
+  const float lr_c = lr * inv_bc1;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = vec_ok ? n / 4 : 0;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = tid; i < n4; i += 2 * nth) {
+    const int64_t i2 = i + nth;
+    const bool two = i2 < n4;
+    float4 pa = p4[i], ga = ld_stream4(reinterpret_cast<const float*>(g4 + i)), ma = m4[i], va = v4[i];
+    float4 pb = pa, gb = ga, mb = ma, vb = va;
+    if (two) { pb = p4[i2]; gb = ld_stream4(reinterpret_cast<const float*>(g4 + i2)); mb = m4[i2]; vb = v4[i2]; }
+    adam_update(pa.x, ga.x, ma.x, va.x, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+    adam_update(pa.y, ga.y, ma.y, va.y, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+    adam_update(pa.z, ga.z, ma.z, va.z, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+    adam_update(pa.w, ga.w, ma.w, va.w, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+    if (two) {
+      adam_update(pb.x, gb.x, mb.x, vb.x, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+      adam_update(pb.y, gb.y, mb.y, vb.y, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+      adam_update(pb.z, gb.z, mb.z, vb.z, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+      adam_update(pb.w, gb.w, mb.w, vb.w, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+      p4[i2] = pb; m4[i2] = mb; v4[i2] = vb;
+    }
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += nth) {     // tail, or everything when a pointer is not 16-byte aligned
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, g[i], mi, vi, lr_c, b1, b2, eps, wd, inv_sqrt_bc2);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -86,10 +118,12 @@ extern "C" int b200gat_adam_step_f32(float* param, const float* grad, float* exp
   B200GAT_CHECK_ARG(step >= 1, "step counts from 1");
   if (n == 0) return kOk;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  const int64_t want = (n + 255) / 256, cap = (int64_t)kNumSMs * 16;
+  const int vec_ok = (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0;
+  const int64_t want = (n / 8 + 255) / 256 + 1, cap = (int64_t)kNumSMs * 8;
   const int grid = (int)(want < cap ? want : cap);
   count_launch(), adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                          weight_decay, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)));
+                                                                          weight_decay, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)),
+                                                                          vec_ok);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -194,6 +194,12 @@ def run_ours(args):
             roof["traffic"] = json.load(open(traffic_file)).get(dom)
         except Exception:
             pass
+    # `achieved` divides the gather-model (algorithmic) bytes, which pay for every gathered row, by the launch time; rows
+    # that hit in L2 make it exceed the DRAM peak.  `dram_frac` is the same launch time against the bytes DRAM really
+    # moved (ncu dram__bytes_read + write of the committed --set full capture).
+    if roof["traffic"]:
+        roof["dram_gbs"] = round(roof["traffic"] / (per_call[dom]["avg_ms"] * 1e-3) / 1e9, 1)
+        roof["dram_frac"] = round(roof["dram_gbs"] / pk["hbm_gbs"], 4)
 
     extras = next_row_extras(model, fd, eid, nu, ni, dev)
     cpu = cpu_baseline(args, nu, ni, ei, feats, (u, i, j)) if not args.no_cpu_baseline else None

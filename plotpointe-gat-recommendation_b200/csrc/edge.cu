@@ -591,26 +591,29 @@ __global__ void __launch_bounds__(kEdgeThreads) bwd_combine_kernel(const float* 
 // --------------------------------------------------------------------------------------------
 // backward, step 2: ds_dst[i,h] = sum over in-edges of de (CSR order, via the CSR->CSC map)
 // --------------------------------------------------------------------------------------------
-template <int H>
+// W lanes per row (32 / W rows per warp): a row is a chain rowptr -> csr2csc -> de, so rows in flight set the speed
+template <int H, int W>
 __global__ void __launch_bounds__(128) ds_dst_kernel(const float* __restrict__ de, const int32_t* __restrict__ rowptr,
                                                      const int32_t* __restrict__ csr2csc, int n_rows,
                                                      float* __restrict__ ds_dst, int ld_ds) {
-  const int lane = threadIdx.x & 31;
-  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (r >= n_rows) return;
-  const int beg = rowptr[r], end = rowptr[r + 1];
+  const int sl = threadIdx.x & (W - 1);
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / W;
+  const bool live = r < n_rows;                      // no early return: the shuffles below are warp-wide
+  const int beg = live ? rowptr[r] : 0, end = live ? rowptr[r + 1] : 0;
   float a[H];
 #pragma unroll
   for (int hh = 0; hh < H; ++hh) a[hh] = 0.f;
-  for (int e = beg + lane; e < end; e += 32) {
+  for (int e = beg + sl; e < end; e += W) {
     const size_t q = (size_t)csr2csc[e];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) a[hh] += de[q * H + hh];
   }
 #pragma unroll
   for (int hh = 0; hh < H; ++hh) {
-    const float t = warp_sum(a[hh]);
-    if (lane == 0) ds_dst[(size_t)r * ld_ds + hh] = t;
+    float t = a[hh];
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if (live && sl == 0) ds_dst[(size_t)r * ld_ds + hh] = t;
   }
 }
 
@@ -1182,11 +1185,12 @@ extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const 
     B200GAT_LAUNCH_CHECK();
     return kOk;
   }
-  const int grid = ceil_div(n_rows * 32, 128);
+  constexpr int kW = 8;
+  const int grid = ceil_div(n_rows * kW, 128);
   cudaStream_t st = (cudaStream_t)stream;
-  if (heads == 1) count_launch(), ds_dst_kernel<1><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
-  else if (heads == 2) count_launch(), ds_dst_kernel<2><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
-  else if (heads == 4) count_launch(), ds_dst_kernel<4><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  if (heads == 1) count_launch(), ds_dst_kernel<1, kW><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 2) count_launch(), ds_dst_kernel<2, kW><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
+  else if (heads == 4) count_launch(), ds_dst_kernel<4, kW><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
   else { set_error("unsupported heads=%d", heads); return kErrUnsupported; }
   B200GAT_LAUNCH_CHECK();
   return kOk;

@@ -2,11 +2,12 @@
 // mean -- replaces scripts/train_gat_custom.py:350-359 (three S x C gathers, two S x C products and
 // the reductions) and its autograd backward (an index_put with duplicate rows).
 //
-// forward : warp per triple; per-triple gradient coefficients are kept (2S floats); block partial
+// forward : 8 lanes per triple; per-triple gradient coefficients are kept (2S floats); block partial
 //           sums are reduced in a fixed order -> deterministic loss.
 // backward: the 3S (node, triple) incidences are stably sorted by node once per triple set
-//           (radix sort from graph.cu); a warp per node then accumulates its incidences in that
+//           (radix sort from graph.cu); 8 lanes per node then accumulate its incidences in that
 //           order -> dZ[N, C] without atomics, every row written exactly once.
+// Both kernels are chains of dependent loads per unit of work, so they use narrow lane groups to keep many in flight.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -20,6 +21,11 @@ constexpr int kBce = B200GAT_LOSS_BCE;
 __device__ __forceinline__ float softplusf(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
 __device__ __forceinline__ float sigmoidf_(float a) { return 1.f / (1.f + expf(-a)); }
 
+// 8 lanes per triple (32 triples per block of 256 threads): a triple is a chain triple ids -> node_map -> three rows, so
+// the kernel's speed is the number of triples in flight; a lane owns 4-channel pieces sl, sl + 8, ... of each row.
+constexpr int kTripleW = 8;
+constexpr int kTriplesPerBlock = 256 / kTripleW;
+
 template <int LOSS>
 __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ z, int C, int64_t n_users, int64_t n_items,
                                                        const int64_t* __restrict__ u, const int64_t* __restrict__ i,
@@ -27,27 +33,34 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ node_map,
                                                        float* __restrict__ coef /*[2S]: d/dpos, d/dneg*/,
                                                        double* __restrict__ partial, int32_t* __restrict__ n_bad) {
-  __shared__ float wsum[8];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t t = blockIdx.x * 8LL + w;
+  constexpr int W = kTripleW;
+  __shared__ float wsum[kTriplesPerBlock];
+  const int sl = threadIdx.x & (W - 1), g = threadIdx.x / W;
+  const int64_t t = blockIdx.x * (int64_t)kTriplesPerBlock + g;
   float term = 0.f;
+  float pos = 0.f, neg = 0.f;
   if (t < S) {
     int64_t uu = u[t], ii = i[t], jj = j[t];
     const bool ok = uu >= 0 && uu < n_users && ii >= 0 && ii < n_items && jj >= 0 && jj < n_items;
-    if (!ok) { uu = 0; ii = 0; jj = 0; if (lane == 0) atomicAdd(n_bad, 1); }
+    if (!ok) { uu = 0; ii = 0; jj = 0; if (sl == 0) atomicAdd(n_bad, 1); }
     int64_t nu_ = uu, ni_ = n_users + ii, nj_ = n_users + jj;
     if (node_map) { nu_ = node_map[nu_]; ni_ = node_map[ni_]; nj_ = node_map[nj_]; }
     const float* zu = z + nu_ * C;
     const float* zi = z + ni_ * C;
     const float* zj = z + nj_ * C;
-    float pos = 0.f, neg = 0.f;
-    for (int c = lane * 4; c < C; c += 128) {
+    for (int c = sl * 4; c < C; c += W * 4) {
       const float4 a = ldg4(zu + c);
       pos += dot4(a, ldg4(zi + c));
       neg += dot4(a, ldg4(zj + c));
     }
-    pos = warp_sum(pos);
-    neg = warp_sum(neg);
+  }
+  // all 32 lanes take part (the groups of a warp are independent; xor offsets < 8 stay inside a group)
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) {
+    pos += __shfl_xor_sync(kFull, pos, o);
+    neg += __shfl_xor_sync(kFull, neg, o);
+  }
+  if (t < S) {
     float gp, gn;
     if (LOSS == kBpr) {  // -log(sigmoid(pos-neg) + 1e-8), train_gat_custom.py:355
       const float sg = sigmoidf_(pos - neg);
@@ -59,14 +72,14 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
       gp = -sigmoidf_(-pos);
       gn = sigmoidf_(neg);
     }
-    if (lane == 0) { coef[t] = gp; coef[S + t] = gn; }
+    if (sl == 0) { coef[t] = gp; coef[S + t] = gn; }
   }
-  if (lane == 0) wsum[w] = term;
+  if (sl == 0) wsum[g] = term;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {   // fixed order -> deterministic loss
     double a = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a += (double)wsum[k];
+    for (int k = 0; k < kTriplesPerBlock; ++k) a += (double)wsum[k];
     partial[blockIdx.x] = a;
   }
 }
@@ -100,6 +113,12 @@ __global__ void incidence_keys_kernel(const int64_t* __restrict__ u, const int64
   }
 }
 
+// kLossW lanes per node (4 nodes per warp): most nodes carry 0-2 incidences, so the kernel is a chain of dependent loads per
+// node (ptr -> ids -> triple -> node_map -> partner row) and its speed is the number of chains in flight, not bytes.
+// A lane owns 4-channel pieces sl, sl + W, sl + 2W, sl + 3W of every block of 16 W channels.  No shuffles: the groups of a
+// warp may run different trip counts.
+constexpr int kLossW = 8;
+
 __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__ z, int C, int64_t n_nodes, int64_t n_users,
                                                        const int64_t* __restrict__ u, const int64_t* __restrict__ i,
                                                        const int64_t* __restrict__ j, int64_t S,
@@ -109,8 +128,9 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
                                                        int64_t node_count, const int32_t* __restrict__ node_map,
                                                        float* __restrict__ dz /*[node_count, C]*/,
                                                        __nv_bfloat16* __restrict__ dz_bf16 /*optional bf16 copy*/) {
-  const int lane = threadIdx.x & 31;
-  const int64_t local = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  constexpr int W = kLossW;
+  const int sl = threadIdx.x & (W - 1);
+  const int64_t local = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / W;
   if (local >= node_count) return;
   const int64_t n = node_list ? (int64_t)node_list[local] : node_begin + local;
   const bool real = n >= 0;                      // node_list entries < 0 are padding rows: written as zeros
@@ -119,27 +139,41 @@ __global__ void __launch_bounds__(128) loss_bwd_kernel(const float* __restrict__
   const int64_t n_items = n_nodes - n_users;
   auto safe = [](int64_t v, int64_t lim) { return (v < 0 || v >= lim) ? (int64_t)0 : v; };
   auto zrow = [&](int64_t node) { return node_map ? (int64_t)node_map[node] : node; };
-  for (int c = lane * 4; c < C; c += 128) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = beg; q < end; ++q) {
+  for (int cb = 0; cb < C; cb += 16 * W) {
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto add_row = [&](float cf, int64_t node) {
+      const float* r = z + zrow(node) * C + cb + sl * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (cb + (k * W + sl) * 4 < C) acc[k] = fma4(cf, ldg4(r + k * W * 4), acc[k]);
+    };
+    for (int q = beg; q < end; ++q) {            // node-sorted, stable: a fixed accumulation order
       const int id = ids[q];
       const int role = id / (int)S;
       const int64_t t = id - (int64_t)role * S;
       if (role == 0) {
-        acc = fma4(coef[t], ldg4(z + zrow(n_users + safe(i[t], n_items)) * C + c), acc);
-        acc = fma4(coef[S + t], ldg4(z + zrow(n_users + safe(j[t], n_items)) * C + c), acc);
+        add_row(coef[t], n_users + safe(i[t], n_items));
+        add_row(coef[S + t], n_users + safe(j[t], n_items));
       } else {
-        acc = fma4(coef[(role - 1) * S + t], ldg4(z + zrow(safe(u[t], n_users)) * C + c), acc);
+        add_row(coef[(role - 1) * S + t], safe(u[t], n_users));
       }
     }
-    acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
-    *reinterpret_cast<float4*>(dz + local * C + c) = acc;
-    if (dz_bf16) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dz_bf16 + local * C + c) = pk;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = cb + (k * W + sl) * 4;
+      if (c >= C) continue;
+      float4 a = acc[k];
+      a.x *= g; a.y *= g; a.z *= g; a.w *= g;
+      *reinterpret_cast<float4*>(dz + local * C + c) = a;
+      if (dz_bf16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dz_bf16 + local * C + c) = pk;
+      }
     }
   }
 }
@@ -196,7 +230,7 @@ extern "C" int b200gat_rank_loss_fwd_f32(const float* z, int64_t n_users, int64_
   const int64_t S = n_triples, N = n_users + n_items;
   LossWs w = carve(workspace, N, S);
   B200GAT_CUDA(cudaMemsetAsync(w.n_bad, 0, 4, st));
-  const int blocks = ceil_div(S, 8);
+  const int blocks = ceil_div(S, kTriplesPerBlock);
   if (loss_kind == kBpr) {
     count_launch(), loss_fwd_kernel<kBpr><<<blocks, 256, 0, st>>>(z, channels, n_users, n_items, u, i, j, S, node_map, w.coef, w.partial, w.n_bad);
     count_launch(), loss_finalize_kernel<<<1, 256, 0, st>>>(w.partial, blocks, 1.0 / (double)S, w.n_bad, loss);
@@ -233,7 +267,7 @@ extern "C" int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_
   if (node_count == 0) return kOk;
   LossWs w = carve(workspace, N, S);
   const float scale = loss_kind == kBpr ? 1.f / (float)S : 0.5f / (float)S;
-  count_launch(), loss_bwd_kernel<<<ceil_div(node_count * 32, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids,
+  count_launch(), loss_bwd_kernel<<<ceil_div(node_count * kLossW, 128), 128, 0, st>>>(z, channels, N, n_users, u, i, j, S, w.coef, w.ptr, w.ids,
                                                                  grad_out, scale, node_list, node_begin, node_count, node_map, dz,
                                                                  (__nv_bfloat16*)dz_bf16);
   B200GAT_LAUNCH_CHECK();

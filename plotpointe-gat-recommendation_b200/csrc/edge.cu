@@ -102,6 +102,14 @@ constexpr int kEdgeThreads = 128;
 #ifndef EDGE_MINB
 #define EDGE_MINB 8
 #endif
+// resident blocks per SM for 2 <= H*C/128 <= 4.  Config 3 (heads 4, bf16 rows), ms for both layers:
+//   forward 4 blocks 7.28 | 5 blocks 6.29 | 6 blocks 6.23      backward 4 blocks 6.25 | 5 blocks 6.41 (spills) | 6 blocks 6.55
+#ifndef EDGE_MINB_H4_FWD
+#define EDGE_MINB_H4_FWD 5
+#endif
+#ifndef EDGE_MINB_H4_BWD
+#define EDGE_MINB_H4_BWD 4
+#endif
 
 template <typename T, int H, int CV>
 struct RowBuf {
@@ -140,7 +148,7 @@ __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float 
 }
 
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? 4 : 2)) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? EDGE_MINB_H4_FWD : 2)) edge_fwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const int4* __restrict__ sched,
                                                                 const int32_t* __restrict__ col,
                                                                 const int32_t* __restrict__ perm, int n_rows, int row_offset,
@@ -377,23 +385,22 @@ __global__ void __launch_bounds__(256) node_prep_kernel(const float* __restrict_
 }
 
 // out[c] = sum over parts; 8 interleaved stripes per column, combined in a fixed order
-__global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out) {
-  __shared__ float red[8][128];
-  const int lc = threadIdx.x & 127, stripe = threadIdx.x >> 7;
-  for (int c0 = 0; c0 < C; c0 += 128) {
-    const int c = c0 + lc;
-    float a = 0.f;
-    if (c < C)
-      for (int k = stripe; k < n_parts; k += 8) a += part[(size_t)k * C + c];
-    red[stripe][lc] = a;
-    __syncthreads();
-    if (stripe == 0 && c < C) {
-      float t = red[0][lc];
+// out[c] = sum_k part[k, c] in a fixed order: 8 stripes of partial rows, then the stripes in order.  One block per 32 columns
+// (a single 1024-thread block took 34 us for 1184 partial rows).
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int lc = threadIdx.x & 31, stripe = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lc;
+  float a = 0.f;
+  if (c < C)
+    for (int k = stripe; k < n_parts; k += 8) a += part[(size_t)k * C + c];
+  red[stripe][lc] = a;
+  __syncthreads();
+  if (stripe == 0 && c < C) {
+    float t = red[0][lc];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) t += red[w][lc];
-      out[c] = t;
-    }
-    __syncthreads();
+    for (int w = 1; w < 8; ++w) t += red[w][lc];
+    out[c] = t;
   }
 }
 
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
 template <typename T, int POLICY, int H, int CV, bool DROPOUT>
-__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? 4 : 2)) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
+__global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? EDGE_MINB_H4_BWD : 2)) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const T* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
                                                                 const int4* __restrict__ sched,
@@ -1101,7 +1108,7 @@ extern "C" int b200gat_node_prep_f32(const float* dout, const float* out_heads, 
                                                                    (int)row_offset, (float4*)nodestat,
                                                                    dbias ? (float*)workspace : nullptr, (__nv_bfloat16*)dout_bf16);
   })
-  if (dbias) count_launch(), colsum_finish_kernel<<<1, 1024, 0, st>>>((const float*)workspace, grid, channels, dbias);
+  if (dbias) count_launch(), colsum_finish_kernel<<<ceil_div(channels, 32), 256, 0, st>>>((const float*)workspace, grid, channels, dbias);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -8,7 +8,9 @@ nu, ni, n_inter, k = synth.CONFIGS["amazon"]
 ei, feats = synth.make_graph(nu, ni, n_inter, k)
 eid, fd = ei.to(dev), feats.to(dev)
 u, i, j = (t.to(dev) for t in synth.make_triples(nu, ni, 200000))
-for name, dt, loss_fn in (("h4 f32 bpr", torch.float32, b200gat.bpr_loss), ("h4 bf16 bpr", torch.bfloat16, b200gat.bpr_loss), ("h4 bf16 bce", torch.bfloat16, b200gat.bce_loss)):
+cases = (("h4 f32 bpr", torch.float32, b200gat.bpr_loss), ("h4 bf16 bpr", torch.bfloat16, b200gat.bpr_loss), ("h4 bf16 bce", torch.bfloat16, b200gat.bce_loss))
+only = os.environ.get("CASES")
+for name, dt, loss_fn in [c for c in cases if not only or c[0] in only.split(",")]:
     torch.manual_seed(42)
     m = b200gat.PyGGAT(nu, ni, 128, 128, 2, heads=4, attn_dropout=0.1, feature_dtype=dt).to(dev).train()
     opt = b200gat.Adam(m.parameters(), lr=1e-3, weight_decay=1e-4)

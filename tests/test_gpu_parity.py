@@ -105,7 +105,10 @@ def _custom_inputs(n, e, c, seed, scale, hub=None):
 
 
 @pytest.mark.parametrize("n,e,scale,hub,flip", [(200, 3000, 1.0, None, False), (150, 2500, 12.0, 7, False), (40, 20, 1.0, None, False),
-                                               (2000, 60000, 3.0, 5, False), (2000, 60000, 3.0, 5, True)])
+                                               (2000, 60000, 3.0, 5, False), (2000, 60000, 3.0, 5, True),
+                                               # empty / tiny / odd row counts (the last warp of the half-warp kernels is ragged)
+                                               (1, 0, 1.0, None, False), (1, 3, 1.0, None, False), (3, 2, 1.0, None, False),
+                                               (17, 16, 1.0, None, False), (33, 700, 1.0, None, False), (129, 1, 1.0, None, True)])
 def test_custom_layer_forward_backward(dev, n, e, scale, hub, flip):
     import b200gat
     c = 128
@@ -127,15 +130,19 @@ def test_custom_layer_forward_backward(dev, n, e, scale, hub, flip):
     y = layer(xd, eid)
     (y * gy.to(dev)).sum().backward()
     got = [y, xd.grad, layer.lin.weight.grad, layer.a_src.grad, layer.a_dst.grad]
+    # gradients that are exactly zero in exact arithmetic (one destination with equal logits: alpha does not depend on the
+    # attention vectors) have no scale of their own; they are judged on the scale of the quantities they are sums of
+    floor = 1e-6 * ref[torch.float64][0].abs().max().item() * gy.abs().max().item() if e else 0.0
     for name, gt, r32, r64 in zip(["out", "dx", "dW", "da_src", "da_dst"], got, ref[torch.float32], ref[torch.float64]):
         err_ours = (gt.detach().cpu().double() - r64).abs().max().item()
         err_ref = (r32.double() - r64).abs().max().item()
         scale_ = r64.abs().max().item()
         # as close to the fp64 truth as the reference's own fp32 arithmetic (x4 slack), or within rtol 1e-5 of it
-        assert err_ours <= max(4 * err_ref, RTOL * scale_), (name, err_ours, err_ref, scale_)
-        close(gt, r64, rtol=2e-5, name=name)
+        assert err_ours <= max(4 * err_ref, RTOL * scale_, floor), (name, err_ours, err_ref, scale_)
+        if scale_ > 100 * floor:
+            close(gt, r64, rtol=2e-5, name=name)
     # rows without in-edges are exactly zero (reference: zeros_like + index_add_)
-    if not flip:
+    if not flip and n > 3:
         assert torch.count_nonzero(y[-3:]) == 0
 
 

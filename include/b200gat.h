@@ -233,6 +233,19 @@ int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim, int k, fl
                            float* nbr_sim, int32_t* counts, int32_t* n_unsafe, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* ---- multi-GPU exchange over peer memory (the reference itself is single-GPU) -------------
+ * The row-sharded path all-gathers a layer's rows once per layer and direction.  Instead of a collective kernel, every
+ * rank keeps its block in a buffer from b200gat_peer_alloc, exports it (64-byte CUDA IPC handle, exchanged by the host
+ * code), opens its peers' buffers once, and per exchange PULLS each peer's block with b200gat_peer_pull (copy engine over
+ * NVLink; one stream per peer).  The host code orders producers and pulls with a stream-ordered barrier. */
+#define B200GAT_PEER_HANDLE_BYTES 64
+int b200gat_peer_alloc(size_t bytes, void** ptr /*host out*/);
+int b200gat_peer_free(void* ptr);
+int b200gat_peer_export(const void* ptr, void* handle /*host, >= 64 bytes*/, size_t handle_bytes);
+int b200gat_peer_open(const void* handle /*host*/, void** ptr /*host out: the peer's buffer, mapped here*/);
+int b200gat_peer_close(void* ptr);
+int b200gat_peer_pull(void* dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

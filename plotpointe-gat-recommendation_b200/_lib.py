@@ -65,6 +65,12 @@ _SIGS = {
                                           c_size_t, _P]),
     "b200gat_rank_loss_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, c_int64, _P, c_int, _P, _P, c_int64,
                                           c_int64, _P, _P, _P, c_size_t, _P]),
+    "b200gat_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "b200gat_peer_free": (c_int, [_P]),
+    "b200gat_peer_export": (c_int, [_P, _P, c_size_t]),
+    "b200gat_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
+    "b200gat_peer_close": (c_int, [_P]),
+    "b200gat_peer_pull": (c_int, [_P, _P, c_size_t, _P]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

@@ -11,8 +11,9 @@ forward (CSR slice) and their source rows in the backward (CSC slice).  Per laye
   loss    : all-gather of the last layer's rows; every rank evaluates the (tiny) triple set and keeps the gradient
             rows of its own block.
 
-The collectives go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the
-single-GPU path.  The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which
+The row exchanges pull the peers' blocks out of peer memory with the copy engines (``PeerExchange``, b200gat_peer_* in
+include/b200gat.h; set B200GAT_PEER=0 or run where CUDA IPC is unavailable to fall back to NCCL all-gathers); the small
+reductions go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the single-GPU path.  The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which
 is how the gloo tests exercise it.
 """
 from __future__ import annotations
@@ -20,6 +21,7 @@ from __future__ import annotations
 import json
 import os
 import statistics
+import sys
 import time
 from dataclasses import dataclass
 from typing import List, Optional
@@ -90,6 +92,95 @@ def all_gather_rows(local: torch.Tensor, world: int) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------------ peer exchange
+class _RawCuda:
+    """A raw device allocation seen through __cuda_array_interface__ (so torch can wrap it without copying)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerExchange:
+    """All-gather of the ranks' row blocks by pulling them out of peer memory (b200gat_peer_*, include/b200gat.h).
+
+    ``n_buffers`` persistent buffers of ``buffer_bytes`` per rank, one per exchange point of a step; every rank maps all its
+    peers' buffers once (CUDA IPC).  ``gather(b, parts)`` = stream-ordered barrier (one-element all-reduce: when it completes
+    on this rank's stream, every rank's producer kernels ordered before its own barrier have finished), then one copy-engine
+    pull per peer and part on a side stream per peer, then the current stream waits for the pulls.  A buffer is written again
+    one step later; the barriers of the other exchange points in between order that write after every peer's pulls."""
+
+    def __init__(self, lib, world: int, rank: int, dev: torch.device, buffer_bytes: int, n_buffers: int):
+        import ctypes
+        self.lib, self.world, self.rank, self.dev = lib, world, rank, dev
+        self.nbytes = (buffer_bytes + 255) // 256 * 256
+        self.local_ptr, self.local, handles = [], [], []
+        for _ in range(n_buffers):
+            p = ctypes.c_void_p()
+            lib._check(lib._lib.b200gat_peer_alloc(self.nbytes, ctypes.byref(p)), "peer_alloc")
+            h = ctypes.create_string_buffer(64)
+            lib._check(lib._lib.b200gat_peer_export(p, h, 64), "peer_export")
+            self.local_ptr.append(p.value)
+            self.local.append(torch.as_tensor(_RawCuda(p.value, self.nbytes), device=dev))
+            handles.append(h.raw)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self.peer_ptr = []                                   # [rank][buffer] -> device address valid on THIS rank
+        for r in range(world):
+            if r == rank:
+                self.peer_ptr.append(list(self.local_ptr))
+                continue
+            ptrs = []
+            for raw in gathered[r]:
+                q = ctypes.c_void_p()
+                lib._check(lib._lib.b200gat_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)), "peer_open")
+                ptrs.append(q.value)
+            self.peer_ptr.append(ptrs)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.streams = [torch.cuda.Stream(dev) for _ in range(world - 1)]
+        self.order = [(rank + k) % world for k in range(1, world)]       # every rank starts with a different peer
+
+    def view(self, b: int, offset: int, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        assert offset % 16 == 0 and offset + nbytes <= self.nbytes
+        return self.local[b][offset:offset + nbytes].view(dtype).view(shape)
+
+    def gather(self, b: int, parts) -> list:
+        """parts: [(offset, shape_of_one_block, dtype)] -> gathered tensors [(world * rows, ...)]."""
+        import ctypes
+        lib = self.lib
+        dist.all_reduce(self.flag)                           # barrier on the current stream (see class docstring)
+        outs, jobs = [], []
+        for offset, shape, dtype in parts:
+            out = torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=self.dev)
+            blk = out[:shape[0]].numel() * out.element_size()
+            outs.append(out)
+            jobs.append((offset, blk, out.data_ptr()))
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for st, r in zip(self.streams, self.order):
+            st.wait_event(ev)
+            for offset, blk, dst in jobs:
+                lib._check(lib._lib.b200gat_peer_pull(ctypes.c_void_p(dst + r * blk), ctypes.c_void_p(self.peer_ptr[r][b] + offset),
+                                                     blk, ctypes.c_void_p(st.cuda_stream)), "peer_pull")
+        for offset, blk, dst in jobs:                         # own block: a local copy on the current stream
+            lib._check(lib._lib.b200gat_peer_pull(ctypes.c_void_p(dst + self.rank * blk), ctypes.c_void_p(self.local_ptr[b] + offset),
+                                                 blk, ctypes.c_void_p(cur.cuda_stream)), "peer_pull")
+        for st in self.streams:
+            cur.wait_stream(st)
+        return outs
+
+    def close(self) -> None:
+        for r in range(self.world):
+            if r != self.rank:
+                for q in self.peer_ptr[r]:
+                    self.lib._lib.b200gat_peer_close(q)
+        self.peer_ptr = []
+
+
 # ------------------------------------------------------------------------------------------------------ trainer
 class ShardedGAT:
     """Manual forward/backward of the 2-model family (custom / PyG dialect) over a row-sharded graph.
@@ -158,6 +249,22 @@ class ShardedGAT:
             self.a_dst.append(P(a_d.detach().clone().to(self.dev).view(self.heads, hidden)))
             self.bias.append(None if kind == "custom" else P(lay.bias.detach().clone().to(self.dev)))
         del full
+        # exchange over peer memory (copy-engine pulls) when the ranks can map each other's buffers; NCCL all-gathers otherwise
+        self.px = None
+        H_, C_ = self.heads, hidden
+        self._offB = (self.n_max * max(H_ * C_, C_) * 4 + 255) // 256 * 256       # part A: h or dout rows, part B: s or nodestat
+        if self.world > 1 and os.environ.get("B200GAT_PEER", "1") != "0":
+            ok = torch.ones(1, device=self.dev)
+            try:
+                self.px = PeerExchange(_lib, self.world, self.rank, self.dev, self._offB + self.n_max * 4 * H_ * 4, 2 * layers + 1)
+            except Exception as exc:      # noqa: BLE001  (no IPC in this sandbox, no peer access, ...)
+                ok.zero_()
+                self.px = None
+                if self.rank == 0:
+                    print(f"b200gat.sharded: peer exchange unavailable ({exc}); using NCCL all-gathers", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks or none
+            if ok.item() == 0:
+                self.px = None
         self.replicated = list(self.item_proj.parameters()) + self.W + self.a_src + self.a_dst + [b for b in self.bias if b is not None]
         self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay, fused=True)
         self.step_no = 0
@@ -188,14 +295,23 @@ class ShardedGAT:
         p = self.p_drop if self.training else 0.0
         for l in range(self.n_layers):
             f_in = x.shape[1]
-            h_loc, s_loc = self._rows(H * C, dtype=torch.bfloat16 if self.bf16 else torch.float32), self._rows(2 * H)
+            h_dt = torch.bfloat16 if self.bf16 else torch.float32
+            if self.px is not None:
+                h_loc = self.px.view(l, 0, (self.n_max, H * C), h_dt)
+                s_loc = self.px.view(l, self._offB, (self.n_max, 2 * H), torch.float32)
+            else:
+                h_loc, s_loc = self._rows(H * C, dtype=h_dt), self._rows(2 * H)
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), lib.ptr(dws), dwb, st)
-            h_full = all_gather_rows(h_loc, self.world)
-            s_full = all_gather_rows(s_loc, self.world)
-            out = self._rows(C)
+            if self.px is not None:
+                h_full, s_full = self.px.gather(l, [(0, (self.n_max, H * C), h_dt), (self._offB, (self.n_max, 2 * H), torch.float32)])
+            else:
+                h_full = all_gather_rows(h_loc, self.world)
+                s_full = all_gather_rows(s_loc, self.world)
+            last = l == self.n_layers - 1
+            out = self.px.view(self.n_layers, 0, (self.n_max, C), torch.float32) if (self.px is not None and last) else self._rows(C)
             rowstat = self._empty(self.n_loc, H, 2)
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
@@ -211,7 +327,11 @@ class ShardedGAT:
     def loss_and_backward(self, z_loc: torch.Tensor, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
         lib, H, C = self._lib, self.heads, self.hidden
         st = lib.stream()
-        z_full = all_gather_rows(z_loc, self.world)
+        L_ = self.n_layers
+        if self.px is not None and z_loc.data_ptr() == self.px.local_ptr[L_]:
+            z_full = self.px.gather(L_, [(0, (self.n_max, C), torch.float32)])[0]
+        else:
+            z_full = all_gather_rows(z_loc, self.world)
         s_tr = int(u.shape[0])
         ws_bytes = lib.loss_workspace_bytes(self.n, s_tr)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
@@ -239,17 +359,29 @@ class ShardedGAT:
         for l in reversed(range(self.n_layers)):
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
             f_in = x.shape[1]
-            nodestat = self._rows(H, 4)
+            bx = L_ + 1 + l                                        # this layer's backward exchange buffer
+            nodestat = self.px.view(bx, self._offB, (self.n_max, H, 4), torch.float32) if self.px is not None else self._rows(H, 4)
             dwb = lib.dense_workspace_bytes(H, C, f_in)
             dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
             have_full = pre_gathered is not None and l == self.n_layers - 1
-            dout_g = self._rows(C, dtype=torch.bfloat16) if (self.bf16 and not have_full) else None
+            dout_g = None
+            if self.bf16 and not have_full:
+                dout_g = (self.px.view(bx, 0, (self.n_max, C), torch.bfloat16) if self.px is not None
+                          else self._rows(C, dtype=torch.bfloat16))
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
                      lib.ptr(dout_g), lib.ptr(dws), dwb, st)
-            dout_full = pre_gathered if have_full else all_gather_rows(dout_g if self.bf16 else dout, self.world)
-            nodestat_full = all_gather_rows(nodestat, self.world)
+            if self.px is not None:
+                parts = [] if have_full else [(0, (self.n_max, C), torch.bfloat16 if self.bf16 else torch.float32)]
+                if not have_full and not self.bf16:
+                    assert dout.data_ptr() == self.px.local_ptr[bx], "fp32 dout of an inner layer must live in its exchange buffer"
+                got = self.px.gather(bx, parts + [(self._offB, (self.n_max, H, 4), torch.float32)])
+                dout_full = pre_gathered if have_full else got[0]
+                nodestat_full = got[-1]
+            else:
+                dout_full = pre_gathered if have_full else all_gather_rows(dout_g if self.bf16 else dout, self.world)
+                nodestat_full = all_gather_rows(nodestat, self.world)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
@@ -267,7 +399,11 @@ class ShardedGAT:
                 dist.all_reduce(ds_dst)
             ds[:, H:] = ds_dst[self.plan.lo:self.plan.lo + self.n_loc]
             del de, dout_full, nodestat_full
-            dx = self._rows(f_in)
+            # dx of layer l is the dout of layer l-1: in the fp32 tier it is produced straight into that layer's exchange buffer
+            if self.px is not None and l >= 1 and not self.bf16:
+                dx = self.px.view(L_ + l, 0, (self.n_max, f_in), torch.float32)
+            else:
+                dx = self._rows(f_in)
             dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
             lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
                      lib.ptr(dh), lib.ptr(ds), self.n_loc, f_in, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
@@ -361,7 +497,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
             "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{B.LAYERS}, d={B.HIDDEN}, heads={B.HEADS}, BPR on "
                                    f"{B.S_TRIPLES} triples, train mode, Adam step; {e} edges", "n_nodes": nu + ni, "n_edges": e,
-                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs (round-robin node blocks), NCCL all-gather per layer",
+                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs (round-robin node blocks), row exchange per layer: "
+                                                       + ("copy-engine pulls from peer memory" if tr.px is not None else "NCCL all-gather"),
                        "rows_per_rank": tr.n_loc,
                        "l2": "per-step working set exceeds the 126 MB L2"},
             "e2e": {"value": e * B.LAYERS / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,

@@ -85,7 +85,7 @@ def main(kind):
     close(lb, lmb, "loss bf16", 1e-5)
     close(trb.W[0].grad, (mb.layers if kind == "custom" else mb.convs)[0].lin.weight.grad, "dW0 bf16", 1e-3)
     if rank == 0:
-        print("SHARDED_OK", float(loss), float(l_train))
+        print("SHARDED_OK", float(loss), float(l_train), "exchange=" + ("peer" if tr.px is not None else "nccl"))
 
 
 if __name__ == "__main__":

@@ -21,6 +21,11 @@ def main():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); r = orig(local_t, w); b.record(); coll.append(("all_gather_rows", a, b)); return r
     sharded.all_gather_rows = timed_gather
+    orig_pg = sharded.PeerExchange.gather
+    def timed_pg(self_, b_, parts_):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r = orig_pg(self_, b_, parts_); b.record(); coll.append(("peer_gather", a, b)); return r
+    sharded.PeerExchange.gather = timed_pg
     orig_ar = dist.all_reduce
     def timed_ar(t, *a_, **k_):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,7 +44,7 @@ def main():
     agg = {}
     for name, a, b in coll: agg[name] = agg.get(name, 0.0) + a.elapsed_time(b) / steps
     res.update({k_: round(v, 3) for k_, v in agg.items()})
-    res["kernels+coll"] = round(sum(v for k_, v in res.items() if k_.startswith("b200gat_") or k_ in ("all_gather_rows", "all_reduce")), 3)
+    res["kernels+coll"] = round(sum(v for k_, v in res.items() if k_.startswith("b200gat_") or k_ in ("all_gather_rows", "all_reduce", "peer_gather")), 3)
     print(json.dumps(res), flush=True)
     if world > 1: dist.barrier(); dist.destroy_process_group()
 main()

@@ -12,7 +12,8 @@ forward (CSR slice) and their source rows in the backward (CSC slice).  Per laye
             rows of its own block.
 
 The row exchanges pull the peers' blocks out of peer memory with the copy engines (``PeerExchange``, b200gat_peer_* in
-include/b200gat.h; set B200GAT_PEER=0 or run where CUDA IPC is unavailable to fall back to NCCL all-gathers); the small
+include/b200gat.h) when that is the faster path -- 2 ranks by default, B200GAT_PEER=1 forces it, =0 or a box without CUDA IPC
+uses NCCL all-gathers, which is also the default beyond 2 ranks (measured, see ShardedGAT.__init__); the small
 reductions go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the single-GPU path.  The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which
 is how the gloo tests exercise it.
 """
@@ -253,7 +254,11 @@ class ShardedGAT:
         self.px = None
         H_, C_ = self.heads, hidden
         self._offB = (self.n_max * max(H_ * C_, C_) * 4 + 255) // 256 * 256       # part A: h or dout rows, part B: s or nodestat
-        if self.world > 1 and os.environ.get("B200GAT_PEER", "1") != "0":
+        # Measured (config 2, fp32): 2 GPUs: exchange 1.22 ms per step with pulls vs 1.86 ms with NCCL; 8 GPUs: 3.6 ms vs 2.4 ms
+        # (seven concurrent copy-engine streams per GPU do not add up to the NVLink rate).  So: pulls for 2 ranks, NCCL beyond,
+        # unless B200GAT_PEER=1 / 0 forces one of them.
+        mode = os.environ.get("B200GAT_PEER", "auto")
+        if self.world > 1 and (mode == "1" or (mode == "auto" and self.world <= 2)):
             ok = torch.ones(1, device=self.dev)
             try:
                 self.px = PeerExchange(_lib, self.world, self.rank, self.dev, self._offB + self.n_max * 4 * H_ * 4, 2 * layers + 1)

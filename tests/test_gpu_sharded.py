@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("kind,peer", [("custom", "1"), ("pyg", "1"), ("pyg", "0")])
+@pytest.mark.parametrize("kind,peer", [("custom", "1"), ("pyg", "1"), ("pyg", "0"), ("custom", "auto")])
 def test_sharded_matches_single_gpu(kind, peer):
     """peer = "1": row exchanges pull from peer memory (b200gat_peer_*); "0": NCCL all-gathers."""
     if torch.cuda.device_count() < 2:
@@ -21,7 +21,7 @@ def test_sharded_matches_single_gpu(kind, peer):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_OK" in r.stdout
     # a box without CUDA IPC between the two processes falls back to NCCL and says so on stderr
-    assert ("exchange=peer" if peer == "1" else "exchange=nccl") in r.stdout or "peer exchange unavailable" in r.stderr, \
+    assert ("exchange=nccl" if peer == "0" else "exchange=peer") in r.stdout or "peer exchange unavailable" in r.stderr, \
         r.stdout[-2000:] + r.stderr[-2000:]
 
 

@@ -1,21 +1,24 @@
 // Fused GAT edge kernels: one forward launch and one backward (CSC) launch per layer.
 //
 // Forward  (replaces scripts/train_gat_custom.py:79-92 and the PyG GATConv message passing called
-//          at scripts/train_gat_pyg.py:87): warp per destination row over the CSR built in
+//          at scripts/train_gat_pyg.py:87): one lane group per destination row over the CSR built in
 //          graph.cu; logits from the per-node scalars s_src/s_dst; LeakyReLU; segment softmax with
-//          warp shuffles (custom dialect: clamp[-10,10], no max, +1e-9; PyG dialect: online max,
+//          shuffles (custom dialect: clamp[-10,10], no max, +1e-9; PyG dialect: online max,
 //          +1e-16); 128-bit gathers of h[src]; weighted aggregation; head mean + bias.  No E-sized
 //          float tensor is ever written.
-// Backward (replaces autograd's replay of the same lines, train_gat_custom.py:361): warp per SOURCE
-//          row over the CSC; gathers dout[dst] once per edge, recomputes alpha from per-node
+// Backward (replaces autograd's replay of the same lines, train_gat_custom.py:361): one lane group per
+//          SOURCE row over the CSC; gathers dout[dst] once per edge, recomputes alpha from per-node
 //          scalars, accumulates dh[src] in registers (no atomics), emits the logit gradient
 //          de per edge (E*H floats, the only E-sized scratch) and ds_src; a scalar CSR pass then
 //          reduces de per destination into ds_dst.
 //
-// Row width is H*C elements with C a multiple of 128 (lane l owns channels [4l,4l+4) of every
-// 128-wide chunk), H in {1,2,4}; the gathered matrix is fp32 or bf16 (template parameter T),
-// accumulation is always fp32.  Rows come from a descending-degree schedule; rows longer than
-// 128 edges arrive as segments whose partial states a small combine kernel merges in order.
+// Two kernel families, both templated on the gathered dtype T (fp32 or bf16 rows; accumulation is always fp32):
+//   * H*C == 128 (the headline shape): edge_fwd16_kernel / edge_bwd16_kernel, HALF a warp per row, a lane owns
+//     channels [4 sl, 4 sl + 4) and [64 + 4 sl, 64 + 4 sl + 4) -- see the comment above them;
+//   * any H in {1,2,4} x C in {128,256}: edge_fwd_kernel / edge_bwd_kernel, a warp per row, lane l owns channels
+//     [4l, 4l+4) of every 128-wide chunk and head.
+// Rows come from a descending-degree schedule; rows longer than 128 edges arrive as segments whose partial states a
+// small combine kernel merges in order.
 #include <cuda_bf16.h>
 
 #include "common.cuh"

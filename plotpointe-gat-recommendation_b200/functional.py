@@ -1,8 +1,6 @@
 """torch.autograd ops over the C ABI: one GAT layer (both dialects) and the ranking loss."""
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 
 from . import _lib

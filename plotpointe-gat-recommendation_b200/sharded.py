@@ -25,7 +25,7 @@ import statistics
 import sys
 import time
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -1,7 +1,6 @@
 """The callers either side of the hot path: the optimizer step and the sampled evaluator."""
 from __future__ import annotations
 
-import math
 from typing import Dict, Iterable, Sequence
 
 import torch

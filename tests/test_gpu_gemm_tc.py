@@ -1,5 +1,4 @@
 """GPU: the tcgen05 (3xTF32) projection kernels against fp64 truth and against the CUDA-core fp32 kernels."""
-import numpy as np
 import pytest
 import torch
 

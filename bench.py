@@ -12,6 +12,7 @@ copied from pinned host memory and the loss is read back inside the timed region
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -41,14 +42,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md).
+
+    nvidia-smi needs ~0.2 s before its first line, longer than a short timed region, so it is started before the warm-up
+    (`start`) and keeps streaming one timestamped line every 20 ms; `begin` / `end` mark the timed region on the host
+    clock and `stop` keeps the samples whose timestamps fall inside it.  If the region was too short to catch one, the
+    samples of the end-to-end loop that follows (same load) are used and `window` says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -58,30 +65,45 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t_begin = datetime.datetime.now()
+
+    def end(self):
+        self.t_end = datetime.datetime.now()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_stop = datetime.datetime.now()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[2]), float(f[3]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+        t0 = self.t_begin or t_stop
+        t1 = self.t_end or t_stop
+        sel, window = [r for r in rows if t0 <= r[0] <= t1], "timed region"
+        if not sel:
+            sel, window = [r for r in rows if t0 <= r[0] <= t_stop], "timed region + end-to-end loop (timed region shorter than one sample)"
+        sm, mx, reasons = [r[1] for r in sel], [r[2] for r in sel], set()
+        for r in sel:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def algorithmic_bytes(n, e, h, c, dropout, row_bytes=4):
@@ -136,22 +158,24 @@ def run_ours(args):
     b200gat.graph_for(eid, n)
     torch.cuda.synchronize()
     graph_build_ms = (time.time() - t0) * 1e3
+    sampler = ClockSampler(local)
+    sampler.start()                       # streams from here on; only the samples inside the timed region are kept
     for _ in range(args.warmup):
         step(du, di, dj)
     torch.cuda.synchronize()
 
     # ---- device-resident timed region ----------------------------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count()
     _lib.timing = {}
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     torch.cuda.synchronize()
+    sampler.begin()
     ev[0].record()
     for _ in range(args.steps):
         loss = step(du, di, dj)
     ev[1].record()
     torch.cuda.synchronize()
+    sampler.end()
     timing, _lib.timing = _lib.timing, None
     launches = _lib.launch_count() - launches0
     ms_step = ev[0].elapsed_time(ev[1]) / args.steps

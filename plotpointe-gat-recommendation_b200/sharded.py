@@ -465,20 +465,22 @@ def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
-    for _ in range(args.warmup):
-        tr.train_step(du, di, dj)
     sampler = B.ClockSampler(dev.index)
     if rank == 0:
-        sampler.start()
+        sampler.start()                   # streams from here on; only the samples inside the timed region are kept
+    for _ in range(args.warmup):
+        tr.train_step(du, di, dj)
     launches0 = _lib.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     dist.barrier()
     torch.cuda.synchronize()
+    sampler.begin()
     ev[0].record()
     for _ in range(args.steps):
         loss = tr.train_step(du, di, dj)
     ev[1].record()
     torch.cuda.synchronize()
+    sampler.end()
     dist.barrier()
     ms = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -97,3 +97,19 @@ def build_edge_index(n_users: int, n_items: int, train_pos_idx) -> torch.Tensor:
     out[0, 0::2], out[1, 0::2] = uu, items
     out[0, 1::2], out[1, 1::2] = items, uu
     return torch.from_numpy(out)
+
+
+def union_edge_index(ui_edge_index: torch.Tensor, n_users: int, ii_rows: torch.Tensor, ii_cols: torch.Tensor) -> torch.Tensor:
+    """The graph the hot path runs on (BASELINE.json north_star): the User-Item block of ``build_edge_index`` followed by the
+    directed Item-Item kNN block.  ``ii_rows`` / ``ii_cols`` are the COO of graphs/build_ii_knn.py:103-111 (row = item,
+    col = neighbour, item ids), i.e. what ``b200gat.build_ii_knn`` returns or ``scipy.sparse.load_npz(ii_edges_*.npz)``
+    holds; the edge for a COO entry is ``n_users + row -> n_users + col``, appended after the U-I block in COO order (the
+    reference never defines this union; SURVEY.md section 8d records the decision).  int64 [2, E] on ``ui_edge_index``'s
+    device; duplicates are kept, nothing is sorted."""
+    if ui_edge_index.dim() != 2 or ui_edge_index.shape[0] != 2:
+        raise ValueError(f"ui_edge_index must be [2, E], got {tuple(ui_edge_index.shape)}")
+    if ii_rows.shape != ii_cols.shape or ii_rows.dim() != 1:
+        raise ValueError("ii_rows and ii_cols must be 1-D tensors of equal length")
+    dev = ui_edge_index.device
+    ii = torch.stack([ii_rows.to(device=dev, dtype=torch.int64), ii_cols.to(device=dev, dtype=torch.int64)]) + n_users
+    return torch.cat([ui_edge_index.to(torch.int64), ii], dim=1).contiguous()

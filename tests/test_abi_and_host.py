@@ -115,3 +115,27 @@ def test_synthetic_graph_shape():
     nb = ii[1].view(ni, k)
     assert all(len(set(r.tolist())) == k for r in nb)
     np.testing.assert_allclose(feats.norm(dim=1).numpy(), 1.0, rtol=1e-5)
+
+
+def test_union_edge_index_appends_the_knn_block_in_coo_order(golden_dir):
+    """U-I block first, then n_users + row -> n_users + col for every kNN COO entry, nothing sorted or de-duplicated
+    (SURVEY.md 8d); the kNN COO is the reference script's own output (tests/golden/knn_128.npz)."""
+    import b200gat
+    g = np.load(os.path.join(golden_dir, "knn_128.npz"))
+    rows, cols = torch.from_numpy(g["rows"]), torch.from_numpy(g["cols"])
+    n_items = int(g["embeddings"].shape[0])
+    nu = 7
+    tp = {u: np.array([(3 * u + j) % n_items for j in range(u % 3 + 1)]) for u in range(nu)}
+    ui = b200gat.build_edge_index(nu, n_items, tp)
+    ei = b200gat.union_edge_index(ui, nu, rows, cols)
+    assert ei.dtype == torch.int64 and ei.shape == (2, ui.shape[1] + rows.numel())
+    assert torch.equal(ei[:, :ui.shape[1]], ui)
+    assert torch.equal(ei[0, ui.shape[1]:], rows.long() + nu) and torch.equal(ei[1, ui.shape[1]:], cols.long() + nu)
+    # same edges as the oracle's CSR sees them: in-degree of item i = #interactions + #times it is somebody's neighbour
+    deg = torch.bincount(ei[1], minlength=nu + n_items)
+    expect = torch.bincount(cols.long() + nu, minlength=nu + n_items) + torch.bincount(ui[1], minlength=nu + n_items)
+    assert torch.equal(deg, expect)
+    with pytest.raises(ValueError):
+        b200gat.union_edge_index(ui.t(), nu, rows, cols)
+    with pytest.raises(ValueError):
+        b200gat.union_edge_index(ui, nu, rows, cols[:-1])

@@ -139,3 +139,25 @@ def test_union_edge_index_appends_the_knn_block_in_coo_order(golden_dir):
         b200gat.union_edge_index(ui.t(), nu, rows, cols)
     with pytest.raises(ValueError):
         b200gat.union_edge_index(ui, nu, rows, cols[:-1])
+
+
+def test_ranking_metrics_host_logic_matches_reference_metrics(golden_dir):
+    """b200gat.ranking_metrics is plain torch: on the ranks of the reference's own eval_sampled run (golden fixture, same
+    numpy seed) it must return the reference's Recall/NDCG; empty input gives zeros (scripts/train_gat_custom.py:206-210)."""
+    import b200gat
+    from oracle import gat_oracle as O
+    g = dict(np.load(os.path.join(golden_dir, "eval_sampled.npz")))
+    nu, ni, neg_k = int(g["n_users"]), int(g["n_items"]), int(g["neg_k"])
+    train_pos = {}
+    for u, it in zip(g["train_users"], g["train_items"]):
+        train_pos.setdefault(int(u), []).append(int(it))
+    train_pos = {u: np.array(v) for u, v in train_pos.items()}
+    eval_pos = {int(u): int(i) for u, i in zip(g["eval_users"], g["eval_items"])}
+    np.random.seed(int(g["np_seed"]))
+    users, cands = O.sample_eval_candidates(train_pos, eval_pos, ni, neg_k)
+    ranks, _ = O.eval_ranks(torch.from_numpy(g["z"]), nu, users, cands)
+    m = b200gat.ranking_metrics(ranks.to(torch.int32))
+    for k in ("recall@10", "recall@20", "ndcg@10", "ndcg@20"):
+        assert abs(m[k] - float(g["metric:" + k])) < 1e-12, (k, m[k])
+    assert b200gat.ranking_metrics(torch.zeros(0, dtype=torch.int32)) == {"recall@10": 0.0, "recall@20": 0.0, "ndcg@10": 0.0,
+                                                                          "ndcg@20": 0.0}

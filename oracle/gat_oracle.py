@@ -16,9 +16,12 @@ Pinning status
   package, which the reference installs un-pinned (docker/Dockerfile:21-23) and which is absent
   from /root/reference and from this image.  It is restated from the published semantics of
   ``torch_geometric.nn.GATConv`` (2.6.x at the date of the reference's runs) for the one call the
-  reference makes (scripts/train_gat_pyg.py:77,87).  PARITY UNPINNED for this dialect: the only
-  anchor is the cross-check against the pinned custom dialect on inputs where both coincide
-  (``tests/test_oracle_golden.py::test_gatconv_matches_custom_when_unclamped``).
+  reference makes (scripts/train_gat_pyg.py:77,87).  PARITY UNPINNED for this dialect (no reference-held vector can
+  exist here).  Two independent anchors stand in for one: (1) the cross-check against the pinned custom dialect on inputs
+  where both coincide (``tests/test_oracle_golden.py::test_gatconv_matches_custom_when_unclamped``); (2)
+  ``gatconv_dense``, the textbook dense-adjacency masked-softmax statement of the same layer, checked against ``gatconv``
+  in fp64 (output and every gradient) for heads 1/2/4, non-zero bias, parallel edges, rows without in-edges and logits far
+  outside [-10, 10] (``test_gatconv_matches_dense_formulation``).
 * ``eval_ranks`` / ``ranking_metrics`` / ``sample_eval_candidates`` (next row f2): PINNED.  ``make_golden.py`` runs
   the reference's own ``eval_sampled`` (scripts/train_gat_custom.py:184-210) under a fixed numpy seed and stores its
   metrics; the test replays the same numpy stream through ``sample_eval_candidates`` and must reproduce them.
@@ -126,13 +129,18 @@ def node_features(user_emb: torch.Tensor, item_proj_w: torch.Tensor, item_proj_b
 
 
 def custom_gat_forward(state: Dict[str, torch.Tensor], item_feats: torch.Tensor,
-                       edge_index: torch.Tensor) -> torch.Tensor:
-    """CustomGAT.forward (train_gat_custom.py:111-115) over a reference-named state dict."""
+                       edge_index: torch.Tensor, p_drop: float = 0.0,
+                       generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """CustomGAT.forward (train_gat_custom.py:111-115) over a reference-named state dict.  ``p_drop > 0`` is train
+    mode: a fresh keep mask per layer, as ``self.drop(alpha)`` (:89) draws one."""
     x = node_features(state["user_emb.weight"], state["item_proj.weight"], state["item_proj.bias"], item_feats)
     layer = 0
     while f"layers.{layer}.lin.weight" in state:
+        keep = None
+        if p_drop > 0.0:
+            keep = torch.rand(edge_index.shape[1], generator=generator) >= p_drop
         x = simple_gat_layer(x, edge_index, state[f"layers.{layer}.lin.weight"],
-                             state[f"layers.{layer}.a_src"], state[f"layers.{layer}.a_dst"])
+                             state[f"layers.{layer}.a_src"], state[f"layers.{layer}.a_dst"], keep_mask=keep, p_drop=p_drop)
         layer += 1
     return x
 
@@ -174,17 +182,89 @@ def gatconv(x: torch.Tensor, edge_index: torch.Tensor, lin_weight: torch.Tensor,
     return out
 
 
+def gatconv_dense(x: torch.Tensor, edge_index: torch.Tensor, lin_weight: torch.Tensor, att_src: torch.Tensor,
+                  att_dst: torch.Tensor, bias: Optional[torch.Tensor], heads: int,
+                  negative_slope: float = 0.2) -> torch.Tensor:
+    """Second, structurally independent statement of the same ``GATConv`` call (eval mode): dense adjacency and a masked
+    softmax over an [N, N, H] logit tensor instead of gathers and scatters -- the textbook GAT formula
+    ``alpha_ij = softmax_j(LeakyReLU(a_src.h_j + a_dst.h_i))`` over the in-neighbours j of i (Velickovic et al. 2018, eq. 3,
+    which is what ``GATConv`` documents).  Parallel edges count separately in PyG's edge softmax, so the multiplicity
+    M[i, j] of edge j->i enters as ``+ log M`` inside the softmax.  O(N^2 H) memory: small graphs only.  No eps in the
+    denominator: after the max-subtraction PyG's denominator is >= 1, so its ``+1e-16`` is below fp64 resolution.
+    Used only to cross-check :func:`gatconv` (tests/test_oracle_golden.py)."""
+    n = x.shape[0]
+    h = (x @ lin_weight.t()).view(n, heads, -1)                          # [N, H, C]
+    s_src = torch.einsum("nhc,hc->nh", h, att_src.view(heads, -1))
+    s_dst = torch.einsum("nhc,hc->nh", h, att_dst.view(heads, -1))
+    mult = torch.zeros((n, n), dtype=x.dtype)
+    mult.index_put_((edge_index[1], edge_index[0]), torch.ones(edge_index.shape[1], dtype=x.dtype), accumulate=True)
+    z = torch.nn.functional.leaky_relu(s_dst.unsqueeze(1) + s_src.unsqueeze(0), negative_slope)    # [i, j, H]
+    z = z + torch.log(mult).unsqueeze(-1)                                # -inf where there is no edge j -> i
+    has_in = (mult.sum(1) > 0).view(n, 1, 1)
+    alpha = torch.softmax(torch.where(has_in, z, torch.zeros_like(z)), dim=1)
+    alpha = torch.where(has_in, alpha, torch.zeros_like(alpha))          # rows without in-edges aggregate nothing
+    out = torch.einsum("ijh,jhc->ihc", alpha, h).mean(dim=1)
+    if bias is not None:
+        out = out + bias
+    return out
+
+
 def pyg_gat_forward(state: Dict[str, torch.Tensor], item_feats: torch.Tensor, edge_index: torch.Tensor,
-                    heads: int) -> torch.Tensor:
-    """PyGGAT.forward (train_gat_pyg.py:84-88) over a PyG(>=2.5)-named state dict."""
+                    heads: int, p_drop: float = 0.0, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """PyGGAT.forward (train_gat_pyg.py:84-88) over a PyG(>=2.5)-named state dict.  ``p_drop > 0`` is train mode:
+    a fresh Bernoulli keep mask per layer, as ``F.dropout(alpha, p, training=True)`` inside GATConv draws one."""
     x = node_features(state["user_emb.weight"], state["item_proj.weight"], state["item_proj.bias"], item_feats)
     layer = 0
     while f"convs.{layer}.lin.weight" in state:
         p = f"convs.{layer}."
+        keep = None
+        if p_drop > 0.0:
+            keep = torch.rand((edge_index.shape[1], heads), generator=generator) >= p_drop
         x = gatconv(x, edge_index, state[p + "lin.weight"], state[p + "att_src"], state[p + "att_dst"],
-                    state[p + "bias"], heads)
+                    state[p + "bias"], heads, keep_mask=keep, p_drop=p_drop)
         layer += 1
     return x
+
+
+def init_custom_state(n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int) -> Dict[str, torch.Tensor]:
+    """Parameters of the reference ``CustomGAT`` drawn in its constructor's order with its initialisers
+    (scripts/train_gat_custom.py:64-71,97-103), under the caller's ``torch.manual_seed``: a reference-named state dict
+    without instantiating any module (bench.py's CPU arm must not import the product package)."""
+    st = {"user_emb.weight": torch.nn.Embedding(n_users, hidden).weight.detach()}
+    torch.nn.init.normal_(st["user_emb.weight"], std=0.1)
+    proj = torch.nn.Linear(item_feat_dim, hidden)
+    st["item_proj.weight"], st["item_proj.bias"] = proj.weight.detach(), proj.bias.detach()
+    for l in range(layers):
+        w = torch.nn.Linear(hidden, hidden, bias=False).weight.detach()
+        a_s, a_d = torch.empty(hidden), torch.empty(hidden)
+        torch.nn.init.xavier_uniform_(w)
+        torch.nn.init.xavier_uniform_(a_s.unsqueeze(0))
+        torch.nn.init.xavier_uniform_(a_d.unsqueeze(0))
+        st[f"layers.{l}.lin.weight"], st[f"layers.{l}.a_src"], st[f"layers.{l}.a_dst"] = w, a_s, a_d
+    return st
+
+
+def init_pyg_state(n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int, heads: int) -> Dict[str, torch.Tensor]:
+    """Same for ``PyGGAT`` (scripts/train_gat_pyg.py:68-77) with GATConv's published initialisers: glorot for
+    ``lin.weight`` / ``att_src`` / ``att_dst``, zeros for ``bias``."""
+    import math
+    st = {"user_emb.weight": torch.nn.Embedding(n_users, hidden).weight.detach()}
+    torch.nn.init.normal_(st["user_emb.weight"], std=0.1)
+    proj = torch.nn.Linear(item_feat_dim, hidden)
+    st["item_proj.weight"], st["item_proj.bias"] = proj.weight.detach(), proj.bias.detach()
+
+    def glorot(t):
+        bound = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+        return t.uniform_(-bound, bound)
+    for l in range(layers):
+        w = torch.nn.Linear(hidden, heads * hidden, bias=False).weight.detach()
+        st[f"convs.{l}.att_src"] = torch.empty(1, heads, hidden)
+        st[f"convs.{l}.att_dst"] = torch.empty(1, heads, hidden)
+        st[f"convs.{l}.bias"] = torch.zeros(hidden)
+        st[f"convs.{l}.lin.weight"] = glorot(w)
+        glorot(st[f"convs.{l}.att_src"])
+        glorot(st[f"convs.{l}.att_dst"])
+    return st
 
 
 # --------------------------------------------------------------------------------------

@@ -452,64 +452,80 @@ class ShardedGAT:
 
 
 # ------------------------------------------------------------------------------------------------------ bench (N > 1)
-def bench_main(args, rank: int, world: int, dev: torch.device) -> None:
+def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     """bench.py's N>1 leg: strong scaling of the same workload, max-over-ranks device time."""
     from . import _lib, synth
     import bench as B
-    nu, ni, n_inter, k = synth.CONFIGS[args.workload]
+    nu, ni, n_inter, k = B.graph_dims(cfg, synth)
     ei, feats = synth.make_graph(nu, ni, n_inter, k)
     e = int(ei.shape[1])
-    bf16 = getattr(args, "tier", "f32") == "bf16"
-    tr = ShardedGAT("pyg", nu, ni, feats, ei, hidden=B.HIDDEN, layers=B.LAYERS, heads=B.HEADS, attn_dropout=0.1, device=dev,
+    bf16 = cfg["tier"] == "bf16"
+    export = cfg["mode"] == "export"
+    L = cfg["layers"]
+    tr = ShardedGAT(cfg["kind"], nu, ni, feats, ei, hidden=cfg["hidden"], layers=L, heads=cfg["heads"], attn_dropout=0.1, device=dev,
                     feature_dtype=torch.bfloat16 if bf16 else torch.float32)
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
+    if export:
+        step = lambda *_: tr.export_item_embeddings()
+    else:
+        step = lambda a, b, c: tr.train_step(a, b, c, cfg["loss"])
     sampler = B.ClockSampler(dev.index)
     if rank == 0:
         sampler.start()                   # streams from here on; only the samples inside the timed region are kept
     for _ in range(args.warmup):
-        tr.train_step(du, di, dj)
+        step(du, di, dj)
     launches0 = _lib.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     sampler.begin()
     ev[0].record()
     for _ in range(args.steps):
-        loss = tr.train_step(du, di, dj)
+        out = step(du, di, dj)
     ev[1].record()
     torch.cuda.synchronize()
     sampler.end()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     ms = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = _lib.launch_count() - launches0
     t_e2e = []
-    for _ in range(max(args.steps, 3)):
-        dist.barrier()
+    hout = torch.empty((ni, cfg["hidden"]), dtype=torch.float32).pin_memory() if export else None
+    for _ in range(max(min(args.steps, 10) if export else args.steps, 3)):
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        uu, ii, jj = (t.to(dev, non_blocking=True) for t in (hu, hi, hj))
-        lv = tr.train_step(uu, ii, jj).item()
+        if export:
+            hout.copy_(step(), non_blocking=True)
+            torch.cuda.synchronize()
+            lv = float(hout[0, 0])
+        else:
+            uu, ii, jj = (t.to(dev, non_blocking=True) for t in (hu, hi, hj))
+            lv = step(uu, ii, jj).item()
         t_e2e.append((time.perf_counter() - t0) * 1e3)
     e2e = torch.tensor([statistics.median(t_e2e)], device=dev)
-    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     ms_step, e2e_ms = float(ms), float(e2e)
     if rank == 0:
+        conf = B.config_dict(cfg, nu, ni, n_inter, k, world)
+        conf["exchange"] = "copy-engine pulls from peer memory" if tr.px is not None else "NCCL all-gather"
+        conf["rows_per_rank"] = tr.n_loc
         print(json.dumps({
-            "metric": B.METRIC, "value": e * B.LAYERS / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": B.metric_name(cfg), "value": e * L / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: PyG-dialect GATConv x{B.LAYERS}, d={B.HIDDEN}, heads={B.HEADS}, BPR on "
-                                   f"{B.S_TRIPLES} triples, train mode, Adam step; {e} edges", "n_nodes": nu + ni, "n_edges": e,
-                       "layers": B.LAYERS, "parallelism": f"destination-row sharding over {world} GPUs (round-robin node blocks), row exchange per layer: "
-                                                       + ("copy-engine pulls from peer memory" if tr.px is not None else "NCCL all-gather"),
-                       "rows_per_rank": tr.n_loc,
-                       "l2": "per-step working set exceeds the 126 MB L2"},
-            "e2e": {"value": e * B.LAYERS / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(3 * B.S_TRIPLES * 8), "d2h_bytes_per_step": 4},
+            "dtype": "bf16" if bf16 else "f32", "data": "synthetic", "config": conf,
+            "e2e": {"value": e * L / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 0 if export else int(3 * B.S_TRIPLES * 8),
+                    "d2h_bytes_per_step": int(ni * cfg["hidden"] * 4) if export else 4},
             "gpu_launches": int(launches) * world, "clocks": clocks, "epoch_time_ms": ms_step, "loss": lv}))
-    dist.barrier()
-    dist.destroy_process_group()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

@@ -12,6 +12,7 @@ CONFIGS = {
     # name: (n_users, n_items, n_interactions, k)
     "cfg1": (10_000, 20_000, 200_000, 20),
     "amazon": (192_403, 498_196, 1_689_116, 20),
+    "cfg5": (10_000_000, 20_000_000, 200_000_000, 20),      # BASELINE config 5: 30 M nodes, 800 M edges
     "tiny": (300, 500, 4_000, 8),
 }
 

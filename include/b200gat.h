@@ -86,13 +86,19 @@ int b200gat_project_f32(const float* x, const float* W, const float* a_src, cons
                         int in_features, int heads, int channels, float* h, float* s, void* workspace,
                         size_t workspace_bytes, void* stream);
 
-/* "bf16 projection" (BASELINE config 3): operands rounded to bf16 on the way into shared memory, one UMMA
- * kind::f16 per K step, fp32 accumulation in TMEM; h is STORED as bf16 [n_rows, heads*128] (the edge kernels
- * then gather 256-byte rows), s is taken from the fp32 accumulator.  Needs in_features == channels == 128;
- * workspace >= heads * 32 KB.  The backward keeps fp32 gradients (b200gat_project_bwd_f32 with the fp32 x). */
+/* "bf16 projection" (BASELINE configs 3 and 5): operands rounded to bf16 on the way into shared memory, one UMMA
+ * kind::f16 per K step of 16, fp32 accumulation in TMEM; h is STORED as bf16 [n_rows, heads*channels] (the edge kernels
+ * then gather half the bytes), s is taken from the fp32 accumulator.  in_features and channels in {128, 256},
+ * heads * channels <= 1024; workspace >= b200gat_dense_workspace_bytes(heads, channels, in_features).
+ * project_bwd_bf16: the matching backward -- dx = dh_full W as ONE bf16 tensor-core launch contracting over all heads
+ * (K = heads * channels), dW = dh_full^T x in fp32-accurate TF32-split tiles, da_src / da_dst; same arguments as
+ * b200gat_project_bwd_f32 (dh is NOT modified). */
 int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
                          int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
                          size_t workspace_bytes, void* stream);
+int b200gat_project_bwd_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
+                             const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx, float* dW,
+                             float* da_src, float* da_dst, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of (2).  `dh` holds the aggregation part on entry and may be overwritten with the full
  * gradient of h (adds ds_src*a_src + ds_dst*a_dst); ds = [ds_src | ds_dst] [n_rows, 2*heads].
@@ -198,6 +204,65 @@ int b200gat_rank_loss_bwd_f32(const float* z, int64_t n_users, int64_t n_items, 
                               int loss_kind, const float* grad_out, const int32_t* node_list, int64_t node_begin,
                               int64_t node_count, float* dz, void* dz_bf16, void* workspace, size_t workspace_bytes,
                               void* stream);
+/* Row-sharded forms of the same two lines (:350-359) for the multi-GPU path.  z_blocks: HOST array of n_blocks device
+ * pointers, z_blocks[b] = rank b's [n_max, channels] block of Z (its own or peer-mapped memory); node_map (required) gives
+ * the row of node v in the gathered row space (block = row / n_max).  The forward evaluates triples
+ * [t_begin, t_begin + t_count) only -- their three rows are read out of the owners' memory over NVLink, no all-gather of Z --
+ * writes those slices of coef [2 * n_triples] (d/dpos | d/dneg) and loss_partial[0] = this rank's share of the mean; with
+ * need_backward it also sorts all 3 * n_triples incidences by node into `workspace`.  The backward needs the complete coef
+ * (the caller gathers the ranks' slices) and writes dz [node_count, channels] for the nodes in node_list (this rank's rows). */
+int b200gat_rank_loss_fwd_peer_f32(const void* const* z_blocks /*host*/, int n_blocks, int64_t n_max, int64_t n_users,
+                                   int64_t n_items, int channels, const int64_t* u, const int64_t* i, const int64_t* j,
+                                   int64_t n_triples, int64_t t_begin, int64_t t_count, const int32_t* node_map, int loss_kind,
+                                   int need_backward, float* coef, float* loss_partial, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+int b200gat_rank_loss_bwd_peer_f32(const void* const* z_blocks /*host*/, int n_blocks, int64_t n_max, int64_t n_users,
+                                   int64_t n_items, int channels, const int64_t* u, const int64_t* i, const int64_t* j,
+                                   int64_t n_triples, const int32_t* node_map, int loss_kind, const float* coef,
+                                   const float* grad_out, const int32_t* node_list, int64_t node_count, float* dz, void* dz_bf16,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- per-head streaming of a heads > 1 layer (BASELINE config 5: 30 M nodes x 4 heads x 256 channels) ----------------------
+ * When [N, heads*channels] does not fit, the layer (scripts/train_gat_pyg.py:77,87) runs one head at a time with heads = 1
+ * arguments: h_head [N, channels], s_head [N, 2] (b200gat_project_bf16 on that head's rows of W), rowstat_head [n_rows, 2].
+ *   edge_fwd_stream : the forward of one head; out = (accumulate ? out : 0) + out_scale * result (+ bias): out_scale = 1/heads,
+ *                     accumulate = head > 0, bias with the first head -> `out` ends up as the head mean + bias.
+ * The backward does not keep per-head outputs (t_i = sum_k alpha_ik dalpha_ik is recovered from the edges instead):
+ *   node_stat        : nodestat[r] = (s_dst, m, 1/D, 0) from s and rowstat
+ *   edge_bwd_phase1  : arguments of b200gat_edge_bwd_* with heads = 1; dout must already carry the 1/heads of the head mean
+ *                      (b200gat_cast_bf16 with scale); writes dh (aggregation part) and w_ij = alpha_ij * dalpha_ij into `de`
+ *   (caller)         : t = per-destination sums of w (b200gat_ds_dst_f32 on `de`; summed over ranks when sharded),
+ *                      node_stat_set_t stores them into nodestat[.].w (and the blocks are exchanged again when sharded)
+ *   edge_bwd_phase2  : de = slope * (w - alpha * t) in place, ds_src[j] = sum over j's out-edges; colptr/row = CSC arrays,
+ *                      rows [row_offset, row_offset + n_rows)
+ *   (caller)         : ds_dst = b200gat_ds_dst_f32 on `de`, then b200gat_project_bwd_bf16 / b200gat_project_dx_bf16 per head.
+ *   cast_bf16        : dst = bf16(scale * src) (n a multiple of 4). */
+int b200gat_edge_fwd_stream_f32(const float* h, const float* s, const int32_t* sched, int64_t n_sched,
+                                const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                const int32_t* perm, int64_t row_offset, int channels, int policy, float negative_slope,
+                                const float* bias, float* out, float* rowstat, float p_drop, uint64_t seed, float out_scale,
+                                int accumulate, void* stream);
+int b200gat_edge_fwd_stream_bf16(const void* h_bf16, const float* s, const int32_t* sched, int64_t n_sched,
+                                 const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                 const int32_t* perm, int64_t row_offset, int channels, int policy, float negative_slope,
+                                 const float* bias, float* out, float* rowstat, float p_drop, uint64_t seed, float out_scale,
+                                 int accumulate, void* stream);
+int b200gat_node_stat_f32(const float* s, const float* rowstat, int64_t n_rows, int64_t row_offset, int heads, float* nodestat,
+                          void* stream);
+int b200gat_node_stat_set_t_f32(float* nodestat, const float* t, int64_t n, void* stream);
+int b200gat_edge_bwd_phase1_f32(const float* h, const float* s, const float* dout, const float* nodestat, const int32_t* sched,
+                                int64_t n_sched, const int32_t* long_table, int64_t n_long, float* partial, const int32_t* row,
+                                const int32_t* perm_csc, int64_t row_offset, int channels, int policy, float negative_slope,
+                                float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream);
+int b200gat_edge_bwd_phase1_bf16(const void* h_bf16, const float* s, const void* dout_bf16, const float* nodestat,
+                                 const int32_t* sched, int64_t n_sched, const int32_t* long_table, int64_t n_long, float* partial,
+                                 const int32_t* row, const int32_t* perm_csc, int64_t row_offset, int channels, int policy,
+                                 float negative_slope, float* dh, float* de, float* ds_src, int ld_ds, float p_drop, uint64_t seed,
+                                 void* stream);
+int b200gat_edge_bwd_phase2_f32(float* de, const int32_t* colptr, const int32_t* row, const float* s, const float* nodestat,
+                                int64_t n_rows, int64_t row_offset, int policy, float negative_slope, float* ds_src, int ld_ds,
+                                void* stream);
+int b200gat_cast_bf16(const float* src, void* dst_bf16, int64_t n, float scale, void* stream);
 
 /* ---- callers either side of the path ---------------------------------
  * adam_step : one step of torch.optim.Adam(lr, weight_decay=l2) exactly as the reference builds it
@@ -245,6 +310,26 @@ int b200gat_peer_export(const void* ptr, void* handle /*host, >= 64 bytes*/, siz
 int b200gat_peer_open(const void* handle /*host*/, void** ptr /*host out: the peer's buffer, mapped here*/);
 int b200gat_peer_close(void* ptr);
 int b200gat_peer_pull(void* dst, const void* src, size_t bytes, void* stream);
+
+/* Device-side exchange ("fabric"): every rank's exported buffer has the same layout -- b200gat_peer_flag_bytes(n_channels)
+ * bytes of flags (zeroed once, before the first signal), then regions at offsets the host code chooses (the same on every
+ * rank).  bases: HOST array of `world` device pointers, bases[r] = rank r's buffer as mapped on this rank (bases[rank] = the
+ * local one).  epoch: the caller's step counter (grows by one per use of a channel; never reset).
+ *   signal    : ordered after the producer kernels on `stream`, stores epoch into flags[channel][rank] of every peer.
+ *   wait      : a kernel that returns once flags[channel][p] >= epoch for all p (bounded: traps after 20 s).
+ *   allgather : wait, then pull, with all SMs, block p of each part from rank p's buffer into the same place of the local
+ *               buffer (part k = world blocks of block_bytes[k] at offsets[k] + p * block_bytes[k]; the local block is produced
+ *               in place).  1 or 2 parts, 16-byte aligned.
+ *   reduce    : wait, then out[i] = sum over p = 0..world-1, in that order on every rank, of
+ *               ((float*)(bases[p] + offset))[first + i], i < n  (the all-reduce / reduce-scatter of the small tensors:
+ *               ds_dst partial sums, parameter gradients, the loss). */
+int b200gat_peer_flag_bytes(int n_channels, size_t* bytes /*host*/);
+int b200gat_peer_signal(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, void* stream);
+int b200gat_peer_wait(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, void* stream);
+int b200gat_peer_allgather(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, int n_parts,
+                           const uint64_t* offsets /*host*/, const uint64_t* block_bytes /*host*/, void* stream);
+int b200gat_peer_reduce_f32(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, uint64_t offset,
+                            int64_t first, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

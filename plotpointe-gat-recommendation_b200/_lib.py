@@ -51,10 +51,24 @@ _SIGS = {
                                      _P, _P, _P, c_float, c_uint64, _P]),
     "b200gat_node_prep_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "b200gat_project_bf16": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "b200gat_project_bwd_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                                         c_size_t, _P]),
     "b200gat_edge_fwd_bf16": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P,
                                       _P, _P, _P, c_float, c_uint64, _P]),
     "b200gat_edge_bwd_bf16": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int,
                                       c_float, _P, _P, _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_edge_fwd_stream_f32": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
+                                            c_float, c_uint64, c_float, c_int, _P]),
+    "b200gat_edge_fwd_stream_bf16": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
+                                             c_float, c_uint64, c_float, c_int, _P]),
+    "b200gat_node_stat_f32": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
+    "b200gat_node_stat_set_t_f32": (c_int, [_P, _P, c_int64, _P]),
+    "b200gat_edge_bwd_phase1_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float,
+                                            _P, _P, _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_edge_bwd_phase1_bf16": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float,
+                                             _P, _P, _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_edge_bwd_phase2_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
+    "b200gat_cast_bf16": (c_int, [_P, _P, c_int64, c_float, _P]),
     "b200gat_schedule_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(c_size_t)]),
     "b200gat_build_schedule": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "b200gat_edge_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int,
@@ -71,6 +85,15 @@ _SIGS = {
     "b200gat_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
     "b200gat_peer_close": (c_int, [_P]),
     "b200gat_peer_pull": (c_int, [_P, _P, c_size_t, _P]),
+    "b200gat_peer_flag_bytes": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
+    "b200gat_peer_signal": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, _P]),
+    "b200gat_peer_wait": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, _P]),
+    "b200gat_peer_allgather": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, c_int, _P, _P, _P]),
+    "b200gat_peer_reduce_f32": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, c_uint64, c_int64, c_int64, _P, _P]),
+    "b200gat_rank_loss_fwd_peer_f32": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_int64, c_int64, c_int64,
+                                               _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "b200gat_rank_loss_bwd_peer_f32": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_int64, _P, c_int, _P,
+                                               _P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

@@ -198,6 +198,13 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
 int tc_linear_fwd(const float* x, const float* W, const float* bias, int64_t n_rows, float* out, int64_t ldo, void* workspace,
                   cudaStream_t st);
 int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, void* workspace, cudaStream_t st);
+size_t tc_dw_tiles_workspace_bytes(int heads, int in_features);
+size_t bf16_gemm_workspace_bytes(int in_features, int heads, int channels);
+int att_grad_launch(const float* W, const float* v, int H, int C, int F, float* da_src, float* da_dst, cudaStream_t st) {
+  count_launch(), att_grad_kernel<<<ceil_div((int64_t)H * C * 32, 128), 128, 0, st>>>(W, v, H, C, F, da_src, da_dst);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
 }  // namespace b200gat
 
 static size_t simt_workspace_bytes(int heads, int channels, int in_features) {
@@ -208,7 +215,8 @@ static size_t simt_workspace_bytes(int heads, int channels, int in_features) {
 extern "C" int b200gat_dense_workspace_bytes(int heads, int channels, int in_features, size_t* bytes) {
   B200GAT_CHECK_ARG(bytes, "null");
   const size_t a = simt_workspace_bytes(heads, channels, in_features), b = tc_workspace_bytes(heads);
-  *bytes = a > b ? a : b;
+  const size_t c = (bf16_gemm_workspace_bytes(in_features, heads, channels) + 255) / 256 * 256 + tc_dw_tiles_workspace_bytes(heads, in_features);
+  *bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
   return kOk;
 }
 

@@ -119,10 +119,18 @@ struct RowBuf {
   typename Raw4<T>::type v[H][CV];
 };
 
+// How a launch's result lands in `out`: out = (accumulate ? out : 0) + scale * (head mean) + bias.  The plain layer call is
+// {1, 0}; per-head streaming (one launch per head of a heads > 1 layer, config 5) uses {1 / heads, head > 0} and passes the
+// bias with the first head only.
+struct OutMode {
+  float scale;
+  int accumulate;
+};
+
 template <int POLICY, int H, int CV>
 __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float (&m)[H], const float (&lt)[H], float4 (&acc)[H][CV],
                                              const float* __restrict__ bias, float* __restrict__ out,
-                                             float* __restrict__ out_heads, float2* __restrict__ rowstat, int lane) {
+                                             float* __restrict__ out_heads, float2* __restrict__ rowstat, int lane, OutMode om) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
   float inv[H];
@@ -142,11 +150,17 @@ __device__ __forceinline__ void finalize_row(int r, bool has_edges, const float 
       o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
     }
     if (H > 1) { o.x *= 1.f / H; o.y *= 1.f / H; o.z *= 1.f / H; o.w *= 1.f / H; }
+    if (om.scale != 1.f) { o.x *= om.scale; o.y *= om.scale; o.z *= om.scale; o.w *= om.scale; }
     if (bias) {
       const float4 b = ldg4(bias + cv * 128 + lane * 4);
       o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
     }
-    *reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4) = o;
+    float4* op = reinterpret_cast<float4*>(out + (size_t)r * C + cv * 128 + lane * 4);
+    if (om.accumulate) {
+      const float4 prev = *op;
+      o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+    }
+    *op = o;
   }
 }
 
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
                                                                 float neg_slope, const float* __restrict__ bias,
                                                                 float* __restrict__ out, float* __restrict__ out_heads,
                                                                 float2* __restrict__ rowstat, float* __restrict__ partial,
-                                                                float p_drop, uint64_t seed) {
+                                                                float p_drop, uint64_t seed, OutMode om) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
   // rows per load group; two groups in flight.  bf16 rows are half the registers, so twice the rows are kept in flight
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
       }
       return;
     }
-    finalize_row<POLICY, H, CV>(r, beg < end, m, lt, acc, bias, out, out_heads, rowstat, lane);
+    finalize_row<POLICY, H, CV>(r, beg < end, m, lt, acc, bias, out, out_heads, rowstat, lane, om);
   }
 }
 
@@ -274,7 +288,7 @@ template <int POLICY, int H, int CV>
 __global__ void __launch_bounds__(kEdgeThreads) fwd_combine_kernel(const float* __restrict__ partial, const int4* __restrict__ table,
                                                                    int n_long, const float* __restrict__ bias,
                                                                    float* __restrict__ out, float* __restrict__ out_heads,
-                                                                   float2* __restrict__ rowstat) {
+                                                                   float2* __restrict__ rowstat, OutMode om) {
   constexpr int C = CV * 128;
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(kEdgeThreads) fwd_combine_kernel(const float* 
       }
     }
   }
-  finalize_row<POLICY, H, CV>(t.x, true, m, lt, acc, bias, out, out_heads, rowstat, lane);
+  finalize_row<POLICY, H, CV>(t.x, true, m, lt, acc, bias, out, out_heads, rowstat, lane, om);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -410,7 +424,10 @@ __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restr
 // --------------------------------------------------------------------------------------------
 // backward, step 1: CSC pass (persistent warps over the source-row schedule)
 // --------------------------------------------------------------------------------------------
-template <typename T, int POLICY, int H, int CV, bool DROPOUT>
+// TP ("two-phase", per-head streaming without saved per-head outputs): t[i] = sum_k alpha_ik dalpha_ik is not known yet, so
+// this pass emits w_ij = alpha_ij * dalpha_ij into `de` (nodestat.w is ignored, ds_src is not meaningful); the caller reduces w
+// per destination into t, and edge_de_kernel turns w into de = slope * (w - alpha * t) in a second, scalar pass.
+template <typename T, int POLICY, int H, int CV, bool DROPOUT, bool TP = false>
 __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H * CV <= 4 ? EDGE_MINB_H4_BWD : 2)) edge_bwd_kernel(const T* __restrict__ h, const float* __restrict__ s,
                                                                 const T* __restrict__ dout,
                                                                 const float4* __restrict__ nodestat,
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
         for (int hh = 0; hh < H; ++hh) {
           const float tot = warp_multi_sum<U>(dsum[hh], lane);
           const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (5 - Log2<U>::value));   // <dout_i, h_j> of my edge
-          if (owner) my_de[hh] = gA[hh] * dot - cB[hh];
+          if (owner) my_de[hh] = TP ? agg[hh] * dot : gA[hh] * dot - cB[hh];
         }
       };
       for (int k = 0; k < cnt; k += 2 * U) {
@@ -647,6 +664,79 @@ __global__ void __launch_bounds__(256) ds_dst_thread_kernel(const float* __restr
   for (int hh = 0; hh < H; ++hh) ds_dst[(size_t)r * ld_ds + hh] = a[hh];
 }
 
+// second phase of the two-phase backward: de_ij = slope_ij * (w_ij - alpha_ij * t_i) in place over w (CSC order), and
+// ds_src[j] = sum over the out-edges of j.  nodestat[i] = (s_dst, m, 1/D, t) now carries t.  W lanes per source row.
+template <int POLICY, int H, int W>
+__global__ void __launch_bounds__(128) edge_de_kernel(float* __restrict__ de, const int32_t* __restrict__ colptr,
+                                                      const int32_t* __restrict__ row, const float* __restrict__ s,
+                                                      const float4* __restrict__ nodestat, int n_rows, int row_offset,
+                                                      float neg_slope, float* __restrict__ ds_src, int ld_ds) {
+  const int sl = threadIdx.x & (W - 1);
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / W;
+  const bool live = r < n_rows;
+  const int beg = live ? colptr[r] : 0, end = live ? colptr[r + 1] : 0;
+  float ssj[H], a[H];
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    ssj[hh] = live ? __ldg(s + (size_t)(row_offset + r) * (2 * H) + hh) : 0.f;
+    a[hh] = 0.f;
+  }
+  for (int q = beg + sl; q < end; q += W) {
+    const int i = __ldg(row + q);
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) {
+      const float4 st = __ldg(nodestat + (size_t)i * H + hh);
+      const float z0 = ssj[hh] + st.x;
+      const float zl = z0 > 0.f ? z0 : z0 * neg_slope;
+      float zc = zl, pass = 1.f;
+      if (POLICY == kCustom) {
+        zc = fminf(fmaxf(zl, -10.f), 10.f);
+        pass = (zl >= -10.f && zl <= 10.f) ? 1.f : 0.f;
+      }
+      const float alpha = expf(zc - st.y) * st.z;
+      const float gsc = (z0 > 0.f ? 1.f : neg_slope) * pass;
+      const float d = gsc * (de[(size_t)q * H + hh] - alpha * st.w);
+      de[(size_t)q * H + hh] = d;
+      a[hh] += d;
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) {
+    float t = a[hh];
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if (live && sl == 0) ds_src[(size_t)r * ld_ds + hh] = t;
+  }
+}
+
+// nodestat[r, h].w = t[r, h]  (the per-destination sums of the first phase, written into the slot the second phase reads)
+__global__ void set_t_kernel(float4* __restrict__ nodestat, const float* __restrict__ t, int64_t n) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n) nodestat[k].w = t[k];
+}
+
+// nodestat[r, h] = (s_dst, m, 1/D, 0) from the saved per-node scalars (no per-head outputs needed), and an optional scaled bf16
+// copy of dout for the gathers
+__global__ void node_stat_kernel(const float* __restrict__ s, const float2* __restrict__ rowstat, int64_t n_rows, int64_t row_offset,
+                                 int H, float4* __restrict__ nodestat) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n_rows * H) return;
+  const int64_t r = k / H;
+  const int hh = (int)(k - r * H);
+  const float2 rs = rowstat[k];
+  nodestat[k] = make_float4(s[(size_t)(row_offset + r) * (2 * H) + H + hh], rs.x, rs.y, 0.f);
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n4, float scale) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n4; k += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ld_stream4(src + 4 * k);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * scale, v.y * scale), hi = __floats2bfloat162_rn(v.z * scale, v.w * scale);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + 4 * k) = pk;
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // H * C == 128 (the headline shape): HALF a warp per scheduled row.
 // Rows are short (mean in-degree 19, a third of them below 10), so what bounds the warp-per-row kernels is the
@@ -718,7 +808,7 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
                                                                             const float* __restrict__ bias, float* __restrict__ out,
                                                                             float* __restrict__ out_heads,
                                                                             float2* __restrict__ rowstat, float* __restrict__ partial,
-                                                                            float p_drop, uint64_t seed) {
+                                                                            float p_drop, uint64_t seed, OutMode om) {
   constexpr int C = 128;
   constexpr int U = EDGE_U16_FWD * (sizeof(T) == 2 ? 2 : 1);   // rows per load group and half; two groups in flight
   const int lane = threadIdx.x & 31, sl = lane & 15;
@@ -821,13 +911,24 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
     st_stream4(out_heads + (size_t)r * C + ch0, acc0);
     st_stream4(out_heads + (size_t)r * C + ch1, acc1);
   }
+  if (om.scale != 1.f) {
+    acc0.x *= om.scale; acc0.y *= om.scale; acc0.z *= om.scale; acc0.w *= om.scale;
+    acc1.x *= om.scale; acc1.y *= om.scale; acc1.z *= om.scale; acc1.w *= om.scale;
+  }
   if (bias) {
     const float4 b0 = ldg4(bias + ch0), b1 = ldg4(bias + ch1);
     acc0.x += b0.x; acc0.y += b0.y; acc0.z += b0.z; acc0.w += b0.w;
     acc1.x += b1.x; acc1.y += b1.y; acc1.z += b1.z; acc1.w += b1.w;
   }
-  *reinterpret_cast<float4*>(out + (size_t)r * C + ch0) = acc0;
-  *reinterpret_cast<float4*>(out + (size_t)r * C + ch1) = acc1;
+  float4* o0 = reinterpret_cast<float4*>(out + (size_t)r * C + ch0);
+  float4* o1 = reinterpret_cast<float4*>(out + (size_t)r * C + ch1);
+  if (om.accumulate) {
+    const float4 p0 = *o0, p1 = *o1;
+    acc0.x += p0.x; acc0.y += p0.y; acc0.z += p0.z; acc0.w += p0.w;
+    acc1.x += p1.x; acc1.y += p1.y; acc1.z += p1.z; acc1.w += p1.w;
+  }
+  *o0 = acc0;
+  *o1 = acc1;
 }
 
 template <typename T, int POLICY, bool DROPOUT>
@@ -1029,7 +1130,7 @@ template <typename T>
 static int edge_fwd_impl(const T* h, const float* s, const int32_t* sched, int64_t n_rows, const int32_t* long_table,
                          int64_t n_long, float* partial, const int32_t* col, const int32_t* perm, int64_t row_offset, int heads,
                          int channels, int policy, float negative_slope, const float* bias, float* out, float* out_heads,
-                         float* rowstat, float p_drop, uint64_t seed, void* stream) {
+                         float* rowstat, float p_drop, uint64_t seed, void* stream, OutMode om = OutMode{1.f, 0}) {
   B200GAT_CHECK_ARG(h && s && sched && out, "null pointer");
   B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
@@ -1048,17 +1149,17 @@ static int edge_fwd_impl(const T* h, const float* s, const int32_t* sched, int64
       grid = (int)ceil_div(n_rows, 2 * (kEdgeThreads / 32));                                                            \
       count_launch(), edge_fwd16_kernel<T, P, D><<<grid, kEdgeThreads, 0, st>>>(                                        \
           h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,      \
-          (float2*)rowstat, partial, p_drop, seed);                                                                     \
+          (float2*)rowstat, partial, p_drop, seed, om);                                                                 \
     } else {                                                                                                            \
       rc = persistent_grid(edge_fwd_kernel<T, P, kH, kCV, D>, kEdgeThreads, n_rows, &grid);                             \
       if (rc) return rc;                                                                                                \
       count_launch(), edge_fwd_kernel<T, P, kH, kCV, D><<<grid, kEdgeThreads, 0, st>>>(                                 \
           h, s, (const int4*)sched, col, perm, (int)n_rows, (int)row_offset, negative_slope, bias, out, out_heads,      \
-          (float2*)rowstat, partial, p_drop, seed);                                                                     \
+          (float2*)rowstat, partial, p_drop, seed, om);                                                                 \
     }                                                                                                                   \
     if (n_long > 0)                                                                                                     \
       count_launch(), fwd_combine_kernel<P, kH, kCV><<<ceil_div(n_long * 32, kEdgeThreads), kEdgeThreads, 0, st>>>(     \
-          partial, (const int4*)long_table, (int)n_long, bias, out, out_heads, (float2*)rowstat);                       \
+          partial, (const int4*)long_table, (int)n_long, bias, out, out_heads, (float2*)rowstat, om);                   \
   } while (0)
   B200GAT_DISPATCH_HC(heads, cv, {
     if (policy == kCustom) { if (drop) LAUNCH_FWD(kCustom, true); else LAUNCH_FWD(kCustom, false); }
@@ -1120,7 +1221,7 @@ template <typename T>
 static int edge_bwd_impl(const T* h, const float* s, const T* dout, const float* nodestat, const int32_t* sched, int64_t n_rows,
                          const int32_t* long_table, int64_t n_long, float* partial, const int32_t* row, const int32_t* perm_csc,
                          int64_t row_offset, int heads, int channels, int policy, float negative_slope, float* dh, float* de,
-                         float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream) {
+                         float* ds_src, int ld_ds, float p_drop, uint64_t seed, void* stream, bool two_phase = false) {
   B200GAT_CHECK_ARG(h && s && dout && nodestat && sched && dh && ds_src && ld_ds >= heads, "null pointer / bad ld");
   B200GAT_CHECK_ARG(n_long == 0 || (long_table && partial), "split rows need long_table and partial");
   B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
@@ -1135,7 +1236,18 @@ static int edge_bwd_impl(const T* h, const float* s, const T* dout, const float*
   int grid = 0;
 #define LAUNCH_BWD(P, D)                                                                                               \
   do {                                                                                                                 \
-    if (kH * kCV == 1 && EDGE_W == 16) {                                                                               \
+    if (two_phase) {                                                                                                   \
+      if constexpr (kH == 1) {   /* the two-phase form exists for per-head streaming: one head per launch */            \
+        rc = persistent_grid(edge_bwd_kernel<T, P, kH, kCV, D, true>, kEdgeThreads, n_rows, &grid);                    \
+        if (rc) return rc;                                                                                             \
+        count_launch(), edge_bwd_kernel<T, P, kH, kCV, D, true><<<grid, kEdgeThreads, 0, st>>>(                        \
+            h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,      \
+            negative_slope, dh, de, ds_src, ld_ds, partial, p_drop, seed);                                             \
+      } else {                                                                                                         \
+        set_error("the two-phase backward runs one head per launch (heads=%d)", heads);                                \
+        return kErrUnsupported;                                                                                        \
+      }                                                                                                                \
+    } else if (kH * kCV == 1 && EDGE_W == 16) {                                                                        \
       grid = (int)ceil_div(n_rows, 2 * (kEdgeThreads / 32));                                                           \
       count_launch(), edge_bwd16_kernel<T, P, D><<<grid, kEdgeThreads, 0, st>>>(                                       \
           h, s, dout, (const float4*)nodestat, (const int4*)sched, row, perm_csc, (int)n_rows, (int)row_offset,        \
@@ -1202,6 +1314,94 @@ extern "C" int b200gat_ds_dst_f32(const float* de, const int32_t* rowptr, const 
   else if (heads == 2) count_launch(), ds_dst_kernel<2, kW><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
   else if (heads == 4) count_launch(), ds_dst_kernel<4, kW><<<grid, 128, 0, st>>>(de, rowptr, csr2csc, (int)n_rows, ds_dst, ld_ds);
   else { set_error("unsupported heads=%d", heads); return kErrUnsupported; }
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// ---- per-head streaming (BASELINE config 5: heads x channels = 4 x 256 over 30 M nodes does not fit as one [N, H*C] matrix) ----
+// One launch per head with heads = 1 arguments (h_head [N, C], s_head [N, 2]); `out` collects the head mean:
+// out = (accumulate ? out : 0) + out_scale * result (+ bias).
+extern "C" int b200gat_edge_fwd_stream_f32(const float* h, const float* s, const int32_t* sched, int64_t n_rows,
+                                           const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                           const int32_t* perm, int64_t row_offset, int channels, int policy,
+                                           float negative_slope, const float* bias, float* out, float* rowstat, float p_drop,
+                                           uint64_t seed, float out_scale, int accumulate, void* stream) {
+  return edge_fwd_impl<float>(h, s, sched, n_rows, long_table, n_long, partial, col, perm, row_offset, 1, channels, policy,
+                              negative_slope, bias, out, nullptr, rowstat, p_drop, seed, stream, OutMode{out_scale, accumulate});
+}
+extern "C" int b200gat_edge_fwd_stream_bf16(const void* h_bf16, const float* s, const int32_t* sched, int64_t n_rows,
+                                            const int32_t* long_table, int64_t n_long, float* partial, const int32_t* col,
+                                            const int32_t* perm, int64_t row_offset, int channels, int policy,
+                                            float negative_slope, const float* bias, float* out, float* rowstat, float p_drop,
+                                            uint64_t seed, float out_scale, int accumulate, void* stream) {
+  return edge_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)h_bf16, s, sched, n_rows, long_table, n_long, partial, col, perm,
+                                      row_offset, 1, channels, policy, negative_slope, bias, out, nullptr, rowstat, p_drop, seed,
+                                      stream, OutMode{out_scale, accumulate});
+}
+
+// Two-phase backward of ONE head without its saved output (see edge_bwd_kernel's TP note).  phase 1: same arguments as
+// b200gat_edge_bwd_* with heads = 1; nodestat[i] = (s_dst, m, 1/D, ignored); writes dh and w = alpha * dalpha into `de`.
+// The caller sums w per destination (b200gat_ds_dst_f32 on `de`), stores the sums into nodestat[.].w (set_t), and runs phase 2,
+// which rewrites `de` in place with the logit gradients and produces ds_src; ds_dst is then b200gat_ds_dst_f32 on `de` again.
+extern "C" int b200gat_edge_bwd_phase1_f32(const float* h, const float* s, const float* dout, const float* nodestat,
+                                           const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
+                                           float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset,
+                                           int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
+                                           int ld_ds, float p_drop, uint64_t seed, void* stream) {
+  return edge_bwd_impl<float>(h, s, dout, nodestat, sched, n_rows, long_table, n_long, partial, row, perm_csc, row_offset, 1,
+                              channels, policy, negative_slope, dh, de, ds_src, ld_ds, p_drop, seed, stream, true);
+}
+extern "C" int b200gat_edge_bwd_phase1_bf16(const void* h_bf16, const float* s, const void* dout_bf16, const float* nodestat,
+                                            const int32_t* sched, int64_t n_rows, const int32_t* long_table, int64_t n_long,
+                                            float* partial, const int32_t* row, const int32_t* perm_csc, int64_t row_offset,
+                                            int channels, int policy, float negative_slope, float* dh, float* de, float* ds_src,
+                                            int ld_ds, float p_drop, uint64_t seed, void* stream) {
+  return edge_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)h_bf16, s, (const __nv_bfloat16*)dout_bf16, nodestat, sched, n_rows,
+                                      long_table, n_long, partial, row, perm_csc, row_offset, 1, channels, policy, negative_slope,
+                                      dh, de, ds_src, ld_ds, p_drop, seed, stream, true);
+}
+extern "C" int b200gat_edge_bwd_phase2_f32(float* de, const int32_t* colptr, const int32_t* row, const float* s,
+                                           const float* nodestat, int64_t n_rows, int64_t row_offset, int policy,
+                                           float negative_slope, float* ds_src, int ld_ds, void* stream) {
+  B200GAT_CHECK_ARG(de && colptr && row && s && nodestat && ds_src && ld_ds >= 1, "null pointer / bad ld");
+  B200GAT_CHECK_ARG(policy == kCustom || policy == kPyG, "bad policy %d", policy);
+  if (n_rows == 0) return kOk;
+  constexpr int kW = 8;
+  const int grid = ceil_div(n_rows * kW, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (policy == kCustom)
+    count_launch(), edge_de_kernel<kCustom, 1, kW><<<grid, 128, 0, st>>>(de, colptr + row_offset, row, s, (const float4*)nodestat, (int)n_rows,
+                                                                         (int)row_offset, negative_slope, ds_src, ld_ds);
+  else
+    count_launch(), edge_de_kernel<kPyG, 1, kW><<<grid, 128, 0, st>>>(de, colptr + row_offset, row, s, (const float4*)nodestat, (int)n_rows,
+                                                                      (int)row_offset, negative_slope, ds_src, ld_ds);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+// nodestat[r, h] = (s_dst, m, 1/D, 0) for rows [0, n_rows) of a block whose first row is row_offset in s
+extern "C" int b200gat_node_stat_f32(const float* s, const float* rowstat, int64_t n_rows, int64_t row_offset, int heads,
+                                     float* nodestat, void* stream) {
+  B200GAT_CHECK_ARG(s && rowstat && nodestat && heads >= 1, "null pointer");
+  if (n_rows == 0) return kOk;
+  count_launch(), node_stat_kernel<<<ceil_div(n_rows * heads, 256), 256, 0, (cudaStream_t)stream>>>(s, (const float2*)rowstat, n_rows,
+                                                                                                   row_offset, heads, (float4*)nodestat);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+extern "C" int b200gat_node_stat_set_t_f32(float* nodestat, const float* t, int64_t n, void* stream) {
+  B200GAT_CHECK_ARG(nodestat && t, "null pointer");
+  if (n == 0) return kOk;
+  count_launch(), set_t_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((float4*)nodestat, t, n);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+// dst_bf16[k] = bf16(scale * src[k]), n a multiple of 4
+extern "C" int b200gat_cast_bf16(const float* src, void* dst_bf16, int64_t n, float scale, void* stream) {
+  B200GAT_CHECK_ARG(src && dst_bf16 && n % 4 == 0, "null pointer / n must be a multiple of 4");
+  if (n == 0) return kOk;
+  const int64_t n4 = n / 4;
+  const int grid = (int)(ceil_div(n4, 256) < kNumSMs * 16 ? ceil_div(n4, 256) : kNumSMs * 16);
+  count_launch(), cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_bf16, n4, scale);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

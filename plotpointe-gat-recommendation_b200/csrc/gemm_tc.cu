@@ -482,7 +482,10 @@ constexpr int kDwStages = 3;
 // (measured 1.4e-5 relative over 2000 rows).  Every kDwGroup stages (256 node rows, 96 UMMAs) the running tile is
 // therefore "promoted": the epilogue warps add it into a second TMEM tile with round-to-nearest FADDs while the
 // MMA warp continues into the other running tile.  TMEM columns: [0,128) running A, [128,256) running B, [256,384) sum.
-constexpr int kDwGroup = 8;
+#ifndef TC_DW_GROUP
+#define TC_DW_GROUP 2          // stages (x 32 node rows x 16 UMMAs) accumulated by the tensor core before a promotion
+#endif
+constexpr int kDwGroup = TC_DW_GROUP;
 constexpr int kDwSmem = 1024 + kDwStages * kDwStageBytes + kDwEpiWarps * 32 * 128 + 2 * kTileN * 4 + 256;
 
 struct DwParams {
@@ -490,7 +493,8 @@ struct DwParams {
   int64_t ld_dh;
   const float* ds;   // [n_rows, ds_ld], columns ds_src_col / ds_dst_col
   int ds_ld, ds_src_col, ds_dst_col;
-  const float* x;    // [n_rows, 128]
+  const float* x;    // [n_rows, ld_x], this launch's 128 columns
+  int64_t ld_x;
   const float* att_src;
   const float* att_dst;
   int64_t n_rows;
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
         const int64_t row = row0 + warp + 8 * i;
         if (row < r_end) {
           L.g[i] = ld_stream4(p.dh + row * p.ld_dh + c4 * 4);
-          L.xv[i] = ld_stream4(p.x + row * 128 + c4 * 4);
+          L.xv[i] = ld_stream4(p.x + row * p.ld_x + c4 * 4);
           L.d0[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_src_col) : 0.f;
           L.d1[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_dst_col) : 0.f;
         } else {
@@ -706,13 +710,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
   if (warp == kDwProducerWarps + kDwEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
-// out[i] = sum_z part[z*stride + i]
-__global__ void reduce_parts_kernel(const float* __restrict__ part, int n_parts, int64_t stride, int64_t n, float* __restrict__ out) {
+// out[(i / width) * ld_out + i % width] = sum_z part[z*stride + i]   (a [n / width, width] tile of a wider matrix)
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int n_parts, int64_t stride, int64_t n, float* __restrict__ out,
+                                    int width, int64_t ld_out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
   for (int z = 0; z < n_parts; ++z) a += part[z * stride + i];
-  out[i] = a;
+  out[(i / width) * ld_out + i % width] = a;
 }
 
 // da_src[c] = W[c,:] . v[0,:],  da_dst[c] = W[c,:] . v[1,:]     (heads == 1, F == 128)
@@ -801,13 +806,13 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
     }
     tc::DwParams q{};
     q.dh = dh + hh * 128; q.ld_dh = (int64_t)heads * 128; q.ds = ds; q.ds_ld = 2 * heads; q.ds_src_col = hh; q.ds_dst_col = heads + hh;
-    q.x = x; q.att_src = a_src + hh * 128; q.att_dst = a_dst + hh * 128; q.n_rows = n_rows;
+    q.x = x; q.ld_x = 128; q.att_src = a_src + hh * 128; q.att_dst = a_dst + hh * 128; q.n_rows = n_rows;
     q.rows_per_cta = per;
     q.part_dw = part_dw; q.part_v = part_v;
     count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
     count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128,
-                                                                                      dW + (size_t)hh * 128 * 128);
-    count_launch(), tc::reduce_parts_kernel<<<1, 256, 0, st>>>(part_v, grid, 256, 256, v);
+                                                                                      dW + (size_t)hh * 128 * 128, 128, 128);
+    count_launch(), tc::reduce_parts_kernel<<<1, 256, 0, st>>>(part_v, grid, 256, 256, v, 256, 256);
     count_launch(), tc::att_grad_tc_kernel<<<ceil_div(128 * 32, 128), 128, 0, st>>>(Wh, v, da_src + hh * 128, da_dst + hh * 128);
   }
   B200GAT_LAUNCH_CHECK();
@@ -837,47 +842,118 @@ int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, voi
   float* part_dw = (float*)workspace + tc::kBImageBytes / 4;
   tc::DwParams q{};
   q.dh = dy; q.ld_dh = 128; q.ds = nullptr; q.ds_ld = 0; q.ds_src_col = 0; q.ds_dst_col = 0;
-  q.x = x; q.att_src = nullptr; q.att_dst = nullptr; q.n_rows = n_rows;
+  q.x = x; q.ld_x = 128; q.att_src = nullptr; q.att_dst = nullptr; q.n_rows = n_rows;
   int64_t per = (n_rows + kNumSMs - 1) / kNumSMs;
   per = (per + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
   q.rows_per_cta = per;
   const int grid = (int)((n_rows + per - 1) / per);
   q.part_dw = part_dw; q.part_v = nullptr;
   count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
-  count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128, dW);
+  count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128, dW, 128, 128);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+// dW[H*C, F] = dh_full^T x and v[2H, F] = [ds_src | ds_dst]^T x for any H*C, F that are multiples of 128: one proj_dw launch per
+// (128 rows of dW) x (128 columns of x) tile pair, fp32-accurate (TF32 split).  workspace >= tc_dw_tiles_workspace_bytes().
+size_t tc_dw_tiles_workspace_bytes(int heads, int in_features) {
+  return (size_t)kNumSMs * (128 * 128 + 2 * 128) * sizeof(float) + (size_t)2 * heads * in_features * sizeof(float) + 1024;
+}
+int tc_project_dw_tiles(const float* x, const float* a_src, const float* a_dst, const float* dh, const float* ds, int64_t n_rows,
+                        int F, int H, int C, float* dW, float* v /*[2H, F]*/, void* workspace, cudaStream_t st) {
+  int rc = ensure_attrs();
+  if (rc) return rc;
+  float* part_dw = (float*)workspace;
+  float* part_v = part_dw + (size_t)kNumSMs * 128 * 128;
+  int64_t per = (n_rows + kNumSMs - 1) / kNumSMs;
+  per = (per + tc::kDwRows - 1) / tc::kDwRows * tc::kDwRows;
+  const int grid = (int)((n_rows + per - 1) / per);
+  const int HC = H * C;
+  for (int mt = 0; mt < HC / 128; ++mt) {
+    const int hh = (mt * 128) / C;
+    const bool first_of_head = (mt * 128) % C == 0;        // the side sums v do not depend on the dW row tile: take them once
+    for (int ft = 0; ft < F / 128; ++ft) {
+      tc::DwParams q{};
+      q.dh = dh + mt * 128; q.ld_dh = HC; q.ds = ds; q.ds_ld = 2 * H; q.ds_src_col = hh; q.ds_dst_col = H + hh;
+      q.x = x + ft * 128; q.ld_x = F; q.att_src = a_src + mt * 128; q.att_dst = a_dst + mt * 128; q.n_rows = n_rows;
+      q.rows_per_cta = per;
+      q.part_dw = part_dw; q.part_v = first_of_head ? part_v : nullptr;
+      count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
+      count_launch(), tc::reduce_parts_kernel<<<ceil_div(128 * 128, 256), 256, 0, st>>>(part_dw, grid, 128 * 128, 128 * 128,
+                                                                                        dW + (size_t)mt * 128 * F + ft * 128, 128, F);
+      if (first_of_head) {   // part_v [grid][2][128]: row 0 -> v[hh, ft*128..], row 1 -> v[H + hh, ft*128..]
+        count_launch(), tc::reduce_parts_kernel<<<1, 128, 0, st>>>(part_v, grid, 256, 128, v + (size_t)hh * F + ft * 128, 128, F);
+        count_launch(), tc::reduce_parts_kernel<<<1, 128, 0, st>>>(part_v + 128, grid, 256, 128, v + (size_t)(H + hh) * F + ft * 128, 128, F);
+      }
+    }
+  }
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
 
 }  // namespace b200gat
 
-// h_bf16 [n, heads*128] = bf16(x) bf16(W)^T (fp32 accumulate), s = fp32 row dots of the accumulator with a_src / a_dst
+namespace b200gat {  // gemm_bf16.cu, dense_simt.cu
+bool bf16_gemm_supported(int in_features, int heads, int channels);
+size_t bf16_gemm_workspace_bytes(int in_features, int heads, int channels);
+int bf16_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F, int H, int C,
+                     void* h_bf16, float* s, void* workspace, cudaStream_t st);
+int bf16_project_dx(const float* dh, const float* ds, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F,
+                    int H, int C, float* dx, void* workspace, cudaStream_t st);
+int att_grad_launch(const float* W, const float* v, int H, int C, int F, float* da_src, float* da_dst, cudaStream_t st);
+}  // namespace b200gat
+
+// h_bf16 [n, heads*C] = bf16(x) bf16(W)^T (fp32 accumulate), s = fp32 row dots of the accumulator with a_src / a_dst.
+// in_features and channels in {128, 256}, heads * channels <= 1024.
 extern "C" int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
                                     int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   using namespace b200gat;
   B200GAT_CHECK_ARG(x && W && a_src && a_dst && h_bf16 && s && workspace, "null pointer");
-  if (in_features != 128 || channels != 128) {
-    set_error("bf16 projection needs in_features == channels == 128 (got %d, %d)", in_features, channels);
+  if (!bf16_gemm_supported(in_features, heads, channels)) {
+    set_error("bf16 projection needs in_features and channels in {128, 256} and heads * channels <= 1024 (got %d, %d x %d)",
+              in_features, heads, channels);
     return kErrUnsupported;
   }
-  B200GAT_CHECK_ARG(workspace_bytes >= (size_t)heads * tc::kHBImageBytes, "workspace too small");
+  B200GAT_CHECK_ARG(workspace_bytes >= bf16_gemm_workspace_bytes(in_features, heads, channels), "workspace too small");
   if (n_rows == 0) return kOk;
-  int rc = ensure_attrs();
-  if (rc) return rc;
+  return bf16_project_fwd(x, W, a_src, a_dst, n_rows, in_features, heads, channels, h_bf16, s, workspace, (cudaStream_t)stream);
+}
+
+// Backward of the bf16 projection: dx = dh_full W (one bf16 tensor-core launch over all heads, K = heads * channels),
+// dW = dh_full^T x (fp32-accurate TF32-split tiles), da_src / da_dst; dh_full = dh + ds_src (x) a_src + ds_dst (x) a_dst is formed
+// on the fly (dh is not modified).  Same shape limits as b200gat_project_bf16.
+extern "C" int b200gat_project_bwd_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
+                                        const float* ds, int64_t n_rows, int in_features, int heads, int channels,
+                                        float* dx /*nullable*/, float* dW, float* da_src, float* da_dst, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  using namespace b200gat;
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && dh && ds && dW && da_src && da_dst && workspace, "null pointer");
+  if (!bf16_gemm_supported(in_features, heads, channels)) {
+    set_error("bf16 projection backward needs in_features and channels in {128, 256} and heads * channels <= 1024 (got %d, %d x %d)",
+              in_features, heads, channels);
+    return kErrUnsupported;
+  }
+  const size_t img = (bf16_gemm_workspace_bytes(in_features, heads, channels) + 255) / 256 * 256;
+  B200GAT_CHECK_ARG(workspace_bytes >= img + tc_dw_tiles_workspace_bytes(heads, in_features), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* images = (uint8_t*)workspace;
-  for (int hh = 0; hh < heads; ++hh)
-    count_launch(), tc::build_b_image_bf16_kernel<<<ceil_div(128 * 128 / 8, 256), 256, 0, st>>>(
-        W + (size_t)hh * 128 * 128, images + (size_t)hh * tc::kHBImageBytes);
-  tc::HParams p{};
-  p.a = x; p.b_images = images; p.out = (__nv_bfloat16*)h_bf16; p.n_rows = n_rows;
-  p.att_src = a_src; p.att_dst = a_dst; p.s = s; p.heads = heads;
-  const int64_t n_tiles = (n_rows + 127) / 128;
-  dim3 grid((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), heads);
-  count_launch(), tc::proj_bf16_kernel<<<grid, tc::kFwdThreads, tc::kHSmem, st>>>(p);
-  B200GAT_LAUNCH_CHECK();
-  return kOk;
+  const int HC = heads * channels;
+  if (n_rows == 0) {
+    B200GAT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * HC * in_features, st));
+    B200GAT_CUDA(cudaMemsetAsync(da_src, 0, sizeof(float) * HC, st));
+    B200GAT_CUDA(cudaMemsetAsync(da_dst, 0, sizeof(float) * HC, st));
+    return kOk;
+  }
+  int rc;
+  if (dx) {
+    rc = bf16_project_dx(dh, ds, W, a_src, a_dst, n_rows, in_features, heads, channels, dx, workspace, st);
+    if (rc) return rc;
+  }
+  char* ws2 = (char*)workspace + img;
+  float* v = (float*)(ws2 + (size_t)kNumSMs * (128 * 128 + 2 * 128) * sizeof(float));
+  rc = tc_project_dw_tiles(x, a_src, a_dst, dh, ds, n_rows, in_features, heads, channels, dW, v, ws2, st);
+  if (rc) return rc;
+  return att_grad_launch(W, v, heads, channels, in_features, da_src, da_dst, st);
 }
 
 extern "C" int b200gat_set_gemm_mode(int mode) {

@@ -92,7 +92,7 @@ class GATLayerFunction(torch.autograd.Function):
             dw = torch.empty_like(weight)
             da_s = torch.empty_like(a_s)
             da_d = torch.empty_like(a_d)
-            _lib.call("b200gat_project_bwd_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(dh),
+            _lib.call("b200gat_project_bwd_bf16" if bf16 else "b200gat_project_bwd_f32", _lib.ptr(x), _lib.ptr(weight), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(dh),
                       _lib.ptr(ds), n, f_in, heads, channels, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(da_s), _lib.ptr(da_d),
                       _lib.ptr(ws), ws_bytes, st)
         sa, sd = ctx.att_shape

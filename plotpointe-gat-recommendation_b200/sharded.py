@@ -1,31 +1,36 @@
-"""Row-sharded full-graph GAT training over P GPUs of one node (one process per GPU, torch.distributed/NCCL).
+"""Row-sharded full-graph GAT training over P GPUs of one node (one process per GPU).
 
 Nodes are dealt round-robin to the P ranks (user u -> rank u % P, item i -> rank i % P), which balances rows and, for
 the reference's graphs, edges.  Rank p owns its nodes' rows: their input features, their destination rows in the
-forward (CSR slice) and their source rows in the backward (CSC slice).  Per layer the exchange steps are:
+forward (CSR slice) and their source rows in the backward (CSC slice).
 
-  forward : all-gather of the projected rows [h | s]   (N x (H*C + 2H) floats)      -> fused edge forward on local rows
-  backward: all-gather of dout rows and of the per-destination scalars (N x (C + 4H)) -> fused edge backward on local
-            source rows (no atomics, no reduce-scatter); all-reduce of the ds_dst partial sums (N x H) and of the
-            parameter gradients (< 100 KB)
-  loss    : all-gather of the last layer's rows; every rank evaluates the (tiny) triple set and keeps the gradient
-            rows of its own block.
+All exchanges of a step run on the device over peer-mapped memory (``PeerFabric``, b200gat_peer_* in include/b200gat.h):
+every rank keeps one exported buffer with the same layout; a producer kernel writes this rank's row block in place, a
+signal kernel raises a flag in every peer's buffer, and the consuming kernel waits on its own flags and then pulls the
+peers' blocks over NVLink with all SMs.  No host round trip and no library collective inside a step; ``torch.distributed``
+only carries the set-up (IPC handles) and the bench's timing reductions.
 
-The row exchanges pull the peers' blocks out of peer memory with the copy engines (``PeerExchange``, b200gat_peer_* in
-include/b200gat.h) when that is the faster path -- 2 ranks by default, B200GAT_PEER=1 forces it, =0 or a box without CUDA IPC
-uses NCCL all-gathers, which is also the default beyond 2 ranks (measured, see ShardedGAT.__init__); the small
-reductions go through ``torch.distributed`` (plumbing); all arithmetic is the same C-ABI kernels as the single-GPU path.  The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which
-is how the gloo tests exercise it.
+  forward, heads == 1 : all-gather of the projected rows [h | s]        (N x (C + 2) values)   -> fused edge forward
+  forward, heads  > 1 : all-gather of the layer INPUT rows x (F_in wide, H times narrower than h); every rank projects all
+                        rows itself (redundant GEMM work instead of H x the NVLink bytes)
+  backward            : all-gather of dout rows and per-destination scalars (N x (C + 4H)) -> fused edge backward on the local
+                        source rows (no atomics, no reduce-scatter); reduce-pull of the ds_dst partial sums (N x H) and of the
+                        parameter gradients (< 100 KB), both summed in rank order on every rank (bitwise identical everywhere)
+  loss                : the S triples are split over the ranks; a triple's three Z rows are read straight out of the owners'
+                        blocks (S x 3 rows over NVLink instead of an all-gather of N rows); the per-triple coefficients
+                        (2 S floats) are exchanged and each rank forms the gradient rows of its own nodes the same way.
+
+The plan (row layout, per-rank edge selections) is plain torch and also runs on CPU tensors, which is how the gloo tests
+exercise it.
 """
 from __future__ import annotations
 
+import ctypes
 import json
-import os
 import statistics
-import sys
 import time
 from dataclasses import dataclass
-from typing import Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -36,9 +41,9 @@ import torch.distributed as dist
 class ShardPlan:
     """Round-robin block layout.  Users u and items i go to rank u % P / i % P, so every rank owns (within one row) the
     same number of users and of items and, for a random graph, the same number of edges.  Inside a block users come
-    first, then items (the order node_features produces).  Blocks are padded to ``n_max`` rows so that one
-    ``all_gather_into_tensor`` moves a layer; ``perm_map[v]`` is the row of node v in the gathered [P*n_max, ...]
-    tensors, and every index array the kernels see (col, row, schedules) is expressed in that row space."""
+    first, then items (the order node_features produces).  Blocks are padded to ``n_max`` rows so that every rank's block has
+    the same size; ``perm_map[v]`` is the row of node v in the gathered [P*n_max, ...] tensors, and every index array the
+    kernels see (col, row, schedules) is expressed in that row space."""
     rank: int
     world: int
     n_users: int
@@ -84,7 +89,8 @@ def make_plan(edge_index: torch.Tensor, n_users: int, n_items: int, rank: int, w
 
 
 def all_gather_rows(local: torch.Tensor, world: int) -> torch.Tensor:
-    """Gather the ranks' padded row blocks ([n_max, ...] each) into one [world*n_max, ...] tensor."""
+    """Gather the ranks' padded row blocks ([n_max, ...] each) into one [world*n_max, ...] tensor (torch.distributed; the
+    set-up / test path -- inside a step the rows move through ``PeerFabric``)."""
     if world == 1:
         return local
     local = local.contiguous()
@@ -93,7 +99,7 @@ def all_gather_rows(local: torch.Tensor, world: int) -> torch.Tensor:
     return out
 
 
-# ------------------------------------------------------------------------------------------------------ peer exchange
+# ------------------------------------------------------------------------------------------------------ peer fabric
 class _RawCuda:
     """A raw device allocation seen through __cuda_array_interface__ (so torch can wrap it without copying)."""
 
@@ -101,85 +107,137 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
-class PeerExchange:
-    """All-gather of the ranks' row blocks by pulling them out of peer memory (b200gat_peer_*, include/b200gat.h).
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
 
-    ``n_buffers`` persistent buffers of ``buffer_bytes`` per rank, one per exchange point of a step; every rank maps all its
-    peers' buffers once (CUDA IPC).  ``gather(b, parts)`` = stream-ordered barrier (one-element all-reduce: when it completes
-    on this rank's stream, every rank's producer kernels ordered before its own barrier have finished), then one copy-engine
-    pull per peer and part on a side stream per peer, then the current stream waits for the pulls.  A buffer is written again
-    one step later; the barriers of the other exchange points in between order that write after every peer's pulls."""
 
-    def __init__(self, lib, world: int, rank: int, dev: torch.device, buffer_bytes: int, n_buffers: int):
-        import ctypes
+class PeerFabric:
+    """One exported buffer per rank, same layout everywhere: [flags | region 0 | region 1 | ...].
+
+    ``signal(ch)`` (after the producer kernels, stream order) raises this step's epoch in every peer's flags;
+    ``allgather(ch, parts)`` / ``reduce(ch, ...)`` / ``wait(ch)`` launch a kernel that first waits for all peers' flags of
+    channel ``ch`` and then reads their memory.  Epochs grow by one per use; nothing is ever reset.  world == 1 keeps the same
+    code path on a private buffer (the kernels degenerate to a wait on the rank's own flag)."""
+
+    def __init__(self, lib, world: int, rank: int, dev: torch.device, n_channels: int, regions: Dict[str, int]):
         self.lib, self.world, self.rank, self.dev = lib, world, rank, dev
-        self.nbytes = (buffer_bytes + 255) // 256 * 256
-        self.local_ptr, self.local, handles = [], [], []
-        for _ in range(n_buffers):
+        fb = ctypes.c_size_t(0)
+        lib._check(lib._lib.b200gat_peer_flag_bytes(n_channels, ctypes.byref(fb)), "peer_flag_bytes")
+        self.off: Dict[str, int] = {}
+        total = fb.value
+        for name, nbytes in regions.items():
+            self.off[name] = total
+            total += _align(max(int(nbytes), 16))
+        self.nbytes = total
+        self.epoch = [0] * n_channels
+        self._opened: List[int] = []
+        self._local_ptr = None
+        self.local = None
+        ok, err, handle = True, "", b""
+        try:
             p = ctypes.c_void_p()
             lib._check(lib._lib.b200gat_peer_alloc(self.nbytes, ctypes.byref(p)), "peer_alloc")
-            h = ctypes.create_string_buffer(64)
-            lib._check(lib._lib.b200gat_peer_export(p, h, 64), "peer_export")
-            self.local_ptr.append(p.value)
-            self.local.append(torch.as_tensor(_RawCuda(p.value, self.nbytes), device=dev))
-            handles.append(h.raw)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, handles)
-        self.peer_ptr = []                                   # [rank][buffer] -> device address valid on THIS rank
-        for r in range(world):
-            if r == rank:
-                self.peer_ptr.append(list(self.local_ptr))
-                continue
-            ptrs = []
-            for raw in gathered[r]:
-                q = ctypes.c_void_p()
-                lib._check(lib._lib.b200gat_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)), "peer_open")
-                ptrs.append(q.value)
-            self.peer_ptr.append(ptrs)
-        self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.streams = [torch.cuda.Stream(dev) for _ in range(world - 1)]
-        self.order = [(rank + k) % world for k in range(1, world)]       # every rank starts with a different peer
+            self._local_ptr = p.value
+            if world > 1:
+                h = ctypes.create_string_buffer(64)
+                lib._check(lib._lib.b200gat_peer_export(p, h, 64), "peer_export")
+                handle = h.raw
+        except Exception as exc:      # noqa: BLE001
+            ok, err = False, str(exc)
+        self._agree(ok, f"allocating / exporting the exchange buffer ({self.nbytes / 2**20:.0f} MiB): {err}")
+        self.local = torch.as_tensor(_RawCuda(self._local_ptr, self.nbytes), device=dev)
+        self.local[:fb.value].zero_()                       # flags start at 0 = "no step has signalled yet"
+        ptrs = [self._local_ptr] * world
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, handle)
+            ok, err = True, ""
+            try:
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    q = ctypes.c_void_p()
+                    lib._check(lib._lib.b200gat_peer_open(ctypes.create_string_buffer(gathered[r], 64), ctypes.byref(q)), "peer_open")
+                    self._opened.append(q.value)
+                    ptrs[r] = q.value
+            except Exception as exc:      # noqa: BLE001
+                ok, err = False, str(exc)
+            self._agree(ok, f"mapping the peers' exchange buffers (CUDA IPC): {err}")
+            torch.cuda.synchronize(dev)
+            dist.barrier()                                   # every rank's flags are zero before anybody signals
+        self.ptrs = ptrs
+        self.bases = (ctypes.c_void_p * world)(*ptrs)
+        self.stats = None                                    # bench: dict name -> list of (start, end) events
 
-    def view(self, b: int, offset: int, shape, dtype) -> torch.Tensor:
+    def _agree(self, ok: bool, what: str) -> None:
+        """All ranks or none: a rank that failed must not leave the others blocked in the next collective."""
+        flag = torch.tensor([1.0 if ok else 0.0], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:
+            self.close()
+            raise RuntimeError(f"b200gat.sharded: {'failed ' + what if not ok else 'a peer rank failed ' + what.split(':')[0]}; "
+                               "the row-sharded path needs peer access (CUDA IPC over NVLink) between all ranks -- there is "
+                               "no host-staged fallback")
+
+    # ---- views of the LOCAL buffer
+    def view(self, name: str, shape, dtype, byte_offset: int = 0) -> torch.Tensor:
         n = 1
         for d in shape:
-            n *= d
+            n *= int(d)
         nbytes = n * torch.empty((), dtype=dtype).element_size()
-        assert offset % 16 == 0 and offset + nbytes <= self.nbytes
-        return self.local[b][offset:offset + nbytes].view(dtype).view(shape)
+        o = self.off[name] + byte_offset
+        assert o % 16 == 0 and o + nbytes <= self.nbytes, (name, o, nbytes, self.nbytes)
+        return self.local[o:o + nbytes].view(dtype).view(tuple(int(d) for d in shape))
 
-    def gather(self, b: int, parts) -> list:
-        """parts: [(offset, shape_of_one_block, dtype)] -> gathered tensors [(world * rows, ...)]."""
-        import ctypes
+    def region_ptrs(self, name: str):
+        """Host array of device pointers: the start of region ``name`` in every rank's buffer, as mapped on this rank."""
+        return (ctypes.c_void_p * self.world)(*[self.ptrs[b] + self.off[name] for b in range(self.world)])
+
+    # ---- device-side synchronisation and transfers (all on the current stream)
+    def _timed(self, what: str, fn) -> None:
+        if self.stats is None:
+            fn()
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.stats.setdefault(what, []).append((a, b))
+
+    def signal(self, ch: int) -> None:
+        self.epoch[ch] += 1
         lib = self.lib
-        dist.all_reduce(self.flag)                           # barrier on the current stream (see class docstring)
-        outs, jobs = [], []
-        for offset, shape, dtype in parts:
-            out = torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=self.dev)
-            blk = out[:shape[0]].numel() * out.element_size()
-            outs.append(out)
-            jobs.append((offset, blk, out.data_ptr()))
-        cur = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        for st, r in zip(self.streams, self.order):
-            st.wait_event(ev)
-            for offset, blk, dst in jobs:
-                lib._check(lib._lib.b200gat_peer_pull(ctypes.c_void_p(dst + r * blk), ctypes.c_void_p(self.peer_ptr[r][b] + offset),
-                                                     blk, ctypes.c_void_p(st.cuda_stream)), "peer_pull")
-        for offset, blk, dst in jobs:                         # own block: a local copy on the current stream
-            lib._check(lib._lib.b200gat_peer_pull(ctypes.c_void_p(dst + self.rank * blk), ctypes.c_void_p(self.local_ptr[b] + offset),
-                                                 blk, ctypes.c_void_p(cur.cuda_stream)), "peer_pull")
-        for st in self.streams:
-            cur.wait_stream(st)
-        return outs
+        lib._check(lib._lib.b200gat_peer_signal(self.bases, self.world, self.rank, ch, self.epoch[ch], lib.stream()), "peer_signal")
+
+    def wait(self, ch: int) -> None:
+        lib = self.lib
+        self._timed("wait", lambda: lib._check(lib._lib.b200gat_peer_wait(self.bases, self.world, self.rank, ch, self.epoch[ch],
+                                                                          lib.stream()), "peer_wait"))
+
+    def allgather(self, ch: int, parts) -> None:
+        """parts: [(region name, bytes per rank block)] (1 or 2): pull block p of every part from rank p, after channel ch."""
+        lib = self.lib
+        offs = (ctypes.c_uint64 * len(parts))(*[self.off[n] for n, _ in parts])
+        blks = (ctypes.c_uint64 * len(parts))(*[int(b) for _, b in parts])
+        self._timed("allgather", lambda: lib._check(lib._lib.b200gat_peer_allgather(
+            self.bases, self.world, self.rank, ch, self.epoch[ch], len(parts), offs, blks, lib.stream()), "peer_allgather"))
+
+    def reduce(self, ch: int, name: str, first: int, n: int, out: torch.Tensor) -> None:
+        """out[i] = sum over ranks (rank order) of region[first + i] (fp32), after channel ch."""
+        lib = self.lib
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n
+        self._timed("reduce", lambda: lib._check(lib._lib.b200gat_peer_reduce_f32(
+            self.bases, self.world, self.rank, ch, self.epoch[ch], self.off[name], first, n, lib.ptr(out), lib.stream()), "peer_reduce"))
 
     def close(self) -> None:
-        for r in range(self.world):
-            if r != self.rank:
-                for q in self.peer_ptr[r]:
-                    self.lib._lib.b200gat_peer_close(q)
-        self.peer_ptr = []
+        for q in self._opened:
+            self.lib._lib.b200gat_peer_close(ctypes.c_void_p(q))
+        self._opened = []
+        if self._local_ptr is not None:
+            self.local = None
+            self.lib._lib.b200gat_peer_free(ctypes.c_void_p(self._local_ptr))
+            self._local_ptr = None
 
 
 # ------------------------------------------------------------------------------------------------------ trainer
@@ -188,18 +246,24 @@ class ShardedGAT:
 
     Parameters are created with the same initialisers and in the same order as the single-GPU modules under the
     same ``torch.manual_seed``, so a sharded run starts from the identical state; ``user_emb`` rows are owned by the
-    rank that owns the node, everything else is replicated and its gradient all-reduced."""
+    rank that owns the node, everything else is replicated and its gradient summed over the ranks.
+
+    Why a region of the exchange buffer can be rewritten one step later without an extra barrier: a rank starts step t+1 only
+    after its own step t, whose last exchange (the parameter-gradient reduce in training, the Z gather in an export) waited
+    for EVERY peer's signal of that exchange -- and a peer raises that signal only after all its earlier kernels of step t,
+    pulls included, have completed.  A bare ``forward()`` is followed by no such exchange, so it ends with one explicit round."""
 
     def __init__(self, kind: str, n_users: int, n_items: int, item_feats: torch.Tensor, edge_index: torch.Tensor,
                  hidden: int = 128, layers: int = 2, heads: int = 1, attn_dropout: float = 0.1, seed: int = 42,
                  lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None,
-                 feature_dtype=torch.float32):
+                 feature_dtype=torch.float32, n_triples_max: int = 200_000):
         from . import _lib
         if feature_dtype not in (torch.float32, torch.bfloat16):
             raise NotImplementedError("feature_dtype must be float32 or bfloat16")
         self.bf16 = feature_dtype == torch.bfloat16   # bf16 projection: h and the gathered dout travel (and are stored) as bf16
         from .graph import build_graph
         from .modules import CustomGAT, PyGGAT
+        from .train import Adam
         self._lib = _lib
         self.kind = kind
         self.rank = dist.get_rank() if dist.is_initialized() else 0
@@ -210,6 +274,7 @@ class ShardedGAT:
         self.p_drop = attn_dropout
         self.training = True
         self.policy = _lib.POLICY_CUSTOM if kind == "custom" else _lib.POLICY_PYG
+        self.feat_dim = int(item_feats.shape[1])
 
         ei = edge_index.to(self.dev)
         self.plan = plan = make_plan(ei, n_users, n_items, self.rank, self.world)
@@ -227,16 +292,11 @@ class ShardedGAT:
         self.sched_bwd = _lib.make_schedule(self.g_bwd.colptr, plan.lo, self.n_loc, self.g_bwd.n_edges + 1)
         self.node_map = plan.perm_map.to(torch.int32).contiguous()
         self.node_list = plan.local_nodes.to(torch.int32).contiguous()
-        # node id of every gathered row (-1 for the padding rows): the loss gradient is evaluated for ALL rows on every
-        # rank (0.2 ms of redundant work) so that the last layer's dout needs no 354 MB all-gather
-        row_nodes = torch.full((self.n_pad,), -1, dtype=torch.int32, device=self.dev)
-        row_nodes[plan.perm_map] = torch.arange(self.n, dtype=torch.int32, device=self.dev)
-        self.row_nodes = row_nodes
         del ei, ei_p
 
         torch.manual_seed(seed)
-        full = (CustomGAT(n_users, n_items, item_feats.shape[1], hidden, layers) if kind == "custom"
-                else PyGGAT(n_users, n_items, item_feats.shape[1], hidden, layers, heads, attn_dropout))
+        full = (CustomGAT(n_users, n_items, self.feat_dim, hidden, layers) if kind == "custom"
+                else PyGGAT(n_users, n_items, self.feat_dim, hidden, layers, heads, attn_dropout))
         P = torch.nn.Parameter
         self.user_emb = P(full.user_emb.weight.detach()[self.rank::self.world].clone().to(self.dev))
         self.item_proj = full.item_proj.to(self.dev)
@@ -250,73 +310,112 @@ class ShardedGAT:
             self.a_dst.append(P(a_d.detach().clone().to(self.dev).view(self.heads, hidden)))
             self.bias.append(None if kind == "custom" else P(lay.bias.detach().clone().to(self.dev)))
         del full
-        # exchange over peer memory (copy-engine pulls) when the ranks can map each other's buffers; NCCL all-gathers otherwise
-        self.px = None
-        H_, C_ = self.heads, hidden
-        self._offB = (self.n_max * max(H_ * C_, C_) * 4 + 255) // 256 * 256       # part A: h or dout rows, part B: s or nodestat
-        # Measured (config 2, fp32): 2 GPUs: exchange 1.22 ms per step with pulls vs 1.86 ms with NCCL; 8 GPUs: 3.6 ms vs 2.4 ms
-        # (seven concurrent copy-engine streams per GPU do not add up to the NVLink rate).  So: pulls for 2 ranks, NCCL beyond,
-        # unless B200GAT_PEER=1 / 0 forces one of them.
-        mode = os.environ.get("B200GAT_PEER", "auto")
-        if self.world > 1 and (mode == "1" or (mode == "auto" and self.world <= 2)):
-            ok = torch.ones(1, device=self.dev)
-            try:
-                self.px = PeerExchange(_lib, self.world, self.rank, self.dev, self._offB + self.n_max * 4 * H_ * 4, 2 * layers + 1)
-            except Exception as exc:      # noqa: BLE001  (no IPC in this sandbox, no peer access, ...)
-                ok.zero_()
-                self.px = None
-                if self.rank == 0:
-                    print(f"b200gat.sharded: peer exchange unavailable ({exc}); using NCCL all-gathers", file=sys.stderr)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks or none
-            if ok.item() == 0:
-                self.px = None
         self.replicated = list(self.item_proj.parameters()) + self.W + self.a_src + self.a_dst + [b for b in self.bias if b is not None]
-        self.opt = torch.optim.Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay, fused=True)
+        self.n_rep = sum(p.numel() for p in self.replicated)
+        self.opt = Adam([self.user_emb] + self.replicated, lr=lr, weight_decay=weight_decay)   # the reference's update rule
         self.step_no = 0
         self.seed = seed
 
-    # -------------------------------------------------------------------------------------------- helpers
-    def _empty(self, *shape):
-        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+        # ---- exchange buffer: regions and channels
+        H, C, L, n_max, n_pad = self.heads, hidden, layers, self.n_max, self.n_pad
+        self.x_exchange = H > 1                  # heads > 1: move the layer input (F_in wide), project all rows on every rank
+        hsz = 2 if self.bf16 else 4
+        self.s_max = int(n_triples_max)
+        regions: Dict[str, int] = {}
+        for l in range(L):
+            regions[f"F{l}"] = n_pad * (C * 4 if self.x_exchange else H * C * hsz)
+            if not self.x_exchange:
+                regions[f"S{l}"] = n_pad * 2 * H * 4
+            regions[f"D{l}"] = n_pad * C * (4 if l == 0 else hsz)     # D0 doubles as the export's fp32 gather buffer
+            regions[f"NS{l}"] = n_pad * H * 16
+            regions[f"DSD{l}"] = n_pad * H * 4
+        regions["Z"] = n_max * C * 4
+        regions["COEF"] = 2 * self.s_max * 4
+        regions["LOSS"] = 16
+        regions["G"] = self.n_rep * 4
+        self.CH_F = lambda l: l
+        self.CH_Z, self.CH_C = L, L + 1
+        self.CH_B = lambda l: L + 2 + l
+        self.CH_R = lambda l: 2 * L + 2 + l
+        self.CH_G = 3 * L + 2
+        self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 3, regions)
+        self.comm_bytes_per_step = 0            # bytes this rank pulls from its peers per training step
+        self.comm_now = 0
+        self._loss_ws = None
+        self.saved = []
 
-    def _rows(self, *shape, dtype=torch.float32):
-        """Buffer for a tensor that is exchanged: padded to n_max rows (kernels fill the first n_loc)."""
-        return torch.empty((self.n_max,) + shape, dtype=dtype, device=self.dev)
+    def close(self) -> None:
+        self.fab.close()
+
+    # -------------------------------------------------------------------------------------------- helpers
+    def _empty(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
 
     def _layer_seed(self, layer: int) -> int:
         return (self.seed * 1_000_003 + self.step_no * 101 + layer) & (2 ** 62 - 1)
 
+    def _block(self, name: str, width: int, dtype) -> torch.Tensor:
+        """This rank's [n_max, width] block of a gathered region (what the producer kernels write)."""
+        esz = torch.empty((), dtype=dtype).element_size()
+        return self.fab.view(name, (self.n_max, width), dtype, self.rank * self.n_max * width * esz)
+
+    def _full(self, name: str, width: int, dtype) -> torch.Tensor:
+        return self.fab.view(name, (self.n_pad, width), dtype)
+
+    def _pulled(self, parts) -> None:
+        self.comm_now += sum(b for _, b in parts) * (self.world - 1)
+
     # -------------------------------------------------------------------------------------------- forward
-    def forward(self) -> torch.Tensor:
-        """Returns the local rows of Z; keeps what the backward needs in ``self.saved``."""
-        L, H, C, lib = self._lib, self.heads, self.hidden, self._lib
+    def forward(self, _exchange_follows: bool = False) -> torch.Tensor:
+        """Returns the local rows of Z ([n_max, C], the first n_loc are real; lives in the exchange buffer); keeps what the
+        backward needs in ``self.saved``."""
+        lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
         st = lib.stream()
-        from .functional import node_features
-        with torch.enable_grad():
-            x0 = node_features(self.user_emb, self.item_proj.weight, self.item_proj.bias, self.feats_loc)
-        self.x0 = x0
-        x = x0.detach()
+        L = self.n_layers
+        self.comm_now = 0
+        h_dt = torch.bfloat16 if self.bf16 else torch.float32
+        hsz = 2 if self.bf16 else 4
+        # layer-0 input: [user rows | item_proj(features)] without a concat copy (node_features, train_gat_custom.py:105-109)
+        x = self._block("F0", C, torch.float32) if self.x_exchange else self._empty(self.n_max, C)
+        cu = self.plan.cu
+        x[:cu].copy_(self.user_emb.detach())
+        dwb = lib.dense_workspace_bytes(H, C, max(C, self.feat_dim))
+        dws = self._empty(dwb, dtype=torch.uint8)
+        if self.plan.ci:
+            lib.call("b200gat_linear_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
+                     self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
         self.saved = []
         p = self.p_drop if self.training else 0.0
-        for l in range(self.n_layers):
-            f_in = x.shape[1]
-            h_dt = torch.bfloat16 if self.bf16 else torch.float32
-            if self.px is not None:
-                h_loc = self.px.view(l, 0, (self.n_max, H * C), h_dt)
-                s_loc = self.px.view(l, self._offB, (self.n_max, 2 * H), torch.float32)
+        for l in range(L):
+            last = l == L - 1
+            if self.x_exchange:
+                # x rows travel; every rank projects all rows (padding rows of the peers' blocks are never referenced by an edge)
+                fab.signal(self.CH_F(l))
+                parts = [(f"F{l}", self.n_max * C * 4)]
+                fab.allgather(self.CH_F(l), parts)
+                self._pulled(parts)
+                x_full = self._full(f"F{l}", C, torch.float32)
+                h_full = self._empty(self.n_pad, H * C, dtype=h_dt)
+                s_full = self._empty(self.n_pad, 2 * H)
+                lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x_full), lib.ptr(self.W[l]),
+                         lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]), self.n_pad, C, H, C, lib.ptr(h_full), lib.ptr(s_full),
+                         lib.ptr(dws), dwb, st)
             else:
-                h_loc, s_loc = self._rows(H * C, dtype=h_dt), self._rows(2 * H)
-            dwb = lib.dense_workspace_bytes(H, C, f_in)
-            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
-            lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
-                     self.n_loc, f_in, H, C, lib.ptr(h_loc), lib.ptr(s_loc), lib.ptr(dws), dwb, st)
-            if self.px is not None:
-                h_full, s_full = self.px.gather(l, [(0, (self.n_max, H * C), h_dt), (self._offB, (self.n_max, 2 * H), torch.float32)])
+                h_loc, s_loc = self._block(f"F{l}", H * C, h_dt), self._block(f"S{l}", 2 * H, torch.float32)
+                lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]),
+                         lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]), self.n_loc, C, H, C, lib.ptr(h_loc), lib.ptr(s_loc),
+                         lib.ptr(dws), dwb, st)
+                fab.signal(self.CH_F(l))
+                parts = [(f"F{l}", self.n_max * H * C * hsz), (f"S{l}", self.n_max * 2 * H * 4)]
+                fab.allgather(self.CH_F(l), parts)
+                self._pulled(parts)
+                h_full, s_full = self._full(f"F{l}", H * C, h_dt), self._full(f"S{l}", 2 * H, torch.float32)
+            if last:
+                out = fab.view("Z", (self.n_max, C), torch.float32)
+            elif self.x_exchange:
+                out = self._block(f"F{l + 1}", C, torch.float32)           # the next layer's input, produced in place
             else:
-                h_full = all_gather_rows(h_loc, self.world)
-                s_full = all_gather_rows(s_loc, self.world)
-            last = l == self.n_layers - 1
-            out = self.px.view(self.n_layers, 0, (self.n_max, C), torch.float32) if (self.px is not None and last) else self._rows(C)
+                out = self._empty(self.n_max, C)
             rowstat = self._empty(self.n_loc, H, 2)
             out_heads = self._empty(self.n_loc, H, C) if H > 1 else None
             seed = self._layer_seed(l)
@@ -327,66 +426,70 @@ class ShardedGAT:
                      H, C, self.policy, 0.2, lib.ptr(self.bias[l]), lib.ptr(out), lib.ptr(out_heads), lib.ptr(rowstat), p, seed, st)
             self.saved.append((x, h_full, s_full, rowstat, out if H == 1 else out_heads, p, seed))
             x = out
+        if not _exchange_follows and self.world > 1:
+            fab.signal(self.CH_Z)              # a bare forward: one round so that the next call may rewrite the regions
+            fab.wait(self.CH_Z)
         return x
 
+    # -------------------------------------------------------------------------------------------- loss + backward
     def loss_and_backward(self, z_loc: torch.Tensor, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
-        lib, H, C = self._lib, self.heads, self.hidden
+        lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
         st = lib.stream()
-        L_ = self.n_layers
-        if self.px is not None and z_loc.data_ptr() == self.px.local_ptr[L_]:
-            z_full = self.px.gather(L_, [(0, (self.n_max, C), torch.float32)])[0]
-        else:
-            z_full = all_gather_rows(z_loc, self.world)
-        s_tr = int(u.shape[0])
-        ws_bytes = lib.loss_workspace_bytes(self.n, s_tr)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
-        loss = self._empty(1)
+        L, P_, r = self.n_layers, self.world, self.rank
+        hsz = 2 if self.bf16 else 4
+        assert z_loc.data_ptr() == fab.view("Z", (1,), torch.float32).data_ptr(), "z_loc must be the tensor forward() returned"
+        S = int(u.shape[0])
+        if S > self.s_max:
+            raise RuntimeError(f"{S} triples > n_triples_max={self.s_max} given at construction")
         kind = lib.LOSS_BPR if loss_kind == "bpr" else lib.LOSS_BCE
-        lib.call("b200gat_rank_loss_fwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                 lib.ptr(self.node_map), kind, 1, lib.ptr(loss), lib.ptr(ws), ws_bytes, st)
+        ws_bytes = lib.loss_workspace_bytes(self.n, S)
+        if self._loss_ws is None or self._loss_ws.numel() < ws_bytes:
+            self._loss_ws = self._empty(ws_bytes, dtype=torch.uint8)
+        ws = self._loss_ws
+        # ---- loss forward on this rank's slice of the triples; rows come straight out of the owners' Z blocks
+        per = (S + P_ - 1) // P_
+        t0, t1 = min(r * per, S), min((r + 1) * per, S)
+        coef_loc = fab.view("COEF", (2 * S,), torch.float32)
+        coef_loc.zero_()                                      # the reduce below sums the ranks' disjoint slices
+        loss_part = fab.view("LOSS", (1,), torch.float32)
+        z_blocks = fab.region_ptrs("Z")
+        fab.signal(self.CH_Z)
+        fab.wait(self.CH_Z)                                   # every rank's Z block is complete
+        lib.call("b200gat_rank_loss_fwd_peer_f32", z_blocks, P_, self.n_max, self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j),
+                 S, t0, t1 - t0, lib.ptr(self.node_map), kind, 1, lib.ptr(coef_loc), lib.ptr(loss_part), lib.ptr(ws), ws_bytes, st)
+        self.comm_now += 3 * (t1 - t0) * C * 4 * (P_ - 1) // P_
+        fab.signal(self.CH_C)
+        coef = self._empty(2 * S)
+        loss = self._empty(1)
+        fab.reduce(self.CH_C, "COEF", 0, 2 * S, coef)
+        fab.reduce(self.CH_C, "LOSS", 0, 1, loss)
+        self.comm_now += 2 * S * 4 * (P_ - 1)
+        # ---- gradient rows of this rank's nodes (partner rows again read from the owners), straight into the exchange block
         one = torch.ones(1, dtype=torch.float32, device=self.dev)
-        if self.world > 1:
-            dout_all = self._empty(self.n_pad, C)
-            dout_all_g = torch.empty((self.n_pad, C), dtype=torch.bfloat16, device=self.dev) if self.bf16 else None
-            lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                     lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.row_nodes), 0, self.n_pad, lib.ptr(dout_all),
-                     lib.ptr(dout_all_g), lib.ptr(ws), ws_bytes, st)
-            dout = dout_all[self.plan.lo:self.plan.lo + self.n_max]
-            pre_gathered = (dout_all_g if self.bf16 else dout_all)
-        else:
-            dout = self._rows(C)
-            lib.call("b200gat_rank_loss_bwd_f32", lib.ptr(z_full), self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), s_tr,
-                     lib.ptr(self.node_map), kind, lib.ptr(one), lib.ptr(self.node_list), 0, self.n_loc, lib.ptr(dout), None,
-                     lib.ptr(ws), ws_bytes, st)
-            pre_gathered = None
-        del z_full
+        dout = self._block(f"D{L - 1}", C, torch.float32) if not self.bf16 else self._empty(self.n_max, C)
+        lib.call("b200gat_rank_loss_bwd_peer_f32", z_blocks, P_, self.n_max, self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), S,
+                 lib.ptr(self.node_map), kind, lib.ptr(coef), lib.ptr(one), lib.ptr(self.node_list), self.n_loc, lib.ptr(dout), None,
+                 lib.ptr(ws), ws_bytes, st)
+        self.comm_now += 4 * S * C * 4 * (P_ - 1) // (P_ * P_)
         grads = {}
-        for l in reversed(range(self.n_layers)):
+        dwb = lib.dense_workspace_bytes(H, C, max(C, self.feat_dim))
+        dws = self._empty(dwb, dtype=torch.uint8)
+        d_dt = torch.bfloat16 if self.bf16 else torch.float32
+        for l in reversed(range(L)):
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
-            f_in = x.shape[1]
-            bx = L_ + 1 + l                                        # this layer's backward exchange buffer
-            nodestat = self.px.view(bx, self._offB, (self.n_max, H, 4), torch.float32) if self.px is not None else self._rows(H, 4)
-            dwb = lib.dense_workspace_bytes(H, C, f_in)
-            dws = torch.empty(dwb, dtype=torch.uint8, device=self.dev)
+            nodestat = self._block(f"NS{l}", H * 4, torch.float32)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None
-            have_full = pre_gathered is not None and l == self.n_layers - 1
-            dout_g = None
-            if self.bf16 and not have_full:
-                dout_g = (self.px.view(bx, 0, (self.n_max, C), torch.bfloat16) if self.px is not None
-                          else self._rows(C, dtype=torch.bfloat16))
+            dout_g = self._block(f"D{l}", C, torch.bfloat16) if self.bf16 else None
+            if not self.bf16:
+                assert dout.data_ptr() == self._block(f"D{l}", C, torch.float32).data_ptr()
             lib.call("b200gat_node_prep_f32", lib.ptr(dout), lib.ptr(out_h), lib.ptr(self.bias[l] if H == 1 else None),
                      lib.ptr(s_full), lib.ptr(rowstat), self.n_loc, self.plan.lo, H, C, lib.ptr(nodestat), lib.ptr(db),
                      lib.ptr(dout_g), lib.ptr(dws), dwb, st)
-            if self.px is not None:
-                parts = [] if have_full else [(0, (self.n_max, C), torch.bfloat16 if self.bf16 else torch.float32)]
-                if not have_full and not self.bf16:
-                    assert dout.data_ptr() == self.px.local_ptr[bx], "fp32 dout of an inner layer must live in its exchange buffer"
-                got = self.px.gather(bx, parts + [(self._offB, (self.n_max, H, 4), torch.float32)])
-                dout_full = pre_gathered if have_full else got[0]
-                nodestat_full = got[-1]
-            else:
-                dout_full = pre_gathered if have_full else all_gather_rows(dout_g if self.bf16 else dout, self.world)
-                nodestat_full = all_gather_rows(nodestat, self.world)
+            fab.signal(self.CH_B(l))
+            parts = [(f"D{l}", self.n_max * C * hsz), (f"NS{l}", self.n_max * H * 16)]
+            fab.allgather(self.CH_B(l), parts)
+            self._pulled(parts)
+            dout_full, nodestat_full = self._full(f"D{l}", C, d_dt), self._full(f"NS{l}", H * 4, torch.float32)
             dh = self._empty(self.n_loc, H * C)
             de = self._empty(max(self.g_bwd.n_edges, 1), H)
             ds = self._empty(self.n_loc, 2 * H)
@@ -396,46 +499,50 @@ class ShardedGAT:
                      lib.ptr(sb.sched), sb.n_sched, lib.ptr(sb.table), sb.n_long, lib.ptr(sb.partial(H * C + 4)),
                      lib.ptr(self.g_bwd.row), lib.ptr(self.perm_bwd), self.plan.lo, H, C, self.policy, 0.2, lib.ptr(dh),
                      lib.ptr(de), lib.ptr(ds), 2 * H, p, seed, st)
-            ds_dst = self._empty(self.n_pad, H)                              # partial sums over this rank's edges
+            ds_part = self._full(f"DSD{l}", H, torch.float32)               # partial sums over this rank's edges, all rows
             lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad,
-                     self.g_bwd.n_edges, H,
-                     lib.ptr(ds_dst), H, st)
-            if self.world > 1:
-                dist.all_reduce(ds_dst)
-            ds[:, H:] = ds_dst[self.plan.lo:self.plan.lo + self.n_loc]
-            del de, dout_full, nodestat_full
-            # dx of layer l is the dout of layer l-1: in the fp32 tier it is produced straight into that layer's exchange buffer
-            if self.px is not None and l >= 1 and not self.bf16:
-                dx = self.px.view(L_ + l, 0, (self.n_max, f_in), torch.float32)
-            else:
-                dx = self._rows(f_in)
+                     self.g_bwd.n_edges, H, lib.ptr(ds_part), H, st)
+            fab.signal(self.CH_R(l))
+            ds_dst = self._empty(max(self.n_loc, 1), H)
+            fab.reduce(self.CH_R(l), f"DSD{l}", self.plan.lo * H, self.n_loc * H, ds_dst)
+            self.comm_now += self.n_loc * H * 4 * (P_ - 1)
+            ds[:, H:] = ds_dst[:self.n_loc]
+            del de
+            # dx of layer l is the dout of layer l-1: in the fp32 tier it is produced straight into that layer's exchange block
+            dx = self._block(f"D{l - 1}", C, torch.float32) if (l >= 1 and not self.bf16) else self._empty(self.n_max, C)
             dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
-            lib.call("b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
-                     lib.ptr(dh), lib.ptr(ds), self.n_loc, f_in, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
+            lib.call("b200gat_project_bwd_bf16" if self.bf16 else "b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+                     lib.ptr(dh), lib.ptr(ds), self.n_loc, C, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
                      lib.ptr(dws), dwb, st)
             grads[self.W[l]], grads[self.a_src[l]], grads[self.a_dst[l]] = dW, da_s, da_d
             if db is not None:
                 grads[self.bias[l]] = db
             dout = dx
-        # input features: user rows take their gradient rows directly, item_proj through torch autograd
-        for p_ in [self.user_emb] + list(self.item_proj.parameters()):
-            p_.grad = None
-        self.x0.backward(dout[:self.n_loc])
-        for p_, g in grads.items():
-            p_.grad = g
-        if self.world > 1:
-            flat = torch.cat([p_.grad.reshape(-1) for p_ in self.replicated])
-            dist.all_reduce(flat)
-            off = 0
-            for p_ in self.replicated:
-                k = p_.numel()
-                p_.grad = flat[off:off + k].view_as(p_)
-                off += k
+        # input features (node_features backward): user rows take their gradient rows, item_proj its weight / bias gradients
+        cu, ci = self.plan.cu, self.plan.ci
+        self.user_emb.grad = dout[:cu].clone()
+        dpw, dpb = torch.empty_like(self.item_proj.weight), torch.empty_like(self.item_proj.bias)
+        lib.call("b200gat_linear_bwd_f32", lib.ptr(self.feats_loc), lib.ptr(dout, cu * C), C, ci, self.feat_dim, C, lib.ptr(dpw),
+                 lib.ptr(dpb), lib.ptr(dws), dwb, st)
+        grads[self.item_proj.weight], grads[self.item_proj.bias] = dpw, dpb
+        # replicated parameters: sum of the ranks' gradients, in rank order on every rank (bitwise identical everywhere)
+        g_loc = fab.view("G", (self.n_rep,), torch.float32)
+        torch.cat([grads[p_].reshape(-1) for p_ in self.replicated], out=g_loc)
+        fab.signal(self.CH_G)
+        flat = self._empty(self.n_rep)
+        fab.reduce(self.CH_G, "G", 0, self.n_rep, flat)
+        self.comm_now += self.n_rep * 4 * (P_ - 1)
+        off = 0
+        for p_ in self.replicated:
+            k = p_.numel()
+            p_.grad = flat[off:off + k].view_as(p_)
+            off += k
         self.saved = []
+        self.comm_bytes_per_step = self.comm_now
         return loss.view(())
 
     def train_step(self, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
-        z = self.forward()
+        z = self.forward(_exchange_follows=True)
         loss = self.loss_and_backward(z, u, i, j, loss_kind)
         self.opt.step()
         self.step_no += 1
@@ -445,13 +552,69 @@ class ShardedGAT:
     def export_item_embeddings(self) -> torch.Tensor:
         """Config 4: forward-only, returns Z[n_users:] gathered on every rank (tools/export_item_embeddings.py:140-142)."""
         was, self.training = self.training, False
-        z = all_gather_rows(self.forward(), self.world)[self.plan.perm_map]     # back to node order
+        z_loc = self.forward(_exchange_follows=True)
         self.training = was
         self.saved = []
-        return z[self.nu:]
+        fab, C = self.fab, self.hidden
+        # the gather of the ranks' Z blocks doubles as the end-of-call round that lets the next call rewrite the regions
+        zg = fab.view("D0", (self.n_pad, C), torch.float32)
+        zg[self.plan.lo:self.plan.lo + self.n_max].copy_(z_loc)
+        fab.signal(self.CH_B(0))
+        parts = [("D0", self.n_max * C * 4)]
+        fab.allgather(self.CH_B(0), parts)
+        self._pulled(parts)
+        self.comm_bytes_per_step = self.comm_now
+        return zg[self.plan.perm_map[self.nu:]]                   # back to node order, item rows only
 
 
 # ------------------------------------------------------------------------------------------------------ bench (N > 1)
+def _parity_vs_single(tr: "ShardedGAT", cfg, feats, ei, triples, rank: int, world: int, dev) -> Optional[dict]:
+    """One eval-mode forward + loss + backward on the sharded trainer against the single-GPU module path holding the SAME
+    parameters (after the timed steps), every rank checking its own rows: max relative differences (on the tensor's scale)."""
+    import b200gat
+    u, i, j = triples
+    nu, ni = tr.nu, tr.ni
+    tr.training = False
+    z_loc = tr.forward(_exchange_follows=True)
+    loss = tr.loss_and_backward(z_loc, u, i, j, cfg["loss"])
+    z_rows = z_loc[:tr.n_loc].clone()
+    ue = torch.zeros(nu, tr.hidden, device=dev)
+    ue[rank::world] = tr.user_emb.detach()
+    if world > 1:
+        dist.all_reduce(ue)
+    fdt = torch.bfloat16 if tr.bf16 else torch.float32
+    custom = tr.kind == "custom"
+    m = (b200gat.CustomGAT(nu, ni, tr.feat_dim, tr.hidden, tr.n_layers, feature_dtype=fdt) if custom
+         else b200gat.PyGGAT(nu, ni, tr.feat_dim, tr.hidden, tr.n_layers, tr.heads, 0.1, feature_dtype=fdt)).to(dev).eval()
+    lays = m.layers if custom else m.convs
+    with torch.no_grad():
+        m.user_emb.weight.copy_(ue)
+        m.item_proj.weight.copy_(tr.item_proj.weight)
+        m.item_proj.bias.copy_(tr.item_proj.bias)
+        for l, lay in enumerate(lays):
+            lay.lin.weight.copy_(tr.W[l])
+            a_s, a_d = (lay.a_src, lay.a_dst) if custom else (lay.att_src, lay.att_dst)
+            a_s.copy_(tr.a_src[l].view_as(a_s))
+            a_d.copy_(tr.a_dst[l].view_as(a_d))
+            if not custom:
+                lay.bias.copy_(tr.bias[l])
+    z = m(feats.to(dev), ei.to(dev))
+    ref_loss = (b200gat.bpr_loss if cfg["loss"] == "bpr" else b200gat.bce_loss)(z, nu, u, i, j)
+    ref_loss.backward()
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    res = torch.tensor([rel(z_rows, z[tr.plan.local_nodes]), rel(loss, ref_loss), rel(tr.W[0].grad, lays[0].lin.weight.grad),
+                        rel(tr.W[-1].grad, lays[-1].lin.weight.grad),
+                        rel(tr.user_emb.grad, m.user_emb.weight.grad[rank::world]) if tr.plan.cu else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    tr.training = True
+    del m, z
+    torch.cuda.empty_cache()
+    names = ["z_rows", "loss", "dW_layer0", "dW_last", "d_user_emb_rows"]
+    return {"mode": "eval (no dropout), same parameters, after the timed steps; max over ranks of max|a-b| / max|b|",
+            **{k_: float(v) for k_, v in zip(names, res.tolist())}}
+
+
 def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     """bench.py's N>1 leg: strong scaling of the same workload, max-over-ranks device time."""
     from . import _lib, synth
@@ -463,7 +626,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     export = cfg["mode"] == "export"
     L = cfg["layers"]
     tr = ShardedGAT(cfg["kind"], nu, ni, feats, ei, hidden=cfg["hidden"], layers=L, heads=cfg["heads"], attn_dropout=0.1, device=dev,
-                    feature_dtype=torch.bfloat16 if bf16 else torch.float32)
+                    feature_dtype=torch.bfloat16 if bf16 else torch.float32, n_triples_max=B.S_TRIPLES)
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
@@ -484,7 +647,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     sampler.begin()
     ev[0].record()
     for _ in range(args.steps):
-        out = step(du, di, dj)
+        step(du, di, dj)
     ev[1].record()
     torch.cuda.synchronize()
     sampler.end()
@@ -513,10 +676,29 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     if world > 1:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- communication: measured on a few extra steps with events around every exchange kernel (wait included)
+    tr.fab.stats = {}
+    _lib.timing = {}
+    n_prof = 5
+    for _ in range(n_prof):
+        step(du, di, dj)
+    torch.cuda.synchronize()
+    stats, tr.fab.stats = tr.fab.stats, None
+    timing, _lib.timing = _lib.timing, None
+    comm_ms = {k_: sum(a.elapsed_time(b) for a, b in v) / n_prof for k_, v in stats.items()}
+    kern_ms = {k_: sum(a.elapsed_time(b) for a, b in v) / n_prof for k_, v in timing.items()}
+    cm = torch.tensor([sum(comm_ms.values()), sum(kern_ms.values())], device=dev)
+    if world > 1:
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+    comm_bytes = int(tr.comm_bytes_per_step)
+    parity = None
+    if not export and (nu + ni) <= 2_000_000:
+        parity = _parity_vs_single(tr, cfg, feats, ei, (du, di, dj), rank, world, dev)
     ms_step, e2e_ms = float(ms), float(e2e)
     if rank == 0:
         conf = B.config_dict(cfg, nu, ni, n_inter, k, world)
-        conf["exchange"] = "copy-engine pulls from peer memory" if tr.px is not None else "NCCL all-gather"
+        conf["exchange"] = ("device-side pulls over peer-mapped memory (flag wait + all-SM NVLink reads), no library collective in the step; "
+                            + ("layer inputs x exchanged, every rank projects all rows" if tr.x_exchange else "projected rows [h|s] exchanged"))
         conf["rows_per_rank"] = tr.n_loc
         print(json.dumps({
             "metric": B.metric_name(cfg), "value": e * L / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
@@ -525,7 +707,17 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
             "e2e": {"value": e * L / (e2e_ms * 1e-3), "unit": B.UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 0 if export else int(3 * B.S_TRIPLES * 8),
                     "d2h_bytes_per_step": int(ni * cfg["hidden"] * 4) if export else 4},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "epoch_time_ms": ms_step, "loss": lv}))
+            "gpu_launches": int(launches) * world, "clocks": clocks, "epoch_time_ms": ms_step, "loss": lv,
+            "comm": {"bytes_pulled_per_rank_per_step": comm_bytes, "ms_per_step_max_rank": round(float(cm[0]), 4),
+                     "by_kind_ms_rank0": {k_: round(v, 4) for k_, v in comm_ms.items()},
+                     "pull_gbs_rank0": round(comm_bytes / max(comm_ms.get("allgather", 0.0), 1e-9) / 1e6, 1) if world > 1 else None,
+                     "compute_kernels_ms_per_step_max_rank": round(float(cm[1]), 4), "overlap_frac": 0.0,
+                     "note": "exchange kernels sit in-stream between their producer and their consumer (nothing to overlap them "
+                             "with); their time includes waiting for the slowest peer"},
+            "breakdown_ms_per_step_rank0": {k_: round(v, 4) for k_, v in sorted(kern_ms.items())},
+            "parity_vs_single": parity}))
     if world > 1:
         dist.barrier()
+    tr.close()
+    if world > 1:
         dist.destroy_process_group()

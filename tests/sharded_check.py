@@ -65,10 +65,24 @@ def main(kind):
     tr2 = sharded.ShardedGAT(kind, nu, ni, feats, ei, hidden=128, layers=2, heads=heads, attn_dropout=0.1, seed=7, device=dev)
     emb = tr2.export_item_embeddings()                      # config 4: forward-only export equals the module path
     close(emb, z[nu:], "export")
-    tr.train_step(u, i, j)
+    emb2 = tr2.export_item_embeddings()                     # and again: the exchange regions are reused call after call
+    assert torch.equal(emb, emb2)
+    tr2.close()
+    # a few optimizer steps: every rank holds bitwise-identical replicated parameters (the gradient sums run in rank order)
+    for _ in range(3):
+        tr.train_step(u, i, j)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        w0 = tr.W[0].detach().clone()
+        ws = [torch.zeros_like(w0) for _ in range(world)]
+        dist.all_gather(ws, w0)
+        assert all(torch.equal(x, ws[0]) for x in ws), "replicated parameters diverged between ranks"
+    # one-layer model, bare forward() calls back to back (the reference's *_layers1 ablations): no stale rows
+    tr1 = sharded.ShardedGAT(kind, nu, ni, feats, ei, hidden=128, layers=1, heads=heads, attn_dropout=0.1, seed=7, device=dev)
+    tr1.training = False
+    za = tr1.forward().clone()
+    zb_ = tr1.forward().clone()
+    assert torch.equal(za, zb_)
+    tr1.close()
     # bf16 tier: sharded equals the single-GPU bf16 modules (same kernels, same rounding points)
     trb = sharded.ShardedGAT(kind, nu, ni, feats, ei, hidden=128, layers=2, heads=heads, attn_dropout=0.1, seed=7, device=dev,
                              feature_dtype=torch.bfloat16)
@@ -84,8 +98,13 @@ def main(kind):
     close(zb[:trb.n_loc], zmb[trb.plan.local_nodes], "z bf16", 1e-4)
     close(lb, lmb, "loss bf16", 1e-5)
     close(trb.W[0].grad, (mb.layers if kind == "custom" else mb.convs)[0].lin.weight.grad, "dW0 bf16", 1e-3)
+    tr.close()
+    trb.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
-        print("SHARDED_OK", float(loss), float(l_train), "exchange=" + ("peer" if tr.px is not None else "nccl"))
+        print("SHARDED_OK", float(loss), float(l_train), "exchange=peer-fabric")
 
 
 if __name__ == "__main__":

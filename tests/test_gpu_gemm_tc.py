@@ -116,3 +116,56 @@ def test_projection_backward_multi_head(n, heads):
     for name, a, b, r in zip(("dx", "dW", "da_src", "da_dst"), outs[lib.GEMM_TF32X3], outs[lib.GEMM_FP32], ref):
         assert _err(b, r) < 1e-5, (name, "fp32", _err(b, r))
         assert _err(a, r) < 1e-5, (name, "tc", _err(a, r))
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("n", [1, 129, 20011])
+@pytest.mark.parametrize("f_in,channels,heads", [(128, 128, 1), (128, 128, 4), (256, 256, 4), (256, 128, 2), (128, 256, 1)])
+def test_bf16_projection_forward_and_backward(n, f_in, channels, heads):
+    """The bf16 tcgen05 GEMM (gemm_bf16.cu) at every supported shape -- K = 128 / 256 forward, K = heads * channels up to 1024 in
+    the all-heads dx -- against fp64 arithmetic on the bf16-ROUNDED operands (that isolates the kernel from the rounding the
+    tier allows), plus the fp32-accurate dW / da tiles."""
+    from b200gat import _lib as lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(n + f_in + channels + heads)
+    hc = heads * channels
+    x = torch.randn(n, f_in, device=dev)
+    W = torch.randn(hc, f_in, device=dev) * 0.1
+    a_s, a_d = torch.randn(heads, channels, device=dev), torch.randn(heads, channels, device=dev)
+    wsb = lib.dense_workspace_bytes(heads, channels, f_in)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    h = torch.empty(n, hc, dtype=torch.bfloat16, device=dev)
+    s = torch.empty(n, 2 * heads, device=dev)
+    lib.call("b200gat_project_bf16", lib.ptr(x), lib.ptr(W), lib.ptr(a_s), lib.ptr(a_d), n, f_in, heads, channels, lib.ptr(h), lib.ptr(s),
+             lib.ptr(ws), wsb, lib.stream())
+    torch.cuda.synchronize()
+    xr, Wr = _bf16_round(x).cpu(), _bf16_round(W).cpu()
+    h_ref = xr @ Wr.t()
+    hv = h_ref.view(n, heads, channels)
+    s_ref = torch.cat([(hv * a_s.double().cpu()).sum(-1), (hv * a_d.double().cpu()).sum(-1)], dim=1)
+    assert _err(h.float(), h_ref) < 5e-3, _err(h.float(), h_ref)          # stored as bf16: 2^-9 relative
+    assert _err(s, s_ref) < 1e-5, _err(s, s_ref)                          # taken from the fp32 accumulator
+    dh = torch.randn(n, hc, device=dev)
+    ds = torch.randn(n, 2 * heads, device=dev)
+    dx = torch.empty(n, f_in, device=dev)
+    dW, da_s, da_d = torch.empty_like(W), torch.empty_like(a_s), torch.empty_like(a_d)
+    dh_before = dh.clone()
+    lib.call("b200gat_project_bwd_bf16", lib.ptr(x), lib.ptr(W), lib.ptr(a_s), lib.ptr(a_d), lib.ptr(dh), lib.ptr(ds), n, f_in, heads,
+             channels, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d), lib.ptr(ws), wsb, lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dh, dh_before), "dh must not be modified"
+    x64, W64, dh64, ds64 = (t.double().cpu() for t in (x, W, dh, ds))
+    dhf = (dh64.view(n, heads, channels) + ds64[:, :heads, None] * a_s.double().cpu() + ds64[:, heads:, None] * a_d.double().cpu())
+    dhf = dhf.reshape(n, hc)
+    # the kernel rounds dh_full (formed in fp32) and W to bf16; an fp32-vs-fp64 difference in forming dh_full flips the bf16
+    # rounding of a few elements (one bf16 ulp each), which shows up at ~1e-4 of max|dx| -- a wrong tile or K block would be O(1)
+    dx_ref = _bf16_round(dhf.float()) @ Wr
+    assert _err(dx, dx_ref) < 1e-3, _err(dx, dx_ref)
+    assert _err(dx, dhf @ W64) < 2e-2                                       # and the bf16 tier's tolerance against unrounded truth
+    h64 = (x64 @ W64.t()).view(n, heads, channels)
+    assert _err(dW, dhf.t() @ x64) < 1e-5, _err(dW, dhf.t() @ x64)
+    assert _err(da_s, (h64 * ds64[:, :heads, None]).sum(0)) < 1e-5
+    assert _err(da_d, (h64 * ds64[:, heads:, None]).sum(0)) < 1e-5

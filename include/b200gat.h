@@ -99,6 +99,15 @@ int b200gat_project_bf16(const float* x, const float* W, const float* a_src, con
 int b200gat_project_bwd_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
                              const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx, float* dW,
                              float* da_src, float* da_dst, void* workspace, size_t workspace_bytes, void* stream);
+/* _ex forms for the sharded / streaming path: x may already be stored as bf16 (x_is_bf16; the exchanged layer inputs of the
+ * bf16 tier), and dx may accumulate (one call per head into the same dx). */
+int b200gat_project_bf16_ex(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                            int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int b200gat_project_bwd_bf16_ex(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst,
+                                const float* dh, const float* ds, int64_t n_rows, int in_features, int heads, int channels,
+                                float* dx, int accumulate_dx, float* dW, float* da_src, float* da_dst, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* Backward of (2).  `dh` holds the aggregation part on entry and may be overwritten with the full
  * gradient of h (adds ds_src*a_src + ds_dst*a_dst); ds = [ds_src | ds_dst] [n_rows, 2*heads].

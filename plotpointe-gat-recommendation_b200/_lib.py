@@ -57,6 +57,9 @@ _SIGS = {
                                       _P, _P, _P, c_float, c_uint64, _P]),
     "b200gat_edge_bwd_bf16": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int,
                                       c_float, _P, _P, _P, c_int, c_float, c_uint64, _P]),
+    "b200gat_project_bf16_ex": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "b200gat_project_bwd_bf16_ex": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P,
+                                            c_size_t, _P]),
     "b200gat_edge_fwd_stream_f32": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
                                             c_float, c_uint64, c_float, c_int, _P]),
     "b200gat_edge_fwd_stream_bf16": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,

@@ -49,7 +49,7 @@ __global__ void build_image_kernel(const float* __restrict__ w, int64_t ldn, int
 }
 
 struct Params {
-  const float* a;          // [n_rows, lda] fp32 (x, or dh for DX)
+  const void* a;           // [n_rows, lda]: fp32 (x, or dh for DX), or bf16 x when the kernel is instantiated with A16
   int64_t lda;
   const uint8_t* image;    // B image, see build_image_kernel
   int K;                   // contraction length (multiple of 64)
@@ -65,10 +65,12 @@ struct Params {
   int64_t ldo;
   const float* att_src;    // FWD: [heads, NT]   DX: [heads * C]
   const float* att_dst;
+  int accumulate;          // DX: out += result (per-head streaming: one launch per head into the same dx)
 };
 
-// FLAVOR 0: FWD (bf16 out + logits, blockIdx.y = head / column tile), 1: DX (fp32 out, A corrected on the fly)
-template <int NT, int FLAVOR>
+// FLAVOR 0: FWD (bf16 out + logits, blockIdx.y = head / column tile), 1: DX (fp32 out, A corrected on the fly).
+// A16: the A operand is already bf16 in memory (the exchanged layer input of the sharded bf16 tier): staged without conversion.
+template <int NT, int FLAVOR, bool A16 = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(Params p) {
   constexpr bool DX = FLAVOR == 1;
   constexpr int kBStage = NT * 128;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(Params p) {
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_it = my_tiles * n_kb;
     const uint8_t* img = p.image + (size_t)tile_n * n_kb * kBStage;
-    struct Ld { float4 v[R][2]; float d[R][2]; };
+    struct Ld { float4 v[R][2]; float d[R][2]; };     // A16: v[i][0] holds the 8 bf16 values as raw bits
     auto load = [&](int64_t it, Ld& L) {
       const int64_t row0 = (blockIdx.x + (it / n_kb) * gridDim.x) * kTileM;
       const int kb = (int)(it % n_kb);
@@ -123,9 +125,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(Params p) {
       for (int i = 0; i < R; ++i) {
         const int64_t row = row0 + r0 + 32 * i;
         if (row < p.n_rows) {
-          const float* src = p.a + row * p.lda + kb * kKB + chunk * 8;
-          L.v[i][0] = ld_stream4(src);
-          L.v[i][1] = ld_stream4(src + 4);
+          if (A16) {
+            L.v[i][0] = ld_stream4(reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(p.a) + row * p.lda + kb * kKB + chunk * 8));
+          } else {
+            const float* src = reinterpret_cast<const float*>(p.a) + row * p.lda + kb * kKB + chunk * 8;
+            L.v[i][0] = ld_stream4(src);
+            L.v[i][1] = ld_stream4(src + 4);
+          }
           if (DX) {
             const int head = (kb * kKB) / p.channels;
             L.d[i][0] = __ldg(p.ds + row * (2 * p.heads) + head);
@@ -161,7 +167,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(Params p) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < R; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + 32 * i, chunk)) = pack8_bf16(L.v[i][0], L.v[i][1]);
+      for (int i = 0; i < R; ++i) {
+        uint4 pk;
+        if (A16) pk = make_uint4(__float_as_uint(L.v[i][0].x), __float_as_uint(L.v[i][0].y), __float_as_uint(L.v[i][0].z), __float_as_uint(L.v[i][0].w));
+        else pk = pack8_bf16(L.v[i][0], L.v[i][1]);
+        *reinterpret_cast<uint4*>(dst + sw128(r0 + 32 * i, chunk)) = pk;
+      }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * stage);
     };
@@ -224,7 +235,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(Params p) {
         } else if (row < p.n_rows) {   // 128 contiguous bytes of this thread's row
           float* o = p.out_f32 + row * p.ldo + (int64_t)tile_n * NT + c * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) st_stream4(o + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j) {
+            float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.accumulate) {
+              const float4 prev = ld_stream4(o + 4 * j);
+              r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+            }
+            st_stream4(o + 4 * j, r);
+          }
         }
       }
       tc_fence_before();
@@ -249,6 +267,8 @@ static int ensure_attrs() {
   B200GAT_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
   B200GAT_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
   B200GAT_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
+  B200GAT_CUDA(cudaFuncSetAttribute((gemm_bf16_kernel<128, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
+  B200GAT_CUDA(cudaFuncSetAttribute((gemm_bf16_kernel<256, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
   once.done();
   return kOk;
 }
@@ -263,8 +283,8 @@ size_t bf16_gemm_workspace_bytes(int in_features, int heads, int channels) {
 }
 
 // h_bf16 [n, H*C] = bf16(x) bf16(W)^T, s = fp32 row dots of the accumulator with a_src / a_dst
-int bf16_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F, int H, int C,
-                     void* h_bf16, float* s, void* workspace, cudaStream_t st) {
+int bf16_project_fwd(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F, int H,
+                     int C, void* h_bf16, float* s, void* workspace, cudaStream_t st) {
   int rc = tcb::ensure_attrs();
   if (rc) return rc;
   uint8_t* image = (uint8_t*)workspace;
@@ -276,15 +296,17 @@ int bf16_project_fwd(const float* x, const float* W, const float* a_src, const f
   const int64_t n_tiles = (n_rows + 127) / 128;
   const int per = kNumSMs / H > 0 ? kNumSMs / H : 1;
   dim3 grid((unsigned)(n_tiles < per ? n_tiles : per), H);
-  if (C == 128) count_launch(), tcb::gemm_bf16_kernel<128, 0><<<grid, tcb::kThreads, tcb::smem_bytes<128>(), st>>>(p);
-  else count_launch(), tcb::gemm_bf16_kernel<256, 0><<<grid, tcb::kThreads, tcb::smem_bytes<256>(), st>>>(p);
+  if (C == 128 && !x_is_bf16) count_launch(), tcb::gemm_bf16_kernel<128, 0><<<grid, tcb::kThreads, tcb::smem_bytes<128>(), st>>>(p);
+  else if (C == 128) count_launch(), tcb::gemm_bf16_kernel<128, 0, true><<<grid, tcb::kThreads, tcb::smem_bytes<128>(), st>>>(p);
+  else if (!x_is_bf16) count_launch(), tcb::gemm_bf16_kernel<256, 0><<<grid, tcb::kThreads, tcb::smem_bytes<256>(), st>>>(p);
+  else count_launch(), tcb::gemm_bf16_kernel<256, 0, true><<<grid, tcb::kThreads, tcb::smem_bytes<256>(), st>>>(p);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }
 
 // dx[n, F] = (dh + ds_src (x) a_src + ds_dst (x) a_dst)[n, H*C] . W[H*C, F], operands rounded to bf16, fp32 accumulation
 int bf16_project_dx(const float* dh, const float* ds, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F,
-                    int H, int C, float* dx, void* workspace, cudaStream_t st) {
+                    int H, int C, float* dx, int accumulate, void* workspace, cudaStream_t st) {
   int rc = tcb::ensure_attrs();
   if (rc) return rc;
   uint8_t* image = (uint8_t*)workspace;
@@ -293,7 +315,7 @@ int bf16_project_dx(const float* dh, const float* ds, const float* W, const floa
   count_launch(), tcb::build_image_kernel<<<ceil_div((int64_t)F * HC / 8, 256), 256, 0, st>>>(W, 1, F, F, HC, F, image);
   tcb::Params p{};
   p.a = dh; p.lda = HC; p.image = image; p.K = HC; p.n_rows = n_rows; p.out_f32 = dx; p.ds = ds; p.heads = H; p.channels = C;
-  p.ldo = F; p.att_src = a_src; p.att_dst = a_dst;
+  p.ldo = F; p.att_src = a_src; p.att_dst = a_dst; p.accumulate = accumulate;
   const int64_t n_tiles = (n_rows + 127) / 128;
   dim3 grid((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1);
   if (F == 128) count_launch(), tcb::gemm_bf16_kernel<128, 1><<<grid, tcb::kThreads, tcb::smem_bytes<128>(), st>>>(p);

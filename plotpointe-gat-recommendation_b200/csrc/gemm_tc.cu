@@ -493,8 +493,9 @@ struct DwParams {
   int64_t ld_dh;
   const float* ds;   // [n_rows, ds_ld], columns ds_src_col / ds_dst_col
   int ds_ld, ds_src_col, ds_dst_col;
-  const float* x;    // [n_rows, ld_x], this launch's 128 columns
-  int64_t ld_x;
+  const void* x;     // [n_rows, ld_x], this launch's 128 columns; fp32, or bf16 when x_bf16 (the sharded bf16 tier keeps the
+  int64_t ld_x;      // layer inputs it exchanges as bf16)
+  int x_bf16;
   const float* att_src;
   const float* att_dst;
   int64_t n_rows;
@@ -563,7 +564,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
         const int64_t row = row0 + warp + 8 * i;
         if (row < r_end) {
           L.g[i] = ld_stream4(p.dh + row * p.ld_dh + c4 * 4);
-          L.xv[i] = ld_stream4(p.x + row * p.ld_x + c4 * 4);
+          if (p.x_bf16) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ld_x + c4 * 4));
+            L.xv[i] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                                  __uint_as_float(raw.y & 0xffff0000u));
+          } else {
+            L.xv[i] = ld_stream4(reinterpret_cast<const float*>(p.x) + row * p.ld_x + c4 * 4);
+          }
           L.d0[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_src_col) : 0.f;
           L.d1[i] = p.ds ? __ldg(p.ds + row * p.ds_ld + p.ds_dst_col) : 0.f;
         } else {
@@ -859,8 +866,8 @@ int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, voi
 size_t tc_dw_tiles_workspace_bytes(int heads, int in_features) {
   return (size_t)kNumSMs * (128 * 128 + 2 * 128) * sizeof(float) + (size_t)2 * heads * in_features * sizeof(float) + 1024;
 }
-int tc_project_dw_tiles(const float* x, const float* a_src, const float* a_dst, const float* dh, const float* ds, int64_t n_rows,
-                        int F, int H, int C, float* dW, float* v /*[2H, F]*/, void* workspace, cudaStream_t st) {
+int tc_project_dw_tiles(const void* x, int x_is_bf16, const float* a_src, const float* a_dst, const float* dh, const float* ds,
+                        int64_t n_rows, int F, int H, int C, float* dW, float* v /*[2H, F]*/, void* workspace, cudaStream_t st) {
   int rc = ensure_attrs();
   if (rc) return rc;
   float* part_dw = (float*)workspace;
@@ -875,7 +882,8 @@ int tc_project_dw_tiles(const float* x, const float* a_src, const float* a_dst, 
     for (int ft = 0; ft < F / 128; ++ft) {
       tc::DwParams q{};
       q.dh = dh + mt * 128; q.ld_dh = HC; q.ds = ds; q.ds_ld = 2 * H; q.ds_src_col = hh; q.ds_dst_col = H + hh;
-      q.x = x + ft * 128; q.ld_x = F; q.att_src = a_src + mt * 128; q.att_dst = a_dst + mt * 128; q.n_rows = n_rows;
+      q.x = x_is_bf16 ? (const void*)((const __nv_bfloat16*)x + ft * 128) : (const void*)((const float*)x + ft * 128);
+      q.x_bf16 = x_is_bf16; q.ld_x = F; q.att_src = a_src + mt * 128; q.att_dst = a_dst + mt * 128; q.n_rows = n_rows;
       q.rows_per_cta = per;
       q.part_dw = part_dw; q.part_v = first_of_head ? part_v : nullptr;
       count_launch(), tc::proj_dw_kernel<<<grid, tc::kDwThreads, tc::kDwSmem, st>>>(q);
@@ -896,18 +904,18 @@ int tc_project_dw_tiles(const float* x, const float* a_src, const float* a_dst, 
 namespace b200gat {  // gemm_bf16.cu, dense_simt.cu
 bool bf16_gemm_supported(int in_features, int heads, int channels);
 size_t bf16_gemm_workspace_bytes(int in_features, int heads, int channels);
-int bf16_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F, int H, int C,
-                     void* h_bf16, float* s, void* workspace, cudaStream_t st);
+int bf16_project_fwd(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F, int H,
+                     int C, void* h_bf16, float* s, void* workspace, cudaStream_t st);
 int bf16_project_dx(const float* dh, const float* ds, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int F,
-                    int H, int C, float* dx, void* workspace, cudaStream_t st);
+                    int H, int C, float* dx, int accumulate, void* workspace, cudaStream_t st);
 int att_grad_launch(const float* W, const float* v, int H, int C, int F, float* da_src, float* da_dst, cudaStream_t st);
 }  // namespace b200gat
 
 // h_bf16 [n, heads*C] = bf16(x) bf16(W)^T (fp32 accumulate), s = fp32 row dots of the accumulator with a_src / a_dst.
-// in_features and channels in {128, 256}, heads * channels <= 1024.
-extern "C" int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
-                                    int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+// in_features and channels in {128, 256}, heads * channels <= 1024.  x_is_bf16: x is already stored as bf16.
+extern "C" int b200gat_project_bf16_ex(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst,
+                                       int64_t n_rows, int in_features, int heads, int channels, void* h_bf16, float* s,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
   using namespace b200gat;
   B200GAT_CHECK_ARG(x && W && a_src && a_dst && h_bf16 && s && workspace, "null pointer");
   if (!bf16_gemm_supported(in_features, heads, channels)) {
@@ -917,16 +925,22 @@ extern "C" int b200gat_project_bf16(const float* x, const float* W, const float*
   }
   B200GAT_CHECK_ARG(workspace_bytes >= bf16_gemm_workspace_bytes(in_features, heads, channels), "workspace too small");
   if (n_rows == 0) return kOk;
-  return bf16_project_fwd(x, W, a_src, a_dst, n_rows, in_features, heads, channels, h_bf16, s, workspace, (cudaStream_t)stream);
+  return bf16_project_fwd(x, x_is_bf16, W, a_src, a_dst, n_rows, in_features, heads, channels, h_bf16, s, workspace, (cudaStream_t)stream);
+}
+extern "C" int b200gat_project_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                                    int in_features, int heads, int channels, void* h_bf16, float* s, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return b200gat_project_bf16_ex(x, 0, W, a_src, a_dst, n_rows, in_features, heads, channels, h_bf16, s, workspace, workspace_bytes, stream);
 }
 
 // Backward of the bf16 projection: dx = dh_full W (one bf16 tensor-core launch over all heads, K = heads * channels),
 // dW = dh_full^T x (fp32-accurate TF32-split tiles), da_src / da_dst; dh_full = dh + ds_src (x) a_src + ds_dst (x) a_dst is formed
-// on the fly (dh is not modified).  Same shape limits as b200gat_project_bf16.
-extern "C" int b200gat_project_bwd_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
-                                        const float* ds, int64_t n_rows, int in_features, int heads, int channels,
-                                        float* dx /*nullable*/, float* dW, float* da_src, float* da_dst, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+// on the fly (dh is not modified).  Same shape limits as b200gat_project_bf16.  _ex: x may be stored as bf16, and dx may
+// accumulate (per-head streaming: one call per head into the same dx).
+extern "C" int b200gat_project_bwd_bf16_ex(const void* x, int x_is_bf16, const float* W, const float* a_src, const float* a_dst,
+                                           const float* dh, const float* ds, int64_t n_rows, int in_features, int heads,
+                                           int channels, float* dx /*nullable*/, int accumulate_dx, float* dW, float* da_src,
+                                           float* da_dst, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace b200gat;
   B200GAT_CHECK_ARG(x && W && a_src && a_dst && dh && ds && dW && da_src && da_dst && workspace, "null pointer");
   if (!bf16_gemm_supported(in_features, heads, channels)) {
@@ -946,14 +960,21 @@ extern "C" int b200gat_project_bwd_bf16(const float* x, const float* W, const fl
   }
   int rc;
   if (dx) {
-    rc = bf16_project_dx(dh, ds, W, a_src, a_dst, n_rows, in_features, heads, channels, dx, workspace, st);
+    rc = bf16_project_dx(dh, ds, W, a_src, a_dst, n_rows, in_features, heads, channels, dx, accumulate_dx, workspace, st);
     if (rc) return rc;
   }
   char* ws2 = (char*)workspace + img;
   float* v = (float*)(ws2 + (size_t)kNumSMs * (128 * 128 + 2 * 128) * sizeof(float));
-  rc = tc_project_dw_tiles(x, a_src, a_dst, dh, ds, n_rows, in_features, heads, channels, dW, v, ws2, st);
+  rc = tc_project_dw_tiles(x, x_is_bf16, a_src, a_dst, dh, ds, n_rows, in_features, heads, channels, dW, v, ws2, st);
   if (rc) return rc;
   return att_grad_launch(W, v, heads, channels, in_features, da_src, da_dst, st);
+}
+extern "C" int b200gat_project_bwd_bf16(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
+                                        const float* ds, int64_t n_rows, int in_features, int heads, int channels,
+                                        float* dx /*nullable*/, float* dW, float* da_src, float* da_dst, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return b200gat_project_bwd_bf16_ex(x, 0, W, a_src, a_dst, dh, ds, n_rows, in_features, heads, channels, dx, 0, dW, da_src, da_dst,
+                                     workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200gat_set_gemm_mode(int mode) {

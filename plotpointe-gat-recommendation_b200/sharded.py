@@ -256,10 +256,12 @@ class ShardedGAT:
     def __init__(self, kind: str, n_users: int, n_items: int, item_feats: torch.Tensor, edge_index: torch.Tensor,
                  hidden: int = 128, layers: int = 2, heads: int = 1, attn_dropout: float = 0.1, seed: int = 42,
                  lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None,
-                 feature_dtype=torch.float32, n_triples_max: int = 200_000):
+                 feature_dtype=torch.float32, n_triples_max: int = 200_000, stream_heads: bool = False):
         from . import _lib
         if feature_dtype not in (torch.float32, torch.bfloat16):
             raise NotImplementedError("feature_dtype must be float32 or bfloat16")
+        if stream_heads and (kind != "pyg" or feature_dtype != torch.bfloat16):
+            raise NotImplementedError("stream_heads is the bf16-tier PyG-dialect path (BASELINE config 5)")
         self.bf16 = feature_dtype == torch.bfloat16   # bf16 projection: h and the gathered dout travel (and are stored) as bf16
         from .graph import build_graph
         from .modules import CustomGAT, PyGGAT
@@ -293,6 +295,11 @@ class ShardedGAT:
         self.node_map = plan.perm_map.to(torch.int32).contiguous()
         self.node_list = plan.local_nodes.to(torch.int32).contiguous()
         del ei, ei_p
+        # the forward uses the CSR side of its sub-graph only, the backward the CSC side (+ the CSR row pointers and the
+        # CSR->CSC map for the per-destination sums): drop the rest (8 x 4 B per edge of config 5's 800 M edges)
+        self.g_fwd.row = self.g_fwd.perm_csc = self.g_fwd.csr2csc = self.g_fwd.perm = None
+        self.g_bwd.col = self.g_bwd.perm = self.g_bwd.perm_csc = None
+        self.g_fwd.sched_fwd = self.g_fwd.sched_bwd = self.g_bwd.sched_fwd = self.g_bwd.sched_bwd = None
 
         torch.manual_seed(seed)
         full = (CustomGAT(n_users, n_items, self.feat_dim, hidden, layers) if kind == "custom"
@@ -319,10 +326,18 @@ class ShardedGAT:
         # ---- exchange buffer: regions and channels
         H, C, L, n_max, n_pad = self.heads, hidden, layers, self.n_max, self.n_pad
         self.x_exchange = H > 1                  # heads > 1: move the layer input (F_in wide), project all rows on every rank
+        self.stream = bool(stream_heads)
         hsz = 2 if self.bf16 else 4
         self.s_max = int(n_triples_max)
         regions: Dict[str, int] = {}
-        for l in range(L):
+        if self.stream:
+            # per-head streaming (config 5): two alternating bf16 regions for the gathered layer inputs (the idle one holds the
+            # gathered dout in the backward), one head's nodestat and per-destination partial sums at a time
+            regions["X0"] = n_pad * C * 2
+            regions["X1"] = n_pad * C * 2
+            regions["NSh"] = n_pad * 16
+            regions["DSDh"] = n_pad * 4
+        for l in range(L if not self.stream else 0):
             regions[f"F{l}"] = n_pad * (C * 4 if self.x_exchange else H * C * hsz)
             if not self.x_exchange:
                 regions[f"S{l}"] = n_pad * 2 * H * 4
@@ -338,7 +353,8 @@ class ShardedGAT:
         self.CH_B = lambda l: L + 2 + l
         self.CH_R = lambda l: 2 * L + 2 + l
         self.CH_G = 3 * L + 2
-        self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 3, regions)
+        self.CH_HA, self.CH_HR1, self.CH_HB, self.CH_HR2 = 3 * L + 3, 3 * L + 4, 3 * L + 5, 3 * L + 6   # per-head rounds (streaming)
+        self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 7, regions)
         self.comm_bytes_per_step = 0            # bytes this rank pulls from its peers per training step
         self.comm_now = 0
         self._loss_ws = None
@@ -369,6 +385,8 @@ class ShardedGAT:
     def forward(self, _exchange_follows: bool = False) -> torch.Tensor:
         """Returns the local rows of Z ([n_max, C], the first n_loc are real; lives in the exchange buffer); keeps what the
         backward needs in ``self.saved``."""
+        if self.stream:
+            return self._forward_stream(_exchange_follows)
         lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
         st = lib.stream()
         L = self.n_layers
@@ -431,6 +449,150 @@ class ShardedGAT:
             fab.wait(self.CH_Z)
         return x
 
+    # -------------------------------------------------------------------------------------------- per-head streaming
+    def _x0_bf16(self, dst: torch.Tensor) -> None:
+        """Layer-0 input rows [user rows | item_proj(features)] as bf16 into ``dst`` [n_max, C] (recomputed in the backward
+        instead of being kept: it is a function of parameters and inputs only)."""
+        lib, C = self._lib, self.hidden
+        st = lib.stream()
+        cu = self.plan.cu
+        x = self._empty(self.n_max, C)
+        x[:cu].copy_(self.user_emb.detach())
+        dwb = lib.dense_workspace_bytes(1, C, max(C, self.feat_dim))
+        dws = self._empty(dwb, dtype=torch.uint8)
+        if self.plan.ci:
+            lib.call("b200gat_linear_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
+                     self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
+        lib.call("b200gat_cast_bf16", lib.ptr(x), lib.ptr(dst), self.n_max * C, 1.0, st)
+
+    def _forward_stream(self, _exchange_follows: bool) -> torch.Tensor:
+        """heads > 1 one head at a time: [N, heads*C] never exists.  Per layer: the bf16 input rows are exchanged once, then for
+        every head the projection of ALL rows (h_head [N, C] bf16, reused buffer) and the fused edge forward of the local rows,
+        which accumulates the head mean into ``out``.  Saved for the backward: the layer input rows (bf16, layers > 0), and per
+        head the per-node scalars s and rowstat."""
+        lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
+        st = lib.stream()
+        L = self.n_layers
+        self.comm_now = 0
+        blk = self.n_max * C * 2
+        xb = fab.view("X0", (self.n_max, C), torch.bfloat16, self.rank * blk)
+        self._x0_bf16(xb)
+        self.saved = []
+        p = self.p_drop if self.training else 0.0
+        dwb = lib.dense_workspace_bytes(1, C, C)
+        dws = self._empty(dwb, dtype=torch.uint8)
+        h_head = self._empty(self.n_pad, C, dtype=torch.bfloat16)
+        sf = self.sched_fwd
+        for l in range(L):
+            reg = f"X{l % 2}"
+            fab.signal(self.CH_F(l))
+            parts = [(reg, blk)]
+            fab.allgather(self.CH_F(l), parts)
+            self._pulled(parts)
+            x_full = fab.view(reg, (self.n_pad, C), torch.bfloat16)
+            x_keep = None if l == 0 else fab.view(reg, (self.n_max, C), torch.bfloat16, self.rank * blk).clone()
+            last = l == L - 1
+            out = fab.view("Z", (self.n_max, C), torch.float32) if last else self._empty(self.n_max, C)
+            seed = self._layer_seed(l)
+            s_heads, rs_heads = [], []
+            for hh in range(H):
+                s_h = self._empty(self.n_pad, 2)
+                rs_h = self._empty(self.n_loc, 2)
+                lib.call("b200gat_project_bf16_ex", lib.ptr(x_full), 1, lib.ptr(self.W[l], hh * C * C), lib.ptr(self.a_src[l], hh * C),
+                         lib.ptr(self.a_dst[l], hh * C), self.n_pad, C, 1, C, lib.ptr(h_head), lib.ptr(s_h), lib.ptr(dws), dwb, st)
+                lib.call("b200gat_edge_fwd_stream_bf16", lib.ptr(h_head), lib.ptr(s_h), lib.ptr(sf.sched), sf.n_sched, lib.ptr(sf.table),
+                         sf.n_long, lib.ptr(sf.partial(C + 4)), lib.ptr(self.g_fwd.col), lib.ptr(self.perm_fwd), self.plan.lo, C,
+                         self.policy, 0.2, lib.ptr(self.bias[l]) if hh == 0 else None, lib.ptr(out), lib.ptr(rs_h), p, seed + 7919 * hh,
+                         1.0 / H, int(hh > 0), st)
+                s_heads.append(s_h)
+                rs_heads.append(rs_h)
+            self.saved.append((x_keep, s_heads, rs_heads, p, seed))
+            if not last:        # the next layer's input rows, bf16, straight into the other region's block
+                nxt = fab.view(f"X{(l + 1) % 2}", (self.n_max, C), torch.bfloat16, self.rank * blk)
+                lib.call("b200gat_cast_bf16", lib.ptr(out), lib.ptr(nxt), self.n_max * C, 1.0, st)
+        del h_head
+        if not _exchange_follows and self.world > 1:
+            fab.signal(self.CH_Z)
+            fab.wait(self.CH_Z)
+        return out
+
+    def _backward_stream(self, dout: torch.Tensor, grads: dict) -> torch.Tensor:
+        """Backward of the streamed layers.  Nothing per-head was kept but scalars: h of the local source rows is re-projected
+        per head, and t_i = sum_k alpha_ik dalpha_ik comes out of a first pass over the edges (two-phase backward, edge.cu)."""
+        lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
+        st = lib.stream()
+        L, lo, P_ = self.n_layers, self.plan.lo, self.world
+        blk = self.n_max * C * 2
+        dwb = lib.dense_workspace_bytes(1, C, C)
+        dws = self._empty(dwb, dtype=torch.uint8)
+        sb = self.sched_bwd
+        e_loc = max(self.g_bwd.n_edges, 1)
+        for l in reversed(range(L)):
+            x_keep, s_heads, rs_heads, p, seed = self.saved[l]
+            if x_keep is None:
+                x_keep = self._empty(self.n_max, C, dtype=torch.bfloat16)
+                self._x0_bf16(x_keep)
+            db = torch.empty_like(self.bias[l])
+            lib.call("b200gat_colsum_f32", lib.ptr(dout), self.n_loc, C, lib.ptr(db), lib.ptr(dws), dwb, st)
+            grads[self.bias[l]] = db
+            # gathered dout, bf16, already carrying the 1/heads of the head mean (exact: a power of two)
+            dg = fab.view("X0", (self.n_max, C), torch.bfloat16, self.rank * blk)
+            lib.call("b200gat_cast_bf16", lib.ptr(dout), lib.ptr(dg), self.n_max * C, 1.0 / H, st)
+            fab.signal(self.CH_B(l))
+            parts = [("X0", blk)]
+            fab.allgather(self.CH_B(l), parts)
+            self._pulled(parts)
+            dout_full = fab.view("X0", (self.n_pad, C), torch.bfloat16)
+            dx = self._empty(self.n_max, C)
+            dW = torch.empty_like(self.W[l])
+            da_s, da_d = torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
+            h_loc = self._empty(self.n_loc, C, dtype=torch.bfloat16)
+            s_tmp = self._empty(self.n_loc, 2)
+            dh = self._empty(self.n_loc, C)
+            de = self._empty(e_loc)
+            ds = self._empty(self.n_loc, 2)
+            red = self._empty(max(self.n_loc, 1))
+            ns_blk = fab.view("NSh", (self.n_max, 4), torch.float32, self.rank * self.n_max * 16)
+            ns_full = fab.view("NSh", (self.n_pad, 4), torch.float32)
+            part = fab.view("DSDh", (self.n_pad,), torch.float32)
+            ns_parts = [("NSh", self.n_max * 16)]
+            for hh in range(H):
+                s_h, rs_h = s_heads[hh], rs_heads[hh]
+                W_h, as_h, ad_h = lib.ptr(self.W[l], hh * C * C), lib.ptr(self.a_src[l], hh * C), lib.ptr(self.a_dst[l], hh * C)
+                lib.call("b200gat_project_bf16_ex", lib.ptr(x_keep), 1, W_h, as_h, ad_h, self.n_loc, C, 1, C, lib.ptr(h_loc), lib.ptr(s_tmp),
+                         lib.ptr(dws), dwb, st)
+                lib.call("b200gat_node_stat_f32", lib.ptr(s_h), lib.ptr(rs_h), self.n_loc, lo, 1, lib.ptr(ns_blk), st)
+                fab.signal(self.CH_HA)
+                fab.allgather(self.CH_HA, ns_parts)
+                self._pulled(ns_parts)
+                # the kernels index h by gathered row (row_offset + r): hand them the local block shifted back by row_offset rows
+                lib.call("b200gat_edge_bwd_phase1_bf16", lib.ptr(h_loc, -lo * C), lib.ptr(s_h), lib.ptr(dout_full), lib.ptr(ns_full),
+                         lib.ptr(sb.sched), sb.n_sched, lib.ptr(sb.table), sb.n_long, lib.ptr(sb.partial(C + 4)), lib.ptr(self.g_bwd.row),
+                         lib.ptr(self.perm_bwd), lo, C, self.policy, 0.2, lib.ptr(dh), lib.ptr(de), lib.ptr(ds), 2, p, seed + 7919 * hh, st)
+                lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad,
+                         self.g_bwd.n_edges, 1, lib.ptr(part), 1, st)
+                fab.signal(self.CH_HR1)
+                fab.reduce(self.CH_HR1, "DSDh", lo, self.n_loc, red)                   # t of the local destinations
+                lib.call("b200gat_node_stat_set_t_f32", lib.ptr(ns_blk), lib.ptr(red), self.n_loc, st)
+                fab.signal(self.CH_HB)
+                fab.allgather(self.CH_HB, ns_parts)
+                self._pulled(ns_parts)
+                lib.call("b200gat_edge_bwd_phase2_f32", lib.ptr(de), lib.ptr(self.g_bwd.colptr), lib.ptr(self.g_bwd.row), lib.ptr(s_h),
+                         lib.ptr(ns_full), self.n_loc, lo, self.policy, 0.2, lib.ptr(ds), 2, st)
+                lib.call("b200gat_ds_dst_f32", lib.ptr(de), lib.ptr(self.g_bwd.rowptr), lib.ptr(self.g_bwd.csr2csc), self.n_pad,
+                         self.g_bwd.n_edges, 1, lib.ptr(part), 1, st)
+                fab.signal(self.CH_HR2)
+                fab.reduce(self.CH_HR2, "DSDh", lo, self.n_loc, red)
+                self.comm_now += 2 * self.n_loc * 4 * (P_ - 1)
+                ds[:, 1] = red[:self.n_loc]
+                lib.call("b200gat_project_bwd_bf16_ex", lib.ptr(x_keep), 1, W_h, as_h, ad_h, lib.ptr(dh), lib.ptr(ds), self.n_loc, C, 1, C,
+                         lib.ptr(dx), int(hh > 0), lib.ptr(dW, hh * C * C), lib.ptr(da_s, hh * C), lib.ptr(da_d, hh * C),
+                         lib.ptr(dws), dwb, st)
+            grads[self.W[l]], grads[self.a_src[l]], grads[self.a_dst[l]] = dW, da_s, da_d
+            dout = dx
+            self.saved[l] = None
+        return dout
+
     # -------------------------------------------------------------------------------------------- loss + backward
     def loss_and_backward(self, z_loc: torch.Tensor, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
         lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
@@ -467,6 +629,8 @@ class ShardedGAT:
         # ---- gradient rows of this rank's nodes (partner rows again read from the owners), straight into the exchange block
         one = torch.ones(1, dtype=torch.float32, device=self.dev)
         dout = self._block(f"D{L - 1}", C, torch.float32) if not self.bf16 else self._empty(self.n_max, C)
+        if self.stream:
+            dout.zero_()                         # rows [n_loc, n_max) are cast and exchanged with the rest: keep them finite
         lib.call("b200gat_rank_loss_bwd_peer_f32", z_blocks, P_, self.n_max, self.nu, self.ni, C, lib.ptr(u), lib.ptr(i), lib.ptr(j), S,
                  lib.ptr(self.node_map), kind, lib.ptr(coef), lib.ptr(one), lib.ptr(self.node_list), self.n_loc, lib.ptr(dout), None,
                  lib.ptr(ws), ws_bytes, st)
@@ -475,7 +639,9 @@ class ShardedGAT:
         dwb = lib.dense_workspace_bytes(H, C, max(C, self.feat_dim))
         dws = self._empty(dwb, dtype=torch.uint8)
         d_dt = torch.bfloat16 if self.bf16 else torch.float32
-        for l in reversed(range(L)):
+        if self.stream:
+            dout = self._backward_stream(dout, grads)
+        for l in (reversed(range(L)) if not self.stream else ()):
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
             nodestat = self._block(f"NS{l}", H * 4, torch.float32)
             db = torch.empty_like(self.bias[l]) if self.bias[l] is not None else None

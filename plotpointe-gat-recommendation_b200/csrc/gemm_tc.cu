@@ -486,6 +486,12 @@ constexpr int kDwStages = 3;
 #define TC_DW_GROUP 2          // stages (x 32 node rows x 16 UMMAs) accumulated by the tensor core before a promotion
 #endif
 constexpr int kDwGroup = TC_DW_GROUP;
+// Only the hi*hi product is large enough for that truncation to matter: the three cross terms (2^-11 and 2^-22 of it) go
+// into a tile of their own, [384,512), which runs over all of the CTA's rows and is added once at the end.  The running
+// tiles then see one truncating accumulation per K step instead of four.
+#ifndef TC_DW_XTILE
+#define TC_DW_XTILE 1
+#endif
 constexpr int kDwSmem = 1024 + kDwStages * kDwStageBytes + kDwEpiWarps * 32 * 128 + 2 * kTileN * 4 + 256;
 
 struct DwParams {
@@ -637,10 +643,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
           const uint32_t ko = kg * 4096;
           const uint64_t dah = make_desc(a_hi + ko, 512, 2048, 1), dal = make_desc(a_lo + ko, 512, 2048, 1);
           const uint64_t dbh = make_desc(b_hi + ko, 512, 2048, 1), dbl = make_desc(b_lo + ko, 512, 2048, 1);
+#if TC_DW_XTILE
+          const uint32_t dx_ = tmem_base + 3 * kTileN;
+          umma_tf32(dx_, dal, dbl, idesc, (it | kg) != 0);
+          umma_tf32(dx_, dal, dbh, idesc, 1);
+          umma_tf32(dx_, dah, dbl, idesc, 1);
+          umma_tf32(d, dah, dbh, idesc, (in_grp | kg) != 0);
+#else
           umma_tf32(d, dal, dbl, idesc, (in_grp | kg) != 0);
           umma_tf32(d, dal, dbh, idesc, 1);
           umma_tf32(d, dah, dbl, idesc, 1);
           umma_tf32(d, dah, dbh, idesc, 1);
+#endif
         }
         umma_commit(bar_empty + 8 * stage);
         if (in_grp == kDwGroup - 1 || it == n_stages_total - 1) umma_commit(bar_tfull + 8 * buf);
@@ -687,6 +701,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) proj_dw_kernel(DwParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += acc[j];
         }
+#if TC_DW_XTILE
+        {
+          float xt[32];   // the cross terms of all rows (complete: the last group's commit covers every earlier UMMA)
+          tmem_ld32(lane_base + 3 * kTileN + c * 32, xt);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += xt[j];
+        }
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;

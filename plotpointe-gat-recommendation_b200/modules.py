@@ -4,7 +4,9 @@
 * :class:`GATConv` / :class:`PyGGAT` mirror the PyG call made at scripts/train_gat_pyg.py:68-88
 
 Constructor signatures, parameter names, shapes and initialisers are the reference's, so a ``state_dict`` saved by the
-reference trainer (``torch.save({"state_dict", "config"})``, train_gat_custom.py:376) loads here and vice versa.
+reference trainer (``torch.save({"state_dict", "config"})``, train_gat_custom.py:376) loads here and vice versa (PyG
+dialect: checkpoints are written with the PyG >= 2.5 key ``lin.weight``; the PyG <= 2.4 keys ``lin_src`` / ``lin_dst`` are
+accepted on load only).
 Only the layer forward/backward changes: it runs the sm_100a kernels behind the C ABI.
 """
 from __future__ import annotations
@@ -79,6 +81,8 @@ class GATConv(torch.nn.Module):
             self.bias = torch.nn.Parameter(torch.empty(out_channels))
         else:
             self.register_parameter("bias", None)
+        self._renamed = None
+        self.register_load_state_dict_post_hook(GATConv._restore_renamed)
         self.reset_parameters()
 
     @staticmethod
@@ -95,12 +99,23 @@ class GATConv(torch.nn.Module):
             torch.nn.init.zeros_(self.bias)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        # PyG <= 2.4 stored the shared projection as lin_src / lin_dst
-        old = prefix + "lin_src.weight"
-        if old in state_dict and prefix + "lin.weight" not in state_dict:
-            state_dict[prefix + "lin.weight"] = state_dict.pop(old)
-            state_dict.pop(prefix + "lin_dst.weight", None)
+        # PyG <= 2.4 stored the shared projection as lin_src / lin_dst (loading only: a checkpoint saved from here carries
+        # lin.weight, the PyG >= 2.5 name).  The child Linear reads the SAME dict object after this returns, so the alias is
+        # added in place and taken out again by the post hook: the caller's checkpoint dict is unchanged after the load.
+        old, dst, new = prefix + "lin_src.weight", prefix + "lin_dst.weight", prefix + "lin.weight"
+        if old in state_dict and new not in state_dict:
+            self._renamed = (state_dict, new, [(k, state_dict.pop(k)) for k in (old, dst) if k in state_dict])
+            state_dict[new] = self._renamed[2][0][1]
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    @staticmethod
+    def _restore_renamed(module, _incompatible) -> None:
+        pending, module._renamed = getattr(module, "_renamed", None), None
+        if pending is not None:
+            sd, new, olds = pending
+            sd.pop(new, None)
+            for k, v in olds:
+                sd[k] = v
 
     def forward(self, x, edge_index, edge_attr=None, size=None, return_attention_weights=None):
         if edge_attr is not None or size is not None or return_attention_weights is not None:

@@ -119,8 +119,13 @@ class PeerFabric:
     channel ``ch`` and then reads their memory.  Epochs grow by one per use; nothing is ever reset.  world == 1 keeps the same
     code path on a private buffer (the kernels degenerate to a wait on the rank's own flag)."""
 
-    def __init__(self, lib, world: int, rank: int, dev: torch.device, n_channels: int, regions: Dict[str, int]):
+    def __init__(self, lib, world: int, rank: int, dev: torch.device, n_channels: int, regions: Dict[str, int],
+                 loopback: bool = False):
+        """``loopback``: a diagnostic mode for ONE process standing in for rank ``rank`` of ``world``: every "peer" is this
+        rank's own buffer (pulls copy a block onto itself, at HBM instead of NVLink speed) and a signal raises all the flags.
+        The peers' blocks are never produced, so results are meaningless -- it exists to time one rank's kernels."""
         self.lib, self.world, self.rank, self.dev = lib, world, rank, dev
+        self.loopback = loopback
         fb = ctypes.c_size_t(0)
         lib._check(lib._lib.b200gat_peer_flag_bytes(n_channels, ctypes.byref(fb)), "peer_flag_bytes")
         self.off: Dict[str, int] = {}
@@ -138,7 +143,7 @@ class PeerFabric:
             p = ctypes.c_void_p()
             lib._check(lib._lib.b200gat_peer_alloc(self.nbytes, ctypes.byref(p)), "peer_alloc")
             self._local_ptr = p.value
-            if world > 1:
+            if world > 1 and not loopback:
                 h = ctypes.create_string_buffer(64)
                 lib._check(lib._lib.b200gat_peer_export(p, h, 64), "peer_export")
                 handle = h.raw
@@ -148,7 +153,7 @@ class PeerFabric:
         self.local = torch.as_tensor(_RawCuda(self._local_ptr, self.nbytes), device=dev)
         self.local[:fb.value].zero_()                       # flags start at 0 = "no step has signalled yet"
         ptrs = [self._local_ptr] * world
-        if world > 1:
+        if world > 1 and not loopback:
             gathered = [None] * world
             dist.all_gather_object(gathered, handle)
             ok, err = True, ""
@@ -172,7 +177,7 @@ class PeerFabric:
     def _agree(self, ok: bool, what: str) -> None:
         """All ranks or none: a rank that failed must not leave the others blocked in the next collective."""
         flag = torch.tensor([1.0 if ok else 0.0], device=self.dev)
-        if self.world > 1:
+        if self.world > 1 and not self.loopback:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() == 0:
             self.close()
@@ -208,7 +213,8 @@ class PeerFabric:
     def signal(self, ch: int) -> None:
         self.epoch[ch] += 1
         lib = self.lib
-        lib._check(lib._lib.b200gat_peer_signal(self.bases, self.world, self.rank, ch, self.epoch[ch], lib.stream()), "peer_signal")
+        for r in (range(self.world) if self.loopback else (self.rank,)):
+            lib._check(lib._lib.b200gat_peer_signal(self.bases, self.world, r, ch, self.epoch[ch], lib.stream()), "peer_signal")
 
     def wait(self, ch: int) -> None:
         lib = self.lib
@@ -256,7 +262,10 @@ class ShardedGAT:
     def __init__(self, kind: str, n_users: int, n_items: int, item_feats: torch.Tensor, edge_index: torch.Tensor,
                  hidden: int = 128, layers: int = 2, heads: int = 1, attn_dropout: float = 0.1, seed: int = 42,
                  lr: float = 1e-3, weight_decay: float = 1e-4, device: Optional[torch.device] = None,
-                 feature_dtype=torch.float32, n_triples_max: int = 200_000, stream_heads: bool = False):
+                 feature_dtype=torch.float32, n_triples_max: int = 200_000, stream_heads: bool = False,
+                 emulate: Optional[tuple] = None):
+        """``emulate=(rank, world)``: diagnostic, single process: build rank ``rank``'s plan of a ``world``-rank job and run its
+        kernels over a loopback fabric (see PeerFabric) -- for timing / profiling one rank's work on one GPU."""
         from . import _lib
         if feature_dtype not in (torch.float32, torch.bfloat16):
             raise NotImplementedError("feature_dtype must be float32 or bfloat16")
@@ -270,6 +279,9 @@ class ShardedGAT:
         self.kind = kind
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if emulate is not None:
+            assert self.world == 1, "emulate= is a single-process diagnostic"
+            self.rank, self.world = int(emulate[0]), int(emulate[1])
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.nu, self.ni, self.n = n_users, n_items, n_users + n_items
         self.hidden, self.heads, self.n_layers = hidden, (1 if kind == "custom" else heads), layers
@@ -354,7 +366,7 @@ class ShardedGAT:
         self.CH_R = lambda l: 2 * L + 2 + l
         self.CH_G = 3 * L + 2
         self.CH_HA, self.CH_HR1, self.CH_HB, self.CH_HR2 = 3 * L + 3, 3 * L + 4, 3 * L + 5, 3 * L + 6   # per-head rounds (streaming)
-        self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 7, regions)
+        self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 7, regions, loopback=emulate is not None)
         self.comm_bytes_per_step = 0            # bytes this rank pulls from its peers per training step
         self.comm_now = 0
         self._loss_ws = None
@@ -767,7 +779,7 @@ def _parity_vs_single(tr: "ShardedGAT", cfg, feats, ei, triples, rank: int, worl
     z = m(feats.to(dev), ei.to(dev))
     ref_loss = (b200gat.bpr_loss if cfg["loss"] == "bpr" else b200gat.bce_loss)(z, nu, u, i, j)
     ref_loss.backward()
-    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    rel = lambda a, b: float((a.detach().double() - b.detach().double()).abs().max() / b.detach().double().abs().max().clamp_min(1e-30))
     res = torch.tensor([rel(z_rows, z[tr.plan.local_nodes]), rel(loss, ref_loss), rel(tr.W[0].grad, lays[0].lin.weight.grad),
                         rel(tr.W[-1].grad, lays[-1].lin.weight.grad),
                         rel(tr.user_emb.grad, m.user_emb.weight.grad[rank::world]) if tr.plan.cu else 0.0], device=dev, dtype=torch.float64)
@@ -843,6 +855,9 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     # ---- communication: measured on a few extra steps with events around every exchange kernel (wait included)
+    if world > 1:
+        dist.barrier()            # rank 0 was busy with the clock sampler: start the profiled steps together
+    torch.cuda.synchronize()
     tr.fab.stats = {}
     _lib.timing = {}
     n_prof = 5

@@ -37,7 +37,7 @@ class Adam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
+                st["step"] = int(st["step"]) + 1          # a torch.optim.Adam state_dict carries the step as a tensor
                 g = p.grad.contiguous()
                 with torch.cuda.device(p.device):
                     _lib.call("b200gat_adam_step_f32", _lib.ptr(p), _lib.ptr(g), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),

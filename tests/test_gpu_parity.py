@@ -480,6 +480,7 @@ def test_config1_shape_against_oracle(dev, kind, loss_name):
     ref_err = {k_: rel(g32[k_], g64[k_]) for k_ in g64}        # the reference's own fp32 arithmetic, per parameter
     m = m.to(dev)
     test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    failures = []
     try:
         for mode in (_lib.GEMM_TF32X3, _lib.GEMM_FP32):
             _lib.set_gemm_mode(mode)
@@ -497,9 +498,11 @@ def test_config1_shape_against_oracle(dev, kind, loss_name):
                 scale = float(g64[k_].abs().max())
                 parity_record(test, f"grad:{k_} (gemm mode {mode})", got * scale, scale, bound * scale,
                               f"reference fp32 vs fp64 on this parameter: {ref_err[k_]:.2e}")
-                assert got <= bound, (mode, k_, got, bound, ref_err[k_])
+                if got > bound:
+                    failures.append((mode, k_, got, bound, ref_err[k_]))
     finally:
         _lib.set_gemm_mode(_lib.GEMM_TF32X3)
+    assert not failures, failures          # (gemm mode, parameter, achieved, allowed, reference fp32 vs fp64)
 
 
 @pytest.mark.parametrize("kind,heads", [("custom", 1), ("pyg", 1), ("pyg", 4)])

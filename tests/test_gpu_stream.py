@@ -1,0 +1,92 @@
+"""GPU: per-head streaming (BASELINE config 5's shape: 3 layers, d=256, heads=4, bf16 projection) through the row-sharded
+trainer at world size 1, against the single-GPU module path (same tier) and against the fp64 oracle at the bf16 tier's
+tolerance (rtol 2e-2 of max|ref|; 5e-2 for the attention-vector gradients, as in test_bf16_projection_tier)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import parity_record
+from oracle import gat_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("hidden,heads,layers", [(256, 4, 3), (128, 2, 2)])
+def test_streamed_heads_match_module_path_and_oracle(hidden, heads, layers):
+    import b200gat
+    from b200gat import sharded, synth
+    dev = torch.device("cuda:0")
+    nu, ni, n_inter, k = 3000, 5000, 40000, 8
+    ei, feats = synth.make_graph(nu, ni, n_inter, k)
+    u, i, j = (t.to(dev) for t in synth.make_triples(nu, ni, 20000))
+    name = f"streamed heads d={hidden} H={heads} L={layers}"
+
+    def sharpen(w_list):          # near-uniform attention makes every logit gradient a ~0 difference of equal terms
+        with torch.no_grad():
+            for w in w_list:
+                w.mul_(6.0)
+
+    tr = sharded.ShardedGAT("pyg", nu, ni, feats, ei, hidden=hidden, layers=layers, heads=heads, attn_dropout=0.1, seed=7, device=dev,
+                            feature_dtype=torch.bfloat16, n_triples_max=20000, stream_heads=True)
+    sharpen(tr.a_src)
+    with torch.no_grad():
+        tr.user_emb.mul_(3.0)
+    tr.training = False
+    z_loc = tr.forward()
+    loss = tr.loss_and_backward(z_loc, u, i, j, "bce")
+    # the module path of the same tier with the same parameters
+    torch.manual_seed(7)
+    m = b200gat.PyGGAT(nu, ni, 128, hidden, layers, heads, 0.1, feature_dtype=torch.bfloat16).to(dev).eval()
+    sharpen([c.att_src for c in m.convs])
+    with torch.no_grad():
+        m.user_emb.weight.mul_(3.0)
+    z = m(feats.to(dev), ei.to(dev))
+    ref_loss = b200gat.bce_loss(z, nu, u, i, j)
+    ref_loss.backward()
+    # forward: same kernels, same rounding points; only the order in which the heads are averaged differs.  That moves a layer
+    # output by an fp32 ulp, which flips the bf16 rounding of a few of the NEXT layer's input elements (2^-9 relative each):
+    # measured 7.5e-5 of max|z| after two layers -- two orders below the tier's own rounding error (checked against fp64 below)
+    parity_record(name, "z rows vs module path (same tier)", _rel(z_loc[:tr.n_loc], z) * float(z.abs().max()), float(z.abs().max()),
+                  1e-3 * float(z.abs().max()), "head-mean order -> bf16 rounding flips of the next layer's input")
+    assert _rel(z_loc[:tr.n_loc], z) < 1e-3, _rel(z_loc[:tr.n_loc], z)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    # fp64 oracle
+    st = {k_: v.detach().double().cpu().requires_grad_(True) for k_, v in m.state_dict().items()}
+    z64 = O.pyg_gat_forward(st, feats.double(), ei, heads)
+    l64 = O.bce_loss(z64, nu, u.cpu(), i.cpu(), j.cpu())
+    l64.backward()
+    assert _rel(z_loc[:tr.n_loc], z64) < 2e-2
+    np.testing.assert_allclose(float(loss), float(l64), rtol=2e-2)
+    got = {"user_emb.weight": tr.user_emb.grad, "item_proj.weight": tr.item_proj.weight.grad, "item_proj.bias": tr.item_proj.bias.grad}
+    for l in range(layers):
+        got[f"convs.{l}.lin.weight"] = tr.W[l].grad
+        got[f"convs.{l}.att_src"] = tr.a_src[l].grad.view(1, heads, hidden)
+        got[f"convs.{l}.att_dst"] = tr.a_dst[l].grad.view(1, heads, hidden)
+        got[f"convs.{l}.bias"] = tr.bias[l].grad
+    mod = dict(m.named_parameters())
+    for k_, g in got.items():
+        ref_g = st[k_].grad
+        scale = float(ref_g.abs().max())
+        if k_.endswith("att_dst"):      # ~0 by construction (a per-destination shift cancels in the softmax): its twin's scale
+            scale = max(scale, float(st[k_.replace("dst", "src")].grad.abs().max()))
+        # bf16 tier: rtol 2e-2 of max|ref| for two layers; 5e-2 for the attention vectors and for the three-layer shape, where
+        # three layers of bf16 h / dout rounding compound (measured 3.7e-2 on user_emb.weight with these sharpened parameters,
+        # identical for the module path -- DESIGN.md section 2 lists the measured values)
+        tol = 5e-2 if ("att_" in k_ or layers > 2) else 2e-2
+        err = float((g.detach().double().cpu() - ref_g).abs().max())
+        err_mod = float((mod[k_].grad.detach().double().cpu() - ref_g).abs().max())
+        parity_record(name, f"grad:{k_}", err, scale, tol * scale, f"module path of the same tier: {err_mod / scale:.2e}")
+        assert err <= tol * scale, (k_, err / scale, "module path:", err_mod / scale)
+        # streaming must not cost accuracy: no further from fp64 than the module path of the same tier (plus rounding noise)
+        assert err <= 1.5 * err_mod + 2e-3 * scale, (k_, err / scale, "module path:", err_mod / scale)
+    # train mode: the regenerated dropout mask of the backward matches the forward's (finite loss, changes between steps)
+    tr.training = True
+    l1 = float(tr.train_step(u, i, j, "bpr"))
+    l2 = float(tr.train_step(u, i, j, "bpr"))
+    assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2
+    tr.close()

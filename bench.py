@@ -568,6 +568,8 @@ def main():
     ap.add_argument("--tier", default=None, choices=["f32", "bf16"],
                     help="override the configuration's tier: f32 (rtol 1e-5) or bf16 projection (h / gathered dout stored as bf16, rtol 2e-2)")
     ap.add_argument("--scale", type=float, default=1.0, help="divide users / items / interactions of the workload by this")
+    ap.add_argument("--stream-heads", default="auto", choices=["auto", "0", "1"],
+                    help="heads > 1, bf16 tier, N-GPU path: one head at a time (config 5 at full size); auto = when [N, heads*C] per layer does not fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true")
     args = ap.parse_args()

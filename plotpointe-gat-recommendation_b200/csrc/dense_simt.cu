@@ -3,6 +3,9 @@
 // ((h*a).sum(-1), train_gat_custom.py:79), and the small parameter-gradient finalisers.
 // This is the strict-fp32 path (true FFMA accumulation); the tensor-core path lives in
 // gemm_tcgen05.cu and is validated against this one.
+#include <stdint.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/b200gat.h"
 
@@ -190,6 +193,7 @@ static const int kSlabs = 2 * kNumSMs;  // split count for reductions over the n
 
 namespace b200gat {  // gemm_tc.cu
 bool tc_supported(int in_features, int heads, int channels);
+int tc_parts();
 size_t tc_workspace_bytes(int heads);
 int tc_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int heads,
                    float* h, float* s, void* workspace, cudaStream_t st);
@@ -228,7 +232,7 @@ extern "C" int b200gat_project_f32(const float* x, const float* W, const float* 
   B200GAT_CHECK_ARG(channels % 4 == 0 && in_features > 0, "bad dims");
   if (n_rows == 0) return kOk;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_supported(in_features, heads, channels)) {
+  if (tc_supported(in_features, heads, channels) && (tc_parts() & 1)) {
     B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(heads), "workspace too small for the tensor-core path");
     return tc_project_fwd(x, W, a_src, a_dst, n_rows, heads, h, s, workspace, st);
   }
@@ -254,8 +258,14 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const int HC = heads * channels, F = in_features, H2 = 2 * heads;
-  if (n_rows > 0 && tc_supported(in_features, heads, channels))
+  const int parts = tc_supported(in_features, heads, channels) ? (tc_parts() & 6) : 0;
+  if (n_rows > 0 && parts == 6)
     return tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, heads, dx, dW, da_src, da_dst, workspace, st);
+  if (n_rows > 0 && parts) {   // diagnostic split: one of dx / dW on the tensor cores (they read dh before it is rewritten below)
+    int rc0 = tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, heads, (parts & 2) ? dx : nullptr, (parts & 4) ? dW : nullptr, da_src,
+                             da_dst, workspace, st);
+    if (rc0) return rc0;
+  }
   float* part = (float*)workspace;                       // [kSlabs, HC + 2H, F]
   float* v = part + (size_t)kSlabs * (HC + H2) * F + (size_t)kSlabs * channels;  // [2H, F]
   if (n_rows == 0) {
@@ -267,10 +277,11 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   count_launch(), add_logit_grad_kernel<<<kNumSMs * 8, 256, 0, st>>>(dh, ds, a_src, a_dst, n_rows, heads, channels);
   B200GAT_LAUNCH_CHECK();
   int rc;
-  if (dx) {  // dx[n,f] = sum_m dh[n,m] W[m,f]
+  if (dx && !(parts & 2)) {  // dx[n,f] = sum_m dh[n,m] W[m,f]
     rc = launch_sgemm(dh, HC, 1, W, F, 1, dx, F, (int)n_rows, F, HC, 1, HC, 0, nullptr, st);
     if (rc) return rc;
   }
+  if (parts & 4) return kOk;
   const int64_t k_slab = (n_rows + kSlabs - 1) / kSlabs;
   const int n_slabs = (int)((n_rows + k_slab - 1) / k_slab);
   // dW[m,f] = sum_n dh[n,m] x[n,f]
@@ -287,6 +298,112 @@ extern "C" int b200gat_project_bwd_f32(const float* x, const float* W, const flo
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// linear128_ffma : y[n, 0:128] = x[n, 0:128] W[128,128]^T + bias with true fp32 FFMA accumulation (round to nearest).
+// The item-feature projection is the one GEMM of the path whose output is mixed with rows that carry no GEMM error at all
+// (the user embedding rows of the same node-feature matrix): the tensor core's truncating accumulation shrinks every item
+// row by ~2e-6, and config 1's cancellation-heavy gradients amplify exactly that imbalance (measured: every parameter
+// gradient within 6.5e-6 of the fp64 oracle with this kernel, up to 1.7e-3 with the tensor-core flavour).
+// Persistent CTAs; W^T resident in shared memory; x tiles of 128 rows double-buffered with cp.async; 8 x 8 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLinRows = 128, kLinThreads = 256, kLinPitch = 132;   // pitch: 16-byte aligned, rows 4 banks apart
+constexpr int kLinSmem = (128 * 128 + 2 * kLinRows * kLinPitch) * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;     // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kLinThreads, 1) linear128_ffma_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                        const float* __restrict__ bias, int64_t n_rows,
+                                                                        float* __restrict__ y, int64_t ldy) {
+  extern __shared__ float4 lin_smem4[];
+  float* Ws = reinterpret_cast<float*>(lin_smem4);          // [k][n] = W[n][k]
+  float* Xs = Ws + 128 * 128;                               // [2][kLinRows][kLinPitch]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t n_tiles = (n_rows + kLinRows - 1) / kLinRows;
+  auto stage = [&](int64_t tile, int buf) {
+    float* dst = Xs + (size_t)buf * kLinRows * kLinPitch;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int idx = tid + i * kLinThreads;                // 0 .. 4095 : 128 rows x 32 chunks of 16 B
+      const int r = idx >> 5, c = idx & 31;
+      const int64_t row = tile * kLinRows + r;
+      cp_async16(dst + r * kLinPitch + c * 4, x + (row < n_rows ? row : 0) * 128 + c * 4, row < n_rows);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) stage(tile, 0);
+  for (int i = tid; i < 128 * 128; i += kLinThreads) {      // transpose W once per CTA (coalesced reads, 32-way spread writes)
+    const int n = i >> 7, k = i & 127;
+    Ws[k * 128 + n] = __ldg(W + i);
+  }
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (bias) { b0 = ldg4(bias + tx * 4); b1 = ldg4(bias + 64 + tx * 4); }
+  int buf = 0;
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {
+      stage(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* X = Xs + (size_t)buf * kLinRows * kLinPitch + (ty * 8) * kLinPitch;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < 128; k4 += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(X + i * kLinPitch + k4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + (k4 + kk) * 128 + tx * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + (k4 + kk) * 128 + 64 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+          acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
+          acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
+          acc[i][4] = fmaf(av, w1.x, acc[i][4]); acc[i][5] = fmaf(av, w1.y, acc[i][5]);
+          acc[i][6] = fmaf(av, w1.z, acc[i][6]); acc[i][7] = fmaf(av, w1.w, acc[i][7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = tile * kLinRows + ty * 8 + i;
+      if (row < n_rows) {
+        float* dst = y + row * ldy;
+        *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[i][0] + b0.x, acc[i][1] + b0.y, acc[i][2] + b0.z, acc[i][3] + b0.w);
+        *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[i][4] + b1.x, acc[i][5] + b1.y, acc[i][6] + b1.z, acc[i][7] + b1.w);
+      }
+    }
+    __syncthreads();      // everybody is done with this buffer before the next iteration's cp.async overwrites it
+  }
+}
+
+static int launch_linear128_ffma(const float* x, const float* W, const float* bias, int64_t n_rows, float* y, int64_t ldy,
+                                 cudaStream_t st) {
+  static DeviceOnce once;
+  if (once.pending()) {
+    B200GAT_CUDA(cudaFuncSetAttribute(linear128_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmem));
+    once.done();
+  }
+  const int64_t n_tiles = (n_rows + kLinRows - 1) / kLinRows;
+  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  count_launch(), linear128_ffma_kernel<<<grid, kLinThreads, kLinSmem, st>>>(x, W, bias, n_rows, y, ldy);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
 // y[n, ldy] = x W^T + bias   (CustomGAT.item_proj, scripts/train_gat_custom.py:100,107; writes straight into the tail of the
 // [N, C] node-feature buffer, which removes the torch.cat copy of :109)
 extern "C" int b200gat_linear_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
@@ -295,10 +412,15 @@ extern "C" int b200gat_linear_f32(const float* x, const float* W, const float* b
   B200GAT_CHECK_ARG(x && W && y && ldy >= out_features, "null pointer / bad ld");
   if (n_rows == 0) return kOk;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_supported(in_features, 1, out_features) && ldy % 4 == 0) {
+  // default: fp32 FFMA (see linear128_ffma_kernel); the tensor-core flavour only on request (B200GAT_TC_PARTS bit 8 AND
+  // B200GAT_LINEAR_TC=1), kept for A/B measurements
+  static const bool linear_tc = getenv("B200GAT_LINEAR_TC") && atoi(getenv("B200GAT_LINEAR_TC")) != 0;
+  if (linear_tc && tc_supported(in_features, 1, out_features) && ldy % 4 == 0 && (tc_parts() & 8)) {
     B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(1), "workspace too small for the tensor-core path");
     return tc_linear_fwd(x, W, bias, n_rows, y, ldy, workspace, st);
   }
+  if (in_features == 128 && out_features == 128 && ldy % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0))
+    return launch_linear128_ffma(x, W, bias, n_rows, y, ldy, st);
   return launch_sgemm(x, in_features, 1, W, 1, in_features, y, ldy, (int)n_rows, out_features, in_features, 1, in_features, 0,
                       bias, st);
 }
@@ -318,7 +440,7 @@ extern "C" int b200gat_linear_bwd_f32(const float* x, const float* dy, int64_t l
     return kOk;
   }
   int rc;
-  if (tc_supported(in_features, 1, out_features) && ldy == out_features) {
+  if (tc_supported(in_features, 1, out_features) && ldy == out_features && (tc_parts() & 16)) {
     rc = tc_linear_dw(x, dy, n_rows, dW, workspace, st);
   } else {
     const int64_t k_slab = (n_rows + kSlabs - 1) / kSlabs;

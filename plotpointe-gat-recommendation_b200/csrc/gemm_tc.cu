@@ -25,6 +25,8 @@
 // anything else is served by dense_simt.cu.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/b200gat.h"
@@ -782,6 +784,17 @@ bool tc_supported(int in_features, int heads, int channels) {
   return g_gemm_mode == B200GAT_GEMM_TF32X3 && in_features == 128 && channels == 128;
 }
 
+// Diagnostic: B200GAT_TC_PARTS (bit mask, default all) limits the tensor-core path to some of the GEMMs so that a parity
+// difference can be attributed: 1 projection forward, 2 dx, 4 dW + att gradients, 8 linear forward, 16 linear dW.
+int tc_parts() {
+  static int parts = -1;
+  if (parts < 0) {
+    const char* e = getenv("B200GAT_TC_PARTS");
+    parts = e ? atoi(e) & 31 : 31;
+  }
+  return parts;
+}
+
 size_t tc_workspace_bytes(int heads) {
   // B images (one per head, or W^T), dW / v partials
   return (size_t)(heads > 1 ? heads : 1) * tc::kBImageBytes + (size_t)kNumSMs * (128 * 128 + 2 * 128) * sizeof(float) +
@@ -833,6 +846,7 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
       p.ds_ld = 2 * heads; p.ds_src_col = hh; p.ds_dst_col = heads + hh; p.accumulate = hh > 0;
       count_launch(), tc::proj_kernel<1><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
     }
+    if (!dW) continue;       // dx only (diagnostic split, see tc_parts)
     tc::DwParams q{};
     q.dh = dh + hh * 128; q.ld_dh = (int64_t)heads * 128; q.ds = ds; q.ds_ld = 2 * heads; q.ds_src_col = hh; q.ds_dst_col = heads + hh;
     q.x = x; q.ld_x = 128; q.att_src = a_src + hh * 128; q.att_dst = a_dst + hh * 128; q.n_rows = n_rows;

@@ -74,7 +74,7 @@ def make_plan(edge_index: torch.Tensor, n_users: int, n_items: int, rank: int, w
     dev = edge_index.device
     cu_all = [(n_users - b + world - 1) // world for b in range(world)]
     ci_all = [(n_items - b + world - 1) // world for b in range(world)]
-    n_max = max(a + b for a, b in zip(cu_all, ci_all))
+    n_max = (max(a + b for a, b in zip(cu_all, ci_all)) + 3) // 4 * 4     # x4: every per-row block is a multiple of 16 bytes
     cu_t = torch.tensor(cu_all, dtype=torch.int64, device=dev)
     u = torch.arange(n_users, dtype=torch.int64, device=dev)
     i = torch.arange(n_items, dtype=torch.int64, device=dev)
@@ -798,13 +798,32 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     from . import _lib, synth
     import bench as B
     nu, ni, n_inter, k = B.graph_dims(cfg, synth)
-    ei, feats = synth.make_graph(nu, ni, n_inter, k)
-    e = int(ei.shape[1])
     bf16 = cfg["tier"] == "bf16"
     export = cfg["mode"] == "export"
-    L = cfg["layers"]
-    tr = ShardedGAT(cfg["kind"], nu, ni, feats, ei, hidden=cfg["hidden"], layers=L, heads=cfg["heads"], attn_dropout=0.1, device=dev,
-                    feature_dtype=torch.bfloat16 if bf16 else torch.float32, n_triples_max=B.S_TRIPLES)
+    L, H, C = cfg["layers"], cfg["heads"], cfg["hidden"]
+    e = 2 * n_inter + k * ni
+    on_device = e > 100_000_000        # the host generator needs minutes and ~100 B/edge of host memory PER RANK at this size
+    if on_device:
+        ei, feats = synth.make_graph_device(nu, ni, n_inter, k, dev)
+        if world > 1:                  # every rank drew the graph itself (same seed, same device type): make sure it IS the same
+            chk = torch.stack([ei.sum(), -ei.sum()]).to(torch.float64)
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+            assert float(chk[0]) == -float(chk[1]), "the ranks generated different graphs"
+    else:
+        ei, feats = synth.make_graph(nu, ni, n_inter, k)
+    assert e == int(ei.shape[1])
+    # per-head streaming: needed when the per-layer [N, heads*C] tensors kept for the backward do not fit
+    n_pad_est = nu + ni + world
+    saved_bytes = L * n_pad_est * H * C * (2 if bf16 else 4) if H > 1 else 0
+    stream_opt = getattr(args, "stream_heads", "auto")
+    stream = (H > 1 and bf16 and cfg["kind"] == "pyg" and not export and
+              (stream_opt == "1" or (stream_opt == "auto" and saved_bytes > 0.35 * torch.cuda.get_device_properties(dev).total_memory)))
+    tr = ShardedGAT(cfg["kind"], nu, ni, feats, ei, hidden=C, layers=L, heads=H, attn_dropout=0.1, device=dev,
+                    feature_dtype=torch.bfloat16 if bf16 else torch.float32, n_triples_max=B.S_TRIPLES, stream_heads=stream)
+    if on_device:
+        del ei, feats
+        ei = feats = None
+        torch.cuda.empty_cache()
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
@@ -873,7 +892,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
         dist.all_reduce(cm, op=dist.ReduceOp.MAX)
     comm_bytes = int(tr.comm_bytes_per_step)
     parity = None
-    if not export and (nu + ni) <= 2_000_000:
+    if not export and (nu + ni) <= 2_000_000 and not on_device:
         parity = _parity_vs_single(tr, cfg, feats, ei, (du, di, dj), rank, world, dev)
     ms_step, e2e_ms = float(ms), float(e2e)
     if rank == 0:
@@ -881,6 +900,9 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
         conf["exchange"] = ("device-side pulls over peer-mapped memory (flag wait + all-SM NVLink reads), no library collective in the step; "
                             + ("layer inputs x exchanged, every rank projects all rows" if tr.x_exchange else "projected rows [h|s] exchanged"))
         conf["rows_per_rank"] = tr.n_loc
+        conf["heads_streamed"] = bool(tr.stream)
+        conf["graph_generator"] = "torch on the device (synth.make_graph_device)" if on_device else "numpy on the host (synth.make_graph)"
+        conf["hbm_peak_allocated_gb_rank0"] = round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)
         print(json.dumps({
             "metric": B.metric_name(cfg), "value": e * L / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

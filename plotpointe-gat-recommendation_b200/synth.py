@@ -56,3 +56,49 @@ def make_triples(n_users: int, n_items: int, n_triples: int, seed: int = 42):
     return (torch.from_numpy(rng.integers(0, n_users, size=n_triples)),
             torch.from_numpy(rng.integers(0, n_items, size=n_triples)),
             torch.from_numpy(rng.integers(0, n_items, size=n_triples)))
+
+
+def make_graph_device(n_users: int, n_items: int, n_inter: int, k: int, device, seed: int = 42, item_zipf: float = 0.9,
+                      item_shift: float = 40.0):
+    """The same construction as :func:`make_graph`, drawn with torch on ``device`` (a different random stream, the same
+    distributions, edge order and shapes).  For BASELINE config 5 at full size (30 M nodes, 800 M edges) the host generator
+    needs ~5 minutes and ~77 GB per process; this one takes seconds.  Returns (edge_index int64 [2, E], item_feats fp32
+    [n_items, 128]) on ``device``.  Deterministic for a given (seed, device type)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    f64 = dict(dtype=torch.float64, device=device)
+    extra = n_inter - n_users
+    assert extra >= 0
+    w = -torch.log1p(-torch.rand(n_users, generator=g, **f64))                     # Exp(1) weights, as the host generator
+    cdf = torch.cumsum(w / w.sum(), 0)
+    users = torch.cat([torch.arange(n_users, device=device),
+                       torch.searchsorted(cdf, torch.rand(extra, generator=g, **f64)).clamp_(max=n_users - 1)])
+    users = torch.sort(users).values                                             # edges grouped by user (build_edge_index order)
+    del w, cdf
+    ranks = torch.arange(1, n_items + 1, **f64)
+    pop = 1.0 / (ranks + item_shift) ** item_zipf
+    cdf = torch.cumsum(pop / pop.sum(), 0)
+    del ranks, pop
+    item_of_rank = torch.randperm(n_items, generator=g, device=device)
+    items = torch.empty(n_inter, dtype=torch.int64, device=device)
+    step = 1 << 26
+    for lo in range(0, n_inter, step):                                            # chunked: the fp64 uniforms are transient
+        n = min(step, n_inter - lo)
+        items[lo:lo + n] = item_of_rank[torch.searchsorted(cdf, torch.rand(n, generator=g, **f64)).clamp_(max=n_items - 1)]
+    del cdf, item_of_rank
+    items += n_users
+    e_ui, e_ii = 2 * n_inter, k * n_items
+    ei = torch.empty((2, e_ui + e_ii), dtype=torch.int64, device=device)
+    ei[0, 0:e_ui:2], ei[1, 0:e_ui:2] = users, items
+    ei[0, 1:e_ui:2], ei[1, 1:e_ui:2] = items, users
+    del users, items
+    step_rows = max((1 << 25) // k, 1)
+    ar_k = torch.arange(k, device=device)
+    for lo in range(0, n_items, step_rows):
+        n = min(step_rows, n_items - lo)
+        off = torch.sort(torch.randint(1, n_items - k + 1, (n, k), generator=g, device=device), dim=1).values + ar_k
+        rows = torch.arange(lo, lo + n, device=device).unsqueeze(1).expand(n, k)
+        ei[0, e_ui + lo * k:e_ui + (lo + n) * k] = (rows + n_users).reshape(-1)
+        ei[1, e_ui + lo * k:e_ui + (lo + n) * k] = ((rows + off) % n_items + n_users).reshape(-1)
+    feats = torch.randn((n_items, 128), generator=g, device=device)
+    feats /= feats.norm(dim=1, keepdim=True)
+    return ei, feats

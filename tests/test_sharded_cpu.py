@@ -88,7 +88,9 @@ def test_plan_edge_cases():
     p = sharded.make_plan(ei, 2, 2, 0, 1)
     assert p.n_max == 4 and p.perm_map.tolist() == [0, 1, 2, 3] and p.fwd_sel.tolist() == [0, 1, 2, 3]
     p0, p1 = sharded.make_plan(ei, 2, 2, 0, 2), sharded.make_plan(ei, 2, 2, 1, 2)
-    assert p0.perm_map.tolist() == [0, 2, 1, 3] and p0.local_nodes.tolist() == [0, 2] and p1.local_nodes.tolist() == [1, 3]
+    # blocks are padded to a multiple of 4 rows (16-byte aligned per-row blocks of any width): rank 1's block starts at row 4
+    assert p0.n_max == 4 and p0.n_loc == 2
+    assert p0.perm_map.tolist() == [0, 4, 1, 5] and p0.local_nodes.tolist() == [0, 2] and p1.local_nodes.tolist() == [1, 3]
     # more ranks than users: some ranks own items only
     p3 = sharded.make_plan(torch.zeros((2, 0), dtype=torch.long), 1, 7, 3, 4)
-    assert p3.cu == 0 and p3.ci == 1 and p3.n_max == 3
+    assert p3.cu == 0 and p3.ci == 1 and p3.n_max == 4

@@ -123,6 +123,11 @@ int b200gat_project_bwd_f32(const float* x, const float* W, const float* a_src, 
  * [N, C] node-feature buffer (no torch.cat copy); backward: dW = dy^T x, dbias = column sums (x needs no gradient). */
 int b200gat_linear_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
                        int out_features, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+/* The same projection on the tensor cores (TF32 hi/lo split): used by the bf16 tier, where the next step rounds x to bf16.
+ * b200gat_linear_f32 itself accumulates with fp32 FFMA (round to nearest): the tensor core's truncating accumulation shrinks
+ * the item rows by ~2e-6 relative to the user rows of the same matrix, which config 1's gradients amplify. */
+int b200gat_linear_tc_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
+                          int out_features, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 int b200gat_linear_bwd_f32(const float* x, const float* dy, int64_t ldy, int64_t n_rows, int in_features,
                            int out_features, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
                            void* stream);

@@ -425,6 +425,20 @@ extern "C" int b200gat_linear_f32(const float* x, const float* W, const float* b
                       bias, st);
 }
 
+// The same projection on the tensor cores (TF32 hi/lo split, ~1e-7 per element but with the tensor core's truncating
+// accumulation): for the bf16 tier, whose next step rounds x to bf16 anyway.  Falls back to b200gat_linear_f32 for other shapes.
+extern "C" int b200gat_linear_tc_f32(const float* x, const float* W, const float* bias, int64_t n_rows, int in_features,
+                                     int out_features, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  B200GAT_CHECK_ARG(x && W && y && ldy >= out_features, "null pointer / bad ld");
+  if (n_rows == 0) return kOk;
+  if (tc_supported(in_features, 1, out_features) && ldy % 4 == 0 && (tc_parts() & 8)) {
+    B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(1), "workspace too small for the tensor-core path");
+    return tc_linear_fwd(x, W, bias, n_rows, y, ldy, workspace, (cudaStream_t)stream);
+  }
+  return b200gat_linear_f32(x, W, bias, n_rows, in_features, out_features, y, ldy, workspace, workspace_bytes, stream);
+}
+
 // dW = dy^T x, dbias = column sums of dy   (backward of the above; x needs no gradient: item features are inputs)
 extern "C" int b200gat_linear_bwd_f32(const float* x, const float* dy, int64_t ldy, int64_t n_rows, int in_features,
                                       int out_features, float* dW, float* dbias, void* workspace, size_t workspace_bytes,

@@ -104,7 +104,7 @@ class NodeFeaturesFunction(torch.autograd.Function):
     without the concat copy: the projection writes straight into the tail rows of the [N, C] buffer."""
 
     @staticmethod
-    def forward(ctx, user_w, proj_w, proj_b, item_feats):
+    def forward(ctx, user_w, proj_w, proj_b, item_feats, tensor_core=False):
         if not item_feats.is_cuda:
             raise RuntimeError("b200gat node_features: tensors must be CUDA tensors (there is no CPU fallback)")
         nu, c = user_w.shape
@@ -117,8 +117,8 @@ class NodeFeaturesFunction(torch.autograd.Function):
         ws_bytes = _lib.dense_workspace_bytes(1, c, f)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
         with torch.cuda.device(feats.device):
-            _lib.call("b200gat_linear_f32", _lib.ptr(feats), _lib.ptr(w), _lib.ptr(b), ni, f, c, _lib.ptr(x0, nu * c), c,
-                      _lib.ptr(ws), ws_bytes, _lib.stream())
+            _lib.call("b200gat_linear_tc_f32" if tensor_core else "b200gat_linear_f32", _lib.ptr(feats), _lib.ptr(w), _lib.ptr(b), ni, f, c,
+                      _lib.ptr(x0, nu * c), c, _lib.ptr(ws), ws_bytes, _lib.stream())
         ctx.save_for_backward(feats)
         ctx.dims = (nu, ni, c, f, b is not None)
         return x0
@@ -135,13 +135,14 @@ class NodeFeaturesFunction(torch.autograd.Function):
         with torch.cuda.device(feats.device):
             _lib.call("b200gat_linear_bwd_f32", _lib.ptr(feats), _lib.ptr(dx0, nu * c), c, ni, f, c, _lib.ptr(dw), _lib.ptr(db),
                       _lib.ptr(ws), ws_bytes, _lib.stream())
-        return dx0[:nu], dw, db, None
+        return dx0[:nu], dw, db, None, None
 
 
-def node_features(user_w, proj_w, proj_b, item_feats):
+def node_features(user_w, proj_w, proj_b, item_feats, tensor_core=False):
+    """``tensor_core``: project the item features with the TF32-split tensor-core kernel (the bf16 tier) instead of fp32 FFMA."""
     if item_feats.requires_grad:
         raise NotImplementedError("b200gat node_features: item_feats is an input and must not require grad")
-    return NodeFeaturesFunction.apply(user_w, proj_w, proj_b, item_feats)
+    return NodeFeaturesFunction.apply(user_w, proj_w, proj_b, item_feats, bool(tensor_core))
 
 
 def gat_layer(x, weight, a_src, a_dst, bias, graph, heads, channels, policy, negative_slope=0.2, p_drop=0.0, seed=0,

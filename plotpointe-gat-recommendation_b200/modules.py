@@ -137,6 +137,7 @@ class CustomGAT(torch.nn.Module):
     def __init__(self, n_users: int, n_items: int, item_feat_dim: int, hidden: int, layers: int, feature_dtype=torch.float32):
         super().__init__()
         self.n_users, self.n_items = n_users, n_items
+        self.feature_dtype = feature_dtype
         self.user_emb = torch.nn.Embedding(n_users, hidden)
         torch.nn.init.normal_(self.user_emb.weight, std=0.1)
         self.item_proj = torch.nn.Linear(item_feat_dim, hidden)
@@ -144,7 +145,8 @@ class CustomGAT(torch.nn.Module):
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
         # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy
-        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats)
+        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats,
+                             tensor_core=self.feature_dtype == torch.bfloat16)
 
     def forward(self, item_feats: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         x = self.node_features(item_feats)
@@ -160,6 +162,7 @@ class PyGGAT(torch.nn.Module):
                  attn_dropout: float, feature_dtype=torch.float32):
         super().__init__()
         self.n_users, self.n_items = n_users, n_items
+        self.feature_dtype = feature_dtype
         self.user_emb = torch.nn.Embedding(n_users, hidden)
         torch.nn.init.normal_(self.user_emb.weight, std=0.1)
         self.item_proj = torch.nn.Linear(item_feat_dim, hidden)
@@ -170,7 +173,8 @@ class PyGGAT(torch.nn.Module):
 
     def node_features(self, item_feats: torch.Tensor) -> torch.Tensor:
         # == torch.cat([self.user_emb.weight, self.item_proj(item_feats)], dim=0), without the concat copy
-        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats)
+        return node_features(self.user_emb.weight, self.item_proj.weight, self.item_proj.bias, item_feats,
+                             tensor_core=self.feature_dtype == torch.bfloat16)
 
     def forward(self, item_feats: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         x = self.node_features(item_feats)

@@ -412,8 +412,8 @@ class ShardedGAT:
         dwb = lib.dense_workspace_bytes(H, C, max(C, self.feat_dim))
         dws = self._empty(dwb, dtype=torch.uint8)
         if self.plan.ci:
-            lib.call("b200gat_linear_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
-                     self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
+            lib.call("b200gat_linear_tc_f32" if self.bf16 else "b200gat_linear_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight),
+                     lib.ptr(self.item_proj.bias), self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
         self.saved = []
         p = self.p_drop if self.training else 0.0
         for l in range(L):
@@ -473,7 +473,7 @@ class ShardedGAT:
         dwb = lib.dense_workspace_bytes(1, C, max(C, self.feat_dim))
         dws = self._empty(dwb, dtype=torch.uint8)
         if self.plan.ci:
-            lib.call("b200gat_linear_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
+            lib.call("b200gat_linear_tc_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
                      self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
         lib.call("b200gat_cast_bf16", lib.ptr(x), lib.ptr(dst), self.n_max * C, 1.0, st)
 

@@ -295,6 +295,13 @@ int b200gat_adam_step_f32(float* param, const float* grad, float* exp_avg, float
  * samples for which no user / negative was found within the attempt budget (0 unless the graph is degenerate). */
 int b200gat_sample_bpr(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
                        uint64_t seed, int64_t* u, int64_t* i, int64_t* j, int32_t* n_fail, void* stream);
+/* _ex: `active_users` (device int32 [n_active], may be NULL) lists the users that have positives, so the user draw needs no
+ * rejection on graphs where most user ids are cold (the reference draws from the keys of its user -> positives dict).  A user
+ * whose positives cover almost the whole catalogue gets its negative by a forward walk from a random item after 1024
+ * rejections; n_fail counts only samples for which no negative exists at all. */
+int b200gat_sample_bpr_ex(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
+                          uint64_t seed, const int32_t* active_users, int64_t n_active, int64_t* u, int64_t* i, int64_t* j,
+                          int32_t* n_fail, void* stream);
 int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int channels, const int64_t* users,
                            const int64_t* candidates, int64_t n_eval, int n_candidates, int32_t* ranks, int32_t* n_bad,
                            void* stream);

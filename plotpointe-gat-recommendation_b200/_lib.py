@@ -44,6 +44,7 @@ _SIGS = {
     "b200gat_linear_bwd_f32": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "b200gat_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     "b200gat_sample_bpr": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_uint64, _P, _P, _P, _P, _P]),
+    "b200gat_sample_bpr_ex": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_uint64, _P, c_int64, _P, _P, _P, _P, _P]),
     "b200gat_eval_ranks_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P]),
     "b200gat_knn_workspace_bytes": (c_int, [c_int64, c_int, ctypes.POINTER(c_size_t)]),
     "b200gat_knn_cosine_f32": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),

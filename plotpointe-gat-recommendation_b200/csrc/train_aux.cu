@@ -167,28 +167,36 @@ __device__ __forceinline__ void philox4(uint64_t seed, uint32_t c0, uint32_t c1,
 __device__ __forceinline__ int64_t bounded(uint32_t r, int64_t n) { return (int64_t)(((uint64_t)r * (uint64_t)n) >> 32); }
 
 __global__ void sample_bpr_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ row, int64_t n_users,
-                                  int64_t n_items, int64_t n_samples, uint64_t seed, int64_t* __restrict__ u_out,
-                                  int64_t* __restrict__ i_out, int64_t* __restrict__ j_out, int32_t* __restrict__ n_fail) {
+                                  int64_t n_items, int64_t n_samples, uint64_t seed, const int32_t* __restrict__ active_users,
+                                  int64_t n_active, int64_t* __restrict__ u_out, int64_t* __restrict__ i_out,
+                                  int64_t* __restrict__ j_out, int32_t* __restrict__ n_fail) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_samples) return;
   uint32_t r[4];
   int64_t u = 0;
   int beg = 0, deg = 0;
   uint32_t attempt = 0;
-  for (; attempt < 64; ++attempt) {              // users without positives are not in the reference's dict: redraw
-    philox4(seed, (uint32_t)t, ((uint32_t)(t >> 32) << 8) | attempt, r);
-    u = bounded(r[0], n_users);
+  if (active_users) {                            // the caller's list of users with positives: one draw, no rejection
+    philox4(seed, (uint32_t)t, ((uint32_t)(t >> 32) << 8), r);
+    u = active_users[bounded(r[0], n_active)];
     beg = colptr[u];
     deg = colptr[u + 1] - beg;
-    if (deg > 0) break;
+  } else {
+    for (; attempt < 64; ++attempt) {            // users without positives are not in the reference's dict: redraw
+      philox4(seed, (uint32_t)t, ((uint32_t)(t >> 32) << 8) | attempt, r);
+      u = bounded(r[0], n_users);
+      beg = colptr[u];
+      deg = colptr[u + 1] - beg;
+      if (deg > 0) break;
+    }
   }
   if (deg <= 0) { atomicAdd(n_fail, 1); u_out[t] = 0; i_out[t] = 0; j_out[t] = 0; return; }
   const int64_t i = (int64_t)row[beg + (int)bounded(r[1], deg)] - n_users;
   int64_t j = -1;
   uint32_t rr[4] = {r[2], r[3], 0, 0};
   int next = 0, avail = 2;                          // two words are left over from the first draw
-  for (uint32_t a2 = 0; a2 < 256 && j < 0; ++a2) {
-    if (next == avail) { philox4(seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)t, ((uint32_t)(t >> 32) << 8) | (a2 & 0xff), rr); next = 0; avail = 4; }
+  for (uint32_t a2 = 0; a2 < 1024 && j < 0; ++a2) {
+    if (next == avail) { philox4(seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)t, ((uint32_t)(t >> 32) << 12) | (a2 & 0xfff), rr); next = 0; avail = 4; }
     const uint32_t word = next == 0 ? rr[0] : (next == 1 ? rr[1] : (next == 2 ? rr[2] : rr[3]));
     const int64_t cand = bounded(word, n_items);
     ++next;
@@ -196,7 +204,18 @@ __global__ void sample_bpr_kernel(const int32_t* __restrict__ colptr, const int3
     for (int q = beg; q < beg + deg; ++q) in |= ((int64_t)row[q] - n_users == cand);
     if (!in) j = cand;
   }
-  if (j < 0) { atomicAdd(n_fail, 1); j = 0; }
+  if (j < 0) {
+    // 1024 rejections in a row: this user has interacted with nearly every item (the reference's loop would spin as long).
+    // Walk forward from a random item to the first one that is not a positive: always terminates unless EVERY item is one.
+    philox4(seed ^ 0xD1B54A32D192ED03ull, (uint32_t)t, (uint32_t)(t >> 32), rr);
+    int64_t cand = bounded(rr[0], n_items);
+    for (int64_t step = 0; step < n_items && j < 0; ++step, cand = cand + 1 == n_items ? 0 : cand + 1) {
+      bool in = false;
+      for (int q = beg; q < beg + deg; ++q) in |= ((int64_t)row[q] - n_users == cand);
+      if (!in) j = cand;
+    }
+  }
+  if (j < 0) { atomicAdd(n_fail, 1); j = 0; }      // the user's positives cover the whole catalogue: no negative exists
   u_out[t] = u;
   i_out[t] = i;
   j_out[t] = j;
@@ -205,13 +224,20 @@ __global__ void sample_bpr_kernel(const int32_t* __restrict__ colptr, const int3
 
 extern "C" int b200gat_sample_bpr(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
                                   uint64_t seed, int64_t* u, int64_t* i, int64_t* j, int32_t* n_fail, void* stream) {
+  return b200gat_sample_bpr_ex(colptr, row, n_users, n_items, n_samples, seed, nullptr, 0, u, i, j, n_fail, stream);
+}
+
+extern "C" int b200gat_sample_bpr_ex(const int32_t* colptr, const int32_t* row, int64_t n_users, int64_t n_items, int64_t n_samples,
+                                     uint64_t seed, const int32_t* active_users, int64_t n_active, int64_t* u, int64_t* i, int64_t* j,
+                                     int32_t* n_fail, void* stream) {
   B200GAT_CHECK_ARG(colptr && row && n_fail && (n_samples == 0 || (u && i && j)), "null pointer");
   B200GAT_CHECK_ARG(n_users > 0 && n_items > 0 && n_samples >= 0, "bad sizes");
+  B200GAT_CHECK_ARG(!active_users || n_active > 0, "empty list of users with positives");
   cudaStream_t st = (cudaStream_t)stream;
   B200GAT_CUDA(cudaMemsetAsync(n_fail, 0, sizeof(int32_t), st));
   if (n_samples == 0) return kOk;
-  count_launch(), sample_bpr_kernel<<<ceil_div(n_samples, 256), 256, 0, st>>>(colptr, row, n_users, n_items, n_samples, seed, u, i, j,
-                                                                             n_fail);
+  count_launch(), sample_bpr_kernel<<<ceil_div(n_samples, 256), 256, 0, st>>>(colptr, row, n_users, n_items, n_samples, seed,
+                                                                             active_users, n_active, u, i, j, n_fail);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

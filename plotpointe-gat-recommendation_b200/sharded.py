@@ -797,12 +797,21 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     """bench.py's N>1 leg: strong scaling of the same workload, max-over-ranks device time."""
     from . import _lib, synth
     import bench as B
+    import sys
+    t_start = time.time()
+
+    def note(what: str) -> None:          # progress on stderr (rank 0): a full-size config-5 run spends minutes in set-up
+        if rank == 0:
+            torch.cuda.synchronize()
+            print(f"[bench +{time.time() - t_start:6.1f}s] {what}; HBM allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB "
+                  f"(peak {torch.cuda.max_memory_allocated(dev) / 2**30:.1f})", file=sys.stderr, flush=True)
+
     nu, ni, n_inter, k = B.graph_dims(cfg, synth)
     bf16 = cfg["tier"] == "bf16"
     export = cfg["mode"] == "export"
     L, H, C = cfg["layers"], cfg["heads"], cfg["hidden"]
     e = 2 * n_inter + k * ni
-    on_device = e > 100_000_000        # the host generator needs minutes and ~100 B/edge of host memory PER RANK at this size
+    on_device = e >= 50_000_000        # the host generator needs minutes and ~100 B/edge of host memory PER RANK at this size
     if on_device:
         ei, feats = synth.make_graph_device(nu, ni, n_inter, k, dev)
         if world > 1:                  # every rank drew the graph itself (same seed, same device type): make sure it IS the same
@@ -812,6 +821,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     else:
         ei, feats = synth.make_graph(nu, ni, n_inter, k)
     assert e == int(ei.shape[1])
+    note(f"graph generated ({e} edges)")
     # per-head streaming: needed when the per-layer [N, heads*C] tensors kept for the backward do not fit
     n_pad_est = nu + ni + world
     saved_bytes = L * n_pad_est * H * C * (2 if bf16 else 4) if H > 1 else 0
@@ -824,6 +834,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
         del ei, feats
         ei = feats = None
         torch.cuda.empty_cache()
+    note(f"trainer built (rows per rank {tr.n_loc}, heads streamed: {tr.stream})")
     u, i, j = synth.make_triples(nu, ni, B.S_TRIPLES)
     hu, hi, hj = (t.pin_memory() for t in (u, i, j))
     du, di, dj = (t.to(dev) for t in (u, i, j))
@@ -834,8 +845,10 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     sampler = B.ClockSampler(dev.index)
     if rank == 0:
         sampler.start()                   # streams from here on; only the samples inside the timed region are kept
-    for _ in range(args.warmup):
+    for w_ in range(args.warmup):
         step(du, di, dj)
+        if w_ == 0:
+            note("first step done")
     launches0 = _lib.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     if world > 1:
@@ -853,6 +866,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     ms = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    note(f"timed region done ({float(ms):.2f} ms per step)")
     launches = _lib.launch_count() - launches0
     t_e2e = []
     hout = torch.empty((ni, cfg["hidden"]), dtype=torch.float32).pin_memory() if export else None
@@ -879,7 +893,7 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     torch.cuda.synchronize()
     tr.fab.stats = {}
     _lib.timing = {}
-    n_prof = 5
+    n_prof = 5 if e <= 100_000_000 else 2
     for _ in range(n_prof):
         step(du, di, dj)
     torch.cuda.synchronize()

@@ -55,11 +55,19 @@ def sample_bpr_epoch(graph, n_users: int, n_items: int, samples: int, seed: int)
     i = torch.empty_like(u)
     j = torch.empty_like(u)
     n_fail = torch.empty(1, dtype=torch.int32, device=dev)
+    # the users that have positives (the keys of the reference's user -> positives dict), once per graph
+    active = getattr(graph, "_active_users", None)
+    if active is None:
+        deg = graph.colptr[1:n_users + 1] - graph.colptr[:n_users]
+        active = torch.nonzero(deg > 0).flatten().to(torch.int32).contiguous()
+        graph._active_users = active
+    if active.numel() == 0:
+        raise RuntimeError("sample_bpr_epoch: no user has a training positive")
     with torch.cuda.device(dev):
-        _lib.call("b200gat_sample_bpr", _lib.ptr(graph.colptr), _lib.ptr(graph.row), n_users, n_items, samples, int(seed) & (2 ** 64 - 1),
-                  _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), _lib.ptr(n_fail), _lib.stream())
+        _lib.call("b200gat_sample_bpr_ex", _lib.ptr(graph.colptr), _lib.ptr(graph.row), n_users, n_items, samples, int(seed) & (2 ** 64 - 1),
+                  _lib.ptr(active), int(active.numel()), _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), _lib.ptr(n_fail), _lib.stream())
     if int(n_fail.item()):
-        raise RuntimeError("sample_bpr_epoch: could not draw a user with positives / a negative item for some samples")
+        raise RuntimeError("sample_bpr_epoch: some sampled user has interacted with every item (no negative exists)")
     return u, i, j
 
 

@@ -813,11 +813,15 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     e = 2 * n_inter + k * ni
     on_device = e >= 50_000_000        # the host generator needs minutes and ~100 B/edge of host memory PER RANK at this size
     if on_device:
-        ei, feats = synth.make_graph_device(nu, ni, n_inter, k, dev)
-        if world > 1:                  # every rank drew the graph itself (same seed, same device type): make sure it IS the same
-            chk = torch.stack([ei.sum(), -ei.sum()]).to(torch.float64)
-            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
-            assert float(chk[0]) == -float(chk[1]), "the ranks generated different graphs"
+        # rank 0 draws the edge list and broadcasts it (the device generator is not bitwise reproducible between processes);
+        # the item features are element-wise Philox draws, which every rank can repeat for itself
+        if rank == 0:
+            ei, _ = synth.make_graph_device(nu, ni, n_inter, k, dev)
+        else:
+            ei = torch.empty((2, e), dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.broadcast(ei, 0)
+        feats = synth.make_feats_device(ni, dev)
     else:
         ei, feats = synth.make_graph(nu, ni, n_inter, k)
     assert e == int(ei.shape[1])

@@ -63,7 +63,8 @@ def make_graph_device(n_users: int, n_items: int, n_inter: int, k: int, device, 
     """The same construction as :func:`make_graph`, drawn with torch on ``device`` (a different random stream, the same
     distributions, edge order and shapes).  For BASELINE config 5 at full size (30 M nodes, 800 M edges) the host generator
     needs ~5 minutes and ~77 GB per process; this one takes seconds.  Returns (edge_index int64 [2, E], item_feats fp32
-    [n_items, 128]) on ``device``.  Deterministic for a given (seed, device type)."""
+    [n_items, 128]) on ``device``.  NOT bitwise reproducible between processes at large sizes (torch.cumsum on CUDA is not
+    deterministic, which moves a few inverse-CDF draws): a multi-GPU job draws the edge list on rank 0 and broadcasts it."""
     g = torch.Generator(device=device).manual_seed(seed)
     f64 = dict(dtype=torch.float64, device=device)
     extra = n_inter - n_users
@@ -99,6 +100,13 @@ def make_graph_device(n_users: int, n_items: int, n_inter: int, k: int, device, 
         rows = torch.arange(lo, lo + n, device=device).unsqueeze(1).expand(n, k)
         ei[0, e_ui + lo * k:e_ui + (lo + n) * k] = (rows + n_users).reshape(-1)
         ei[1, e_ui + lo * k:e_ui + (lo + n) * k] = ((rows + off) % n_items + n_users).reshape(-1)
+    return ei, make_feats_device(n_items, device, seed)
+
+
+def make_feats_device(n_items: int, device, seed: int = 42) -> torch.Tensor:
+    """Unit-norm random item features [n_items, 128] drawn on ``device`` (element-wise Philox draws and a row norm: the same
+    values on every device of the same type, so each rank of a multi-GPU run can make its own copy)."""
+    g = torch.Generator(device=device).manual_seed(seed + 7)
     feats = torch.randn((n_items, 128), generator=g, device=device)
     feats /= feats.norm(dim=1, keepdim=True)
-    return ei, feats
+    return feats

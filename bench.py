@@ -112,22 +112,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md).
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md).
 
-    nvidia-smi needs ~0.2 s before its first line, longer than a short timed region, so it is started before the warm-up
-    (`start`) and keeps streaming one timestamped line every 20 ms; `begin` / `end` mark the timed region on the host
-    clock and `stop` keeps the samples whose timestamps fall inside it.  If the region was too short to catch one, the
-    samples of the end-to-end loop that follows (same load) are used and `window` says so."""
+    A thread polls NVML (pynvml) every 2 ms from `start` on -- the calls release the GIL, so the launching thread is not held
+    up -- and `begin` / `end` mark the timed region; `stop` reports the samples that fall inside it.  Without pynvml it falls
+    back to one `nvidia-smi -lms 20` process whose timestamped lines are filtered the same way (coarser: nvidia-smi delivers
+    a line every ~100 ms whatever the interval asked for)."""
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
         self.t_begin = self.t_end = None
+        self.thread = None
+        self.samples = []          # (perf_counter, sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self._stop = False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                return None
+        return self.idx
+
+    def _poll(self, pynvml, handle):
+        while not self._stop:
+            try:
+                mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((time.perf_counter(), float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            phys = self._physical_index()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
@@ -137,13 +173,33 @@ class ClockSampler:
 
     def begin(self):
         self.t_begin = datetime.datetime.now()
+        self.p_begin = time.perf_counter()
 
     def end(self):
         self.t_end = datetime.datetime.now()
+        self.p_end = time.perf_counter()
+
+    def _summary(self, sel, window, source):
+        sm, reasons = [r[0] for r in sel], set()
+        for r in sel:
+            reasons |= set(r[1])
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(sm), "window": window, "source": source}
 
     def stop(self):
+        if self.thread is not None:
+            p_stop = time.perf_counter()
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            t0 = getattr(self, "p_begin", p_stop)
+            t1 = getattr(self, "p_end", p_stop)
+            dec = lambda m: [n for n, bit in self.REASONS if m & bit]
+            sel, window = [(mhz, dec(m)) for t, mhz, m in self.samples if t0 <= t <= t1], "timed region"
+            if not sel:
+                sel, window = [(mhz, dec(m)) for t, mhz, m in self.samples if t0 <= t <= p_stop], "timed region + end-to-end loop"
+            return self._summary(sel, window, "NVML polled every 2 ms")
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither pynvml nor nvidia-smi available"]}
         t_stop = datetime.datetime.now()
         time.sleep(0.05)
         self.proc.terminate()
@@ -159,21 +215,18 @@ class ClockSampler:
                 continue
             try:
                 ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
-                rows.append((ts, float(f[2]), float(f[3]), f[5:9]))
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                rows.append((ts, float(f[2]), float(f[3]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
         t0 = self.t_begin or t_stop
         t1 = self.t_end or t_stop
-        sel, window = [r for r in rows if t0 <= r[0] <= t1], "timed region"
+        if rows:
+            self.max_mhz = max(r[2] for r in rows)
+        sel, window = [(r[1], r[3]) for r in rows if t0 <= r[0] <= t1], "timed region"
         if not sel:
-            sel, window = [r for r in rows if t0 <= r[0] <= t_stop], "timed region + end-to-end loop (timed region shorter than one sample)"
-        sm, mx, reasons = [r[1] for r in sel], [r[2] for r in sel], set()
-        for r in sel:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+            sel, window = [(r[1], r[3]) for r in rows if t0 <= r[0] <= t_stop], "timed region + end-to-end loop (timed region shorter than one sample)"
+        return self._summary(sel, window, "nvidia-smi -lms 20")
 
 
 def algorithmic_bytes(n, e, h, c, dropout, row_bytes=4):

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   __shared__ float Bs[kBK][kBN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 micro-tile
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;   // M tiles on x: the row count may need more than 65535 of them
   const int64_t kbeg = blockIdx.z * k_slab;
   const int64_t kend = min(K, kbeg + k_slab);
   float acc[4][4] = {};
@@ -88,7 +88,7 @@ __global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs,
 static int launch_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
                         int64_t ldc, int M, int N, int64_t K, int n_slabs, int64_t k_slab, int64_t c_slab_stride,
                         const float* bias, cudaStream_t st) {
-  dim3 grid(ceil_div(N, kBN), ceil_div(M, kBM), n_slabs);
+  dim3 grid(ceil_div(M, kBM), ceil_div(N, kBN), n_slabs);
   const bool ak = sak == 1, bn = sbn == 1;
   if (ak && bn) count_launch(), sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);
   else if (ak && !bn) count_launch(), sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_slab, c_slab_stride, bias);

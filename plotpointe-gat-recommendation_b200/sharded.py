@@ -464,18 +464,24 @@ class ShardedGAT:
     # -------------------------------------------------------------------------------------------- per-head streaming
     def _x0_bf16(self, dst: torch.Tensor) -> None:
         """Layer-0 input rows [user rows | item_proj(features)] as bf16 into ``dst`` [n_max, C] (recomputed in the backward
-        instead of being kept: it is a function of parameters and inputs only)."""
+        instead of being kept: it is a function of parameters and inputs only).  The item rows go through an fp32 staging
+        buffer of at most 2 M rows at a time (config 5: 15 GB if done in one piece)."""
         lib, C = self._lib, self.hidden
         st = lib.stream()
-        cu = self.plan.cu
-        x = self._empty(self.n_max, C)
-        x[:cu].copy_(self.user_emb.detach())
+        cu, ci = self.plan.cu, self.plan.ci
+        if cu:
+            lib.call("b200gat_cast_bf16", lib.ptr(self.user_emb.detach()), lib.ptr(dst), cu * C, 1.0, st)
         dwb = lib.dense_workspace_bytes(1, C, max(C, self.feat_dim))
         dws = self._empty(dwb, dtype=torch.uint8)
-        if self.plan.ci:
-            lib.call("b200gat_linear_tc_f32", lib.ptr(self.feats_loc), lib.ptr(self.item_proj.weight), lib.ptr(self.item_proj.bias),
-                     self.plan.ci, self.feat_dim, C, lib.ptr(x, cu * C), C, lib.ptr(dws), dwb, st)
-        lib.call("b200gat_cast_bf16", lib.ptr(x), lib.ptr(dst), self.n_max * C, 1.0, st)
+        chunk = 2_000_000
+        x = self._empty(min(chunk, max(ci, 1)), C)
+        for lo in range(0, ci, chunk):
+            n = min(chunk, ci - lo)
+            lib.call("b200gat_linear_tc_f32", lib.ptr(self.feats_loc, lo * self.feat_dim), lib.ptr(self.item_proj.weight),
+                     lib.ptr(self.item_proj.bias), n, self.feat_dim, C, lib.ptr(x), C, lib.ptr(dws), dwb, st)
+            lib.call("b200gat_cast_bf16", lib.ptr(x), lib.ptr(dst, (cu + lo) * C), n * C, 1.0, st)
+        if self.n_max > self.n_loc:
+            dst[self.n_loc:].zero_()              # padding rows travel with the block: keep them finite
 
     def _forward_stream(self, _exchange_follows: bool) -> torch.Tensor:
         """heads > 1 one head at a time: [N, heads*C] never exists.  Per layer: the bf16 input rows are exchanged once, then for
@@ -528,7 +534,7 @@ class ShardedGAT:
             fab.wait(self.CH_Z)
         return out
 
-    def _backward_stream(self, dout: torch.Tensor, grads: dict) -> torch.Tensor:
+    def _backward_stream(self, dout_box: list, grads: dict) -> torch.Tensor:
         """Backward of the streamed layers.  Nothing per-head was kept but scalars: h of the local source rows is re-projected
         per head, and t_i = sum_k alpha_ik dalpha_ik comes out of a first pass over the edges (two-phase backward, edge.cu)."""
         lib, H, C, fab = self._lib, self.heads, self.hidden, self.fab
@@ -539,6 +545,7 @@ class ShardedGAT:
         dws = self._empty(dwb, dtype=torch.uint8)
         sb = self.sched_bwd
         e_loc = max(self.g_bwd.n_edges, 1)
+        dout = dout_box.pop()                 # the only reference: it is released below, before dx / dh are allocated
         for l in reversed(range(L)):
             x_keep, s_heads, rs_heads, p, seed = self.saved[l]
             if x_keep is None:
@@ -550,6 +557,7 @@ class ShardedGAT:
             # gathered dout, bf16, already carrying the 1/heads of the head mean (exact: a power of two)
             dg = fab.view("X0", (self.n_max, C), torch.bfloat16, self.rank * blk)
             lib.call("b200gat_cast_bf16", lib.ptr(dout), lib.ptr(dg), self.n_max * C, 1.0 / H, st)
+            dout = None                           # [n_max, C] fp32 (15 GB at config 5): free it before the next allocations
             fab.signal(self.CH_B(l))
             parts = [("X0", blk)]
             fab.allgather(self.CH_B(l), parts)
@@ -652,7 +660,9 @@ class ShardedGAT:
         dws = self._empty(dwb, dtype=torch.uint8)
         d_dt = torch.bfloat16 if self.bf16 else torch.float32
         if self.stream:
-            dout = self._backward_stream(dout, grads)
+            box = [dout]
+            del dout
+            dout = self._backward_stream(box, grads)
         for l in (reversed(range(L)) if not self.stream else ()):
             x, h_full, s_full, rowstat, out_h, p, seed = self.saved[l]
             nodestat = self._block(f"NS{l}", H * 4, torch.float32)
@@ -720,6 +730,8 @@ class ShardedGAT:
         return loss.view(())
 
     def train_step(self, u, i, j, loss_kind: str = "bpr") -> torch.Tensor:
+        for p_ in [self.user_emb] + self.replicated:      # last step's gradients (config 5: 5 GB of user rows) are dead weight now
+            p_.grad = None
         z = self.forward(_exchange_follows=True)
         loss = self.loss_and_backward(z, u, i, j, loss_kind)
         self.opt.step()

@@ -349,6 +349,11 @@ int b200gat_peer_signal(const void* const* bases /*host*/, int world, int rank, 
 int b200gat_peer_wait(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, void* stream);
 int b200gat_peer_allgather(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, int n_parts,
                            const uint64_t* offsets /*host*/, const uint64_t* block_bytes /*host*/, void* stream);
+/* Push variant of the gather: stores this rank's block of every part into the same place of every peer's buffer (reads local
+ * memory once, posted NVLink writes).  Follow it with b200gat_peer_signal on a channel of its own and have the consumer
+ * b200gat_peer_wait on that channel. */
+int b200gat_peer_push(const void* const* bases, int world, int rank, int n_parts, const uint64_t* offsets,
+                      const uint64_t* block_bytes, void* stream);
 int b200gat_peer_reduce_f32(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, uint64_t offset,
                             int64_t first, int64_t n, float* out, void* stream);
 

@@ -154,6 +154,38 @@ __global__ void __launch_bounds__(kPullThreads) peer_allgather_kernel(PeerTable 
   }
 }
 
+// Push variant of the gather: this rank reads ITS block once (local HBM) and stores it into the same place of every peer's
+// buffer (posted NVLink writes).  Nothing to wait for before it starts -- the peers are done with that region, by the same
+// argument that lets a producer overwrite its own block -- and the "my pushes have landed" signal is raised afterwards (the
+// kernel boundary orders the stores before the signal kernel's fence + release store); the consumer waits on that channel.
+__global__ void __launch_bounds__(kPullThreads) peer_push_kernel(PeerTable t, GatherPart p0, GatherPart p1, int n_parts, int rank, int world) {
+  const int others = world - 1;
+  for (int part = 0; part < n_parts; ++part) {
+    const GatherPart gp = part == 0 ? p0 : p1;
+    const uint64_t n_chunks = (gp.block_bytes + kPullChunk - 1) / kPullChunk;
+    const uint64_t block_off = gp.off + (uint64_t)rank * gp.block_bytes;
+    const char* src = reinterpret_cast<const char*>(t.base[rank]) + block_off;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+      const uint64_t pos = c * kPullChunk;
+      uint4 v[kPullUnroll];
+#pragma unroll
+      for (int k = 0; k < kPullUnroll; ++k) {
+        const uint64_t b = pos + ((uint64_t)k * kPullThreads + threadIdx.x) * 16;
+        if (b < gp.block_bytes) v[k] = *reinterpret_cast<const uint4*>(src + b);
+      }
+      for (int q = 0; q < others; ++q) {
+        const int peer = (rank + 1 + (int)((c + q) % others)) % world;      // neighbouring blocks start with different peers
+        char* dst = reinterpret_cast<char*>(t.base[peer]) + block_off;
+#pragma unroll
+        for (int k = 0; k < kPullUnroll; ++k) {
+          const uint64_t b = pos + ((uint64_t)k * kPullThreads + threadIdx.x) * 16;
+          if (b < gp.block_bytes) *reinterpret_cast<uint4*>(dst + b) = v[k];
+        }
+      }
+    }
+  }
+}
+
 // out[i] = sum over ranks p = 0..world-1 (fixed order: every rank gets the same bits) of peer_p.region[first + i]
 __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, uint64_t off, int64_t first, int64_t n, float* __restrict__ out,
                                                           int rank, int world, int channel, uint32_t epoch) {
@@ -220,6 +252,28 @@ extern "C" int b200gat_peer_allgather(const void* const* bases, int world, int r
   const uint64_t chunks = (total / kPullChunk + 2) * (uint64_t)(world - 1);
   const int grid = (int)(chunks < (uint64_t)kNumSMs * 4 ? chunks : (uint64_t)kNumSMs * 4);
   count_launch(), peer_allgather_kernel<<<grid, kPullThreads, 0, (cudaStream_t)stream>>>(t, p[0], p[1], n_parts, rank, world, channel, epoch);
+  B200GAT_LAUNCH_CHECK();
+  return kOk;
+}
+
+extern "C" int b200gat_peer_push(const void* const* bases, int world, int rank, int n_parts, const uint64_t* offsets,
+                                 const uint64_t* block_bytes, void* stream) {
+  PeerTable t;
+  int rc = make_table(bases, world, &t);
+  if (rc) return rc;
+  B200GAT_CHECK_ARG(n_parts >= 1 && n_parts <= 2 && offsets && block_bytes, "1 or 2 parts per gather");
+  GatherPart p[2] = {{0, 0}, {0, 0}};
+  uint64_t total = 0;
+  for (int k = 0; k < n_parts; ++k) {
+    B200GAT_CHECK_ARG(offsets[k] % 16 == 0 && block_bytes[k] % 16 == 0, "gather parts must be 16-byte aligned");
+    p[k].off = offsets[k];
+    p[k].block_bytes = block_bytes[k];
+    total += block_bytes[k];
+  }
+  if (world == 1 || total == 0) return kOk;
+  const uint64_t chunks = total / kPullChunk + 2;
+  const int grid = (int)(chunks < (uint64_t)kNumSMs * 4 ? chunks : (uint64_t)kNumSMs * 4);
+  count_launch(), peer_push_kernel<<<grid, kPullThreads, 0, (cudaStream_t)stream>>>(t, p[0], p[1], n_parts, rank, world);
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -126,6 +126,12 @@ class PeerFabric:
         The peers' blocks are never produced, so results are meaningless -- it exists to time one rank's kernels."""
         self.lib, self.world, self.rank, self.dev = lib, world, rank, dev
         self.loopback = loopback
+        # row gathers: "pull" (wait for the peers' signals, read their blocks) or "push" (store this rank's block into every
+        # peer's buffer, then signal); channel n_channels + ch carries the "pushes have landed" signal of gather channel ch
+        import os
+        self.mode = os.environ.get("B200GAT_EXCHANGE", "push" if world > 2 else "pull")
+        self.n_channels = n_channels
+        n_channels = 2 * n_channels
         fb = ctypes.c_size_t(0)
         lib._check(lib._lib.b200gat_peer_flag_bytes(n_channels, ctypes.byref(fb)), "peer_flag_bytes")
         self.off: Dict[str, int] = {}
@@ -226,6 +232,14 @@ class PeerFabric:
         lib = self.lib
         offs = (ctypes.c_uint64 * len(parts))(*[self.off[n] for n, _ in parts])
         blks = (ctypes.c_uint64 * len(parts))(*[int(b) for _, b in parts])
+        if self.mode == "push" and self.world > 1:
+            def push():
+                lib._check(lib._lib.b200gat_peer_push(self.bases, self.world, self.rank, len(parts), offs, blks, lib.stream()), "peer_push")
+                self.signal(self.n_channels + ch)
+                c2 = self.n_channels + ch
+                lib._check(lib._lib.b200gat_peer_wait(self.bases, self.world, self.rank, c2, self.epoch[c2], lib.stream()), "peer_wait")
+            self._timed("allgather", push)
+            return
         self._timed("allgather", lambda: lib._check(lib._lib.b200gat_peer_allgather(
             self.bases, self.world, self.rank, ch, self.epoch[ch], len(parts), offs, blks, lib.stream()), "peer_allgather"))
 
@@ -947,7 +961,9 @@ def bench_main(args, cfg, rank: int, world: int, dev: torch.device) -> None:
     ms_step, e2e_ms = float(ms), float(e2e)
     if rank == 0:
         conf = B.config_dict(cfg, nu, ni, n_inter, k, world)
-        conf["exchange"] = ("device-side pulls over peer-mapped memory (flag wait + all-SM NVLink reads), no library collective in the step; "
+        how = ("pushes (every rank stores its block into the peers' buffers with all SMs, then signals)" if tr.fab.mode == "push"
+               else "pulls (flag wait + all-SM NVLink reads of the peers' blocks)")
+        conf["exchange"] = (f"device-side {how} over peer-mapped memory, no library collective in the step; "
                             + ("layer inputs x exchanged, every rank projects all rows" if tr.x_exchange else "projected rows [h|s] exchanged"))
         conf["rows_per_rank"] = tr.n_loc
         conf["heads_streamed"] = bool(tr.stream)

@@ -349,6 +349,18 @@ int b200gat_peer_signal(const void* const* bases /*host*/, int world, int rank, 
 int b200gat_peer_wait(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, void* stream);
 int b200gat_peer_allgather(const void* const* bases /*host*/, int world, int rank, int channel, uint32_t epoch, int n_parts,
                            const uint64_t* offsets /*host*/, const uint64_t* block_bytes /*host*/, void* stream);
+/* Fused projection + exchange (row-sharded path; heads == 1, in_features == channels == 128, tensor-core mode; otherwise
+ * B200GAT_ERR_UNSUPPORTED and the caller projects, then pushes): the tcgen05 GEMM's epilogue stores every output tile -- and
+ * the logits -- into this rank's block of each peer's mapped exchange buffer as well as locally, so the NVLink transfer runs
+ * under the GEMM.  peer_h[q] / peer_s[q] / peer_dx[q]: the address of row 0 of this call's h / s / dx in peer q's buffer.
+ * Follow with b200gat_peer_signal on a channel of its own; the consumer waits on that channel (as after b200gat_peer_push). */
+int b200gat_project_push_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                             int in_features, int heads, int channels, float* h, float* s, void* const* peer_h,
+                             void* const* peer_s, int n_peers, void* workspace, size_t workspace_bytes, void* stream);
+int b200gat_project_bwd_push_f32(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
+                                 const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx,
+                                 void* const* peer_dx, int n_peers, float* dW, float* da_src, float* da_dst, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* Push variant of the gather: stores this rank's block of every part into the same place of every peer's buffer (reads local
  * memory once, posted NVLink writes).  Follow it with b200gat_peer_signal on a channel of its own and have the consumer
  * b200gat_peer_wait on that channel. */

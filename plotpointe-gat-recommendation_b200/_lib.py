@@ -94,6 +94,9 @@ _SIGS = {
     "b200gat_peer_signal": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, _P]),
     "b200gat_peer_wait": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, _P]),
     "b200gat_peer_allgather": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, c_int, _P, _P, _P]),
+    "b200gat_project_push_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "b200gat_project_bwd_push_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P,
+                                             c_size_t, _P]),
     "b200gat_peer_push": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "b200gat_peer_reduce_f32": (c_int, [_P, c_int, c_int, c_int, ctypes.c_uint32, c_uint64, c_int64, c_int64, _P, _P]),
     "b200gat_rank_loss_fwd_peer_f32": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_int64, c_int64, c_int64,

@@ -196,9 +196,11 @@ bool tc_supported(int in_features, int heads, int channels);
 int tc_parts();
 size_t tc_workspace_bytes(int heads);
 int tc_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int heads,
-                   float* h, float* s, void* workspace, cudaStream_t st);
+                   float* h, float* s, void* workspace, cudaStream_t st, float* const* peer_h = nullptr, float* const* peer_s = nullptr,
+                   int n_peers = 0);
 int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
-                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st);
+                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st,
+                   float* const* peer_dx = nullptr, int n_peers = 0);
 int tc_linear_fwd(const float* x, const float* W, const float* bias, int64_t n_rows, float* out, int64_t ldo, void* workspace,
                   cudaStream_t st);
 int tc_linear_dw(const float* x, const float* dy, int64_t n_rows, float* dW, void* workspace, cudaStream_t st);
@@ -244,6 +246,55 @@ extern "C" int b200gat_project_f32(const float* x, const float* W, const float* 
   count_launch(), logits_kernel<<<ceil_div(n_rows * 32, 128), 128, 0, st>>>(h, a_src, a_dst, n_rows, heads, channels, s);
   B200GAT_LAUNCH_CHECK();
   return kOk;
+}
+
+// Fused projection + exchange for the row-sharded path (heads == 1, in_features == channels == 128, tensor-core mode): the
+// GEMM epilogue stores every h tile and the logits into this rank's block of each peer's exchange buffer as well as into the
+// local one, so the NVLink transfer runs under the GEMM instead of after it.  peer_h[q] / peer_s[q]: where h / s (row 0 of
+// this call) live in peer q's mapped buffer.  Returns kErrUnsupported for other shapes (the caller then projects and pushes).
+extern "C" int b200gat_project_push_f32(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows,
+                                        int in_features, int heads, int channels, float* h, float* s, void* const* peer_h,
+                                        void* const* peer_s, int n_peers, void* workspace, size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && h && s, "null pointer");
+  B200GAT_CHECK_ARG(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || (peer_h && peer_s)), "0..7 peers");
+  if (!(heads == 1 && tc_supported(in_features, heads, channels) && (tc_parts() & 1))) {
+    set_error("fused projection + exchange needs heads == 1, in_features == channels == 128 and the tensor-core GEMM mode");
+    return kErrUnsupported;
+  }
+  B200GAT_CHECK_ARG(workspace && workspace_bytes >= tc_workspace_bytes(heads), "workspace too small for the tensor-core path");
+  if (n_rows == 0) return kOk;
+  float* ph[7];
+  float* ps[7];
+  for (int q = 0; q < n_peers; ++q) {
+    B200GAT_CHECK_ARG(peer_h[q] && peer_s[q], "null peer pointer");
+    ph[q] = (float*)peer_h[q];
+    ps[q] = (float*)peer_s[q];
+  }
+  return tc_project_fwd(x, W, a_src, a_dst, n_rows, heads, h, s, workspace, (cudaStream_t)stream, ph, ps, n_peers);
+}
+
+// The same for the backward: dx (the next layer's dout) is stored into the peers' buffers from the dx GEMM's epilogue.
+extern "C" int b200gat_project_bwd_push_f32(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh,
+                                            const float* ds, int64_t n_rows, int in_features, int heads, int channels, float* dx,
+                                            void* const* peer_dx, int n_peers, float* dW, float* da_src, float* da_dst,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+  B200GAT_CHECK_ARG(x && W && a_src && a_dst && dh && ds && dx && dW && da_src && da_dst && workspace, "null pointer");
+  B200GAT_CHECK_ARG(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || peer_dx), "0..7 peers");
+  if (!(heads == 1 && tc_supported(in_features, heads, channels) && (tc_parts() & 6) == 6)) {
+    set_error("fused projection backward + exchange needs heads == 1, in_features == channels == 128 and the tensor-core GEMM mode");
+    return kErrUnsupported;
+  }
+  size_t need;
+  b200gat_dense_workspace_bytes(heads, channels, in_features, &need);
+  B200GAT_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  if (n_rows == 0) return b200gat_project_bwd_f32(x, W, a_src, a_dst, const_cast<float*>(dh), ds, n_rows, in_features, heads, channels, dx,
+                                                  dW, da_src, da_dst, workspace, workspace_bytes, stream);
+  float* pd[7];
+  for (int q = 0; q < n_peers; ++q) {
+    B200GAT_CHECK_ARG(peer_dx[q], "null peer pointer");
+    pd[q] = (float*)peer_dx[q];
+  }
+  return tc_project_bwd(x, W, a_src, a_dst, dh, ds, n_rows, heads, dx, dW, da_src, da_dst, workspace, (cudaStream_t)stream, pd, n_peers);
 }
 
 // Given dh (aggregation part, overwritten with the full dh) and ds = [ds_src|ds_dst]:

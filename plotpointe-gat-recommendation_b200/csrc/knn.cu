@@ -37,11 +37,13 @@ constexpr int kCand = 48;                  // approximate candidates kept per ro
 constexpr int kBStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA warp + producer warp
+constexpr int kStage = 32;                 // staged (similarity, column) pairs per row between two merges into the register list
+constexpr int kStageBytesPerWarp = kStage * 32 * 8;   // [entry][lane] uint2: 8 KB
 template <int KC> struct Cfg {
   static constexpr int kNA = KC == 1 ? 2 : 1;                       // A row blocks resident per CTA
   static constexpr int kD = KC * kChunkD;
   static constexpr int kBlkBytes = KC * kChunkBytes;
-  static constexpr int kSmem = 1024 + kNA * kBlkBytes + kBStages * kChunkBytes + 256;
+  static constexpr int kSmem = 1024 + kNA * kBlkBytes + kBStages * kChunkBytes + kNA * 4 * kStageBytesPerWarp + 256;
 };
 // Bound on |bf16 similarity - exact| used by the safety guard: both operands are rounded to nearest (u = 2^-9), so the
 // error is at most (2u + u^2) * sum|a_i b_i| <= 3.91e-3 for unit rows of any width; fp32 accumulation adds ~1e-6.
@@ -93,9 +95,18 @@ __global__ void __launch_bounds__(128) prepare_kernel(const float* __restrict__ 
 }
 
 // ---- 2. candidates --------------------------------------------------------------------------------------------------
-// The running top-64 of a row lives in REGISTERS as a descending list.  Insertion is a fully unrolled bubble pass
+// The running top-48 of a row lives in REGISTERS as a descending list.  Insertion is a fully unrolled bubble pass
 // (compare, conditional swap) -- no local memory, no dependent address chain; lanes that have nothing to insert carry
-// v = -inf through the pass and leave their list untouched, so the pass runs once per warp per accepted column.
+// v = -inf through the pass and leave their list untouched.
+//
+// A pass costs the whole warp ~250 instructions whichever of its 32 rows it serves, and a row accepts
+// ~kCand * ln(n / kCand) columns over a sweep (444 at 498 k items), almost never in the same chunk as its neighbours: with one
+// pass per accepted column the epilogue, not the tensor pipe, bounded the kernel (measured with diagnostic builds at
+// 498,196 x 128-d: 45.7 ms when the epilogue only scans -- chunk maximum + vote --, 113.6 ms with the insertions).  Accepted
+// columns are therefore only APPENDED to a per-row staging area in shared memory (one predicated 8-byte store each), and
+// the lists are brought up to date in batches: when some row of the warp has fewer than 8 free staging slots, every row
+// merges what it has staged -- pass t serves entry t of all 32 rows at once.  Between two merges a row's admission
+// threshold is stale (too low), which only means a few more appends; nothing a fresh threshold would have kept is lost.
 template <int N>
 struct TopList {
   float s[N];
@@ -127,6 +138,9 @@ struct TopList {
 // on the estimate: columns outside the final list have approximate similarity <= max(threshold, 48th entry), which is the
 // bound the re-rank guard uses; a row whose exact k-th neighbour does not clear it is redone exactly (that needs the
 // threshold to rank above ~30 among all columns: P < 1e-7 for a random sample, certain only for adversarial layouts).
+#ifndef KNN_DIAG
+#define KNN_DIAG 0     // diagnostic builds only: 1 the epilogue scans (chunk maximum + vote) but never inserts, 2 it does not read TMEM at all
+#endif
 constexpr int kSampleStride = 16, kSampleKeep = 12, kSampleMinBlocks = 64;
 
 // SAMPLE: sweep the column blocks j0, j0 + kSampleStride, ... and write thr_out[row] = the kSampleKeep-th best similarity seen.
@@ -144,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + NA * kBlkBytes, sBar = sB + kBStages * kChunkBytes;
+  const uint32_t sA = base, sB = base + NA * kBlkBytes, sStage = sB + kBStages * kChunkBytes, sBar = sStage + NA * 4 * kStageBytesPerWarp;
   const uint32_t bar_afull = sBar, bar_aempty = sBar + 8, bar_bfull = sBar + 16, bar_bempty = sBar + 48, bar_tfull = sBar + 80,
                  bar_tempty = sBar + 96;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 128);
@@ -229,56 +243,97 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
     // =============================== epilogue: running top-48 per row ==========================================
     const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
     TopList<kList> top;
+    const uint32_t stage0 = sStage + warp * kStageBytesPerWarp + lane * 8;     // entry k of this row: stage0 + k * 256
     uint32_t ts = 0, tph = 0;
     for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
-      const int64_t row = ((int64_t)(NA * sb + a)) * kBlk + q * 32 + lane;
-      const bool live = (NA * sb + a) < n_blocks && row < n;
+      const int row = (NA * sb + a) * kBlk + q * 32 + lane;          // n < 2^31 (checked by the entry point)
+      const int ni = (int)n;
+      const bool live = (NA * sb + a) < n_blocks && row < ni;
       top.reset();
-      const float thr0 = live ? ((!SAMPLE && thr_in) ? thr_in[row] : -INFINITY) : INFINITY;      // padding rows never insert
+      const float thr0 = live ? ((!SAMPLE && thr_in) ? thr_in[row] : -INFINITY) : INFINITY;      // padding rows never append
       float thr = thr0;
+      int cnt = 0;                                  // staged entries of this row
+      // merge the staged entries of all 32 rows into their lists: pass k serves entry k of every row that has one
+      auto flush = [&]() {
+        const int most = __reduce_max_sync(kFull, cnt);
+        for (int k = 0; k < most; ++k) {
+          float sv = -INFINITY;
+          int sc = -1;
+          if (k < cnt) {
+            const uint2 e = ld_shared_u2(stage0 + k * 256);
+            sv = __uint_as_float(e.x);
+            sc = (int)e.y;
+          }
+          if (!__any_sync(kFull, sv > top.s[kList - 1])) continue;     // stale threshold: nothing of this pass still qualifies
+          top.insert(sv, sc);
+        }
+        cnt = 0;
+        if (live) thr = fmaxf(thr0, top.s[kList - 1]);
+      };
       for (int j = 0; j < n_blocks; j += kJStep) {
         mbar_wait(bar_tfull + 8 * ts, tph);
         tc_fence_after();
+        // the diagonal and the columns past the last item must never be appended: only the row block's own column block and
+        // the last block can contain them (warp-uniform test)
+        const bool edge = j == NA * sb + a || (j + 1) * kBlk > ni;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (KNN_DIAG & 2) continue;
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (ts * 2 + a) * 128 + c * 32, v);
-          const int64_t col0 = (int64_t)j * kBlk + c * 32;
-          // Per lane: bit mask of the columns of this chunk that beat the row's current threshold; then ONE copy of
-          // the insertion pass in a loop -- each lane feeds its own next pending column, so the loop runs
-          // max-over-lanes(popcount) times (usually 0 or 1) and the code stays a few KB (a pass per column position was
-          // 170 KB of SASS and instruction-fetch bound).
-          float vmax = v[0];
+          const int col0 = j * kBlk + c * 32;
+          if (edge) {
 #pragma unroll
-          for (int t = 1; t < 32; ++t) vmax = fmaxf(vmax, v[t]);
+            for (int t = 0; t < 32; ++t)
+              if (col0 + t == row || col0 + t >= ni) v[t] = -INFINITY;
+          }
+          // maxima of the four 8-column groups, then of the chunk
+          float g[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            g[u] = fmaxf(fmaxf(fmaxf(v[8 * u], v[8 * u + 1]), fmaxf(v[8 * u + 2], v[8 * u + 3])),
+                         fmaxf(fmaxf(v[8 * u + 4], v[8 * u + 5]), fmaxf(v[8 * u + 6], v[8 * u + 7])));
+          }
+          const float vmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
           if (!__any_sync(kFull, vmax > thr)) continue;          // nothing in this chunk beats any row's threshold
-          unsigned pend = 0;
-#pragma unroll
-          for (int t = 0; t < 32; ++t) pend |= (v[t] > thr ? 1u : 0u) << t;
-          if ((row >= col0 && row < col0 + 32)) pend &= ~(1u << (int)(row - col0));          // the diagonal
-          if (col0 + 32 > n) pend &= (col0 < n) ? ((1u << (int)(n - col0)) - 1u) : 0u;          // past the last item
-          while (__any_sync(kFull, pend != 0)) {
-            const int t = pend ? (__ffs(pend) - 1) : 0;
-            float sel = v[0];
-#pragma unroll
-            for (int k = 1; k < 32; ++k) sel = (t == k) ? v[k] : sel;
-            top.insert(pend ? sel : -INFINITY, (int)(col0 + t));
-            pend &= pend - 1;
-            if (live) thr = fmaxf(thr0, top.s[kList - 1]);
+          if (KNN_DIAG & 1) { if (vmax == 12345.f) thr = 0.f; continue; }
+          // groups in which some row has a hit (warp-uniform mask); a group appends at most 8 entries per row
+          unsigned gmask = __reduce_or_sync(kFull, (g[0] > thr ? 1u : 0u) | (g[1] > thr ? 2u : 0u) | (g[2] > thr ? 4u : 0u) | (g[3] > thr ? 8u : 0u));
+          while (gmask) {
+            const int u = __ffs(gmask) - 1;
+            gmask &= gmask - 1;
+            if (__any_sync(kFull, cnt > kStage - 8)) flush();     // single call site: the merge is ~1.5 KB of code
+            const int cbase = col0 + 8 * u;
+#define KNN_APPEND8(U)                                                                                     \
+  _Pragma("unroll") for (int t = 0; t < 8; ++t) {                                                          \
+    const float x = v[8 * (U) + t];                                                                        \
+    if (x > thr) {                                                                                         \
+      st_shared_u2(stage0 + cnt * 256, __float_as_uint(x), (uint32_t)(cbase + t));                        \
+      ++cnt;                                                                                               \
+    }                                                                                                      \
+  }
+            switch (u) {
+              case 0: KNN_APPEND8(0) break;
+              case 1: KNN_APPEND8(1) break;
+              case 2: KNN_APPEND8(2) break;
+              default: KNN_APPEND8(3) break;
+            }
+#undef KNN_APPEND8
           }
         }
         tc_fence_before();
         mbar_arrive(bar_tempty + 8 * ts);
         if (++ts == 2) { ts = 0; tph ^= 1; }
       }
+      flush();
       if (live) {
         if (SAMPLE) {
           thr_out[row] = top.s[kList - 1];
         } else {
 #pragma unroll
           for (int k = 0; k < kList; ++k) {
-            cand_sim[row * kCand + k] = top.s[k];
-            cand_idx[row * kCand + k] = top.i[k];
+            cand_sim[(int64_t)row * kCand + k] = top.s[k];
+            cand_idx[(int64_t)row * kCand + k] = top.i[k];
           }
           bound_out[row] = fmaxf(thr0, top.s[kList - 1]);
         }
@@ -505,12 +560,14 @@ static int knn_run(const float* emb, int64_t n_items, int k, float min_similarit
                                                                                            nullptr, thr, nullptr);
   count_launch(), knn::candidates_kernel<KC, false><<<grid, knn::kThreads, C::kSmem, st>>>(image, n_items, n_blocks, cand_sim, cand_idx,
                                                                                           sample ? thr : nullptr, nullptr, bound);
+#if KNN_DIAG == 0
   count_launch(), knn::rerank_kernel<KC><<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
                                                                                       nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows,
                                                                                       bound);
   // rows whose bf16 margin was too thin: exact scan of all columns (no-op when the list is empty)
   count_launch(), knn::exact_rows_kernel<KC><<<kNumSMs * 2, 256, 0, st>>>(en, n_items, unsafe_rows, n_unsafe, k, min_similarity, nbr_idx,
                                                                          nbr_sim, counts);
+#endif
   B200GAT_LAUNCH_CHECK();
   return kOk;
 }

@@ -106,6 +106,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+__device__ __forceinline__ void st_shared_u2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  return r;
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128B swizzle, version 1 (Blackwell). Offsets in bytes.
 // layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the form MN-major

@@ -128,6 +128,28 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                : "memory");
 }
 
+// "cache streaming" accesses: the line is allocated evict-first in L2, so data that is touched once per launch (index lists,
+// the rows a kernel writes) does not push the randomly gathered feature rows out of L2
+__device__ __forceinline__ void st_cs4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs1(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ int ld_cs_i32(const int32_t* p) {
+  int r;
+  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_cs4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_cs2u(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float4 fma4(float a, float4 b, float4 c) {
   c.x = fmaf(a, b.x, c.x);
   c.y = fmaf(a, b.y, c.y);

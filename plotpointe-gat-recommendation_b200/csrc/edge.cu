@@ -67,6 +67,23 @@ template <> struct Raw4<float> { using type = float4; };
 template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
 __device__ __forceinline__ float4 ld_raw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint2 ld_raw4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+#ifndef EDGE_L2_HINTS
+#define EDGE_L2_HINTS 1      // A/B knob: the half-warp backward marks what it touches once per launch (edge ids, the h row a
+#endif                       // half-warp owns, the dh row it writes) evict-first in L2.  Measured at config 2, two runs each:
+                             // backward 2.651 -> 2.628 ms per step (bf16 tier 1.937 -> 1.901); the same hints in the forward
+                             // kernel cost 0.01 ms (its output is the next kernel's input) and are not applied
+// once-per-launch variants of the loads above
+__device__ __forceinline__ float4 ld_once4(const float* p) { return EDGE_L2_HINTS ? ld_cs4(p) : ld_raw4(p); }
+__device__ __forceinline__ uint2 ld_once4(const __nv_bfloat16* p) { return EDGE_L2_HINTS ? ld_cs2u(p) : ld_raw4(p); }
+__device__ __forceinline__ int ld_once(const int32_t* p) { return EDGE_L2_HINTS ? ld_cs_i32(p) : __ldg(p); }
+__device__ __forceinline__ void st_once4(float* p, float4 v) {
+  if (EDGE_L2_HINTS) st_cs4(p, v);
+  else *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ void st_once(float* p, float v) {
+  if (EDGE_L2_HINTS) st_cs1(p, v);
+  else *p = v;
+}
 __device__ __forceinline__ float4 to_f4(float4 v) { return v; }
 __device__ __forceinline__ float4 to_f4(uint2 v) {   // bf16 -> fp32 is a 16-bit shift
   return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
@@ -970,18 +987,18 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
   float ssj = 0.f, dss = 0.f;
   if (beg < end) {   // false for the dead half too (beg = end = 0)
     ssj = __ldg(s + j * 2);
-    hj0 = to_f4(ld_raw4(h + j * C + ch0));
-    hj1 = to_f4(ld_raw4(h + j * C + ch1));
+    hj0 = to_f4(ld_once4(h + j * C + ch0));
+    hj1 = to_f4(ld_once4(h + j * C + ch1));
   }
   const int nch_mine = (end - beg + 15) >> 4;
   const int nch = max(nch_mine, __shfl_xor_sync(kFull, nch_mine, 16));
-  int i_next = (beg + sl < end) ? __ldg(row + beg + sl) : 0;
+  int i_next = (beg + sl < end) ? ld_once(row + beg + sl) : 0;
   for (int ch = 0; ch < nch; ++ch) {
     const int base = beg + ch * 16;
     const int q = base + sl;
     const bool valid = q < end;
     const int i = i_next;
-    if (ch + 1 < nch) i_next = (q + 16 < end) ? __ldg(row + q + 16) : 0;   // next chunk's ids: one load latency off the chain
+    if (ch + 1 < nch) i_next = (q + 16 < end) ? ld_once(row + q + 16) : 0;   // next chunk's ids: one load latency off the chain
     const int cnt = min(16, end - base);
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
     constexpr int NB = EDGE_NB16_BWD;
@@ -1006,7 +1023,7 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
       const float alpha = expf(zc - st.y) * st.z;
       const float gsc = (z0 > 0.f ? 1.f : neg_slope) * pass;
       float ks = 1.f;
-      if (DROPOUT) ks = dropout_scale(seed, (uint32_t)__ldg(perm_csc + q), 0, p_drop, inv_keep);
+      if (DROPOUT) ks = dropout_scale(seed, (uint32_t)ld_once(perm_csc + q), 0, p_drop, inv_keep);
       agg = alpha * ks;
       gA = agg * gsc;
       cB = alpha * st.w * gsc;
@@ -1042,7 +1059,7 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
       }
     }
     if (valid) {
-      de[q] = my_de;
+      de[q] = my_de;          // read again by ds_dst right after this kernel: left to the default policy
       dss += my_de;
     }
   }
@@ -1056,8 +1073,8 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
     return;
   }
   if (sl == 0) ds_src[(size_t)r * ld_ds] = t;
-  *reinterpret_cast<float4*>(dh + (size_t)r * C + ch0) = acc0;
-  *reinterpret_cast<float4*>(dh + (size_t)r * C + ch1) = acc1;
+  st_once4(dh + (size_t)r * C + ch0, acc0);
+  st_once4(dh + (size_t)r * C + ch1, acc1);
 }
 
 // ---- dispatch helpers ---------------------------------------------------------------------------

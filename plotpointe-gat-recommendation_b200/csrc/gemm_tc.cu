@@ -315,177 +315,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) proj_kernel(FwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// proj_bf16 : h_bf16[n,128] = bf16(x) . bf16(W)^T with fp32 accumulation ("bf16 projection", BASELINE config 3).
-// Operands are rounded to bf16 while they are staged (no split: one UMMA kind::f16 per K step of 16), h is stored as
-// bf16 -- the edge kernels then gather 256-byte rows -- and the logits are still taken from the fp32 accumulator.
-// ------------------------------------------------------------------------------------------------
-constexpr int kHKB = 64;                                    // bf16 elements per 128-byte swizzle row
-constexpr int kHStages = 4;
-constexpr int kHAStageBytes = kTileM * 128;                 // 16 KB
-constexpr int kHBImageBytes = (kK / kHKB) * kTileN * 128;   // 32 KB
-constexpr int kHSmem = 1024 + kHBImageBytes + kHStages * kHAStageBytes + 2 * kTileN * 4 + 256;
-
-// image[kb][row n][64 bf16 swizzled] of W[n, k]
-__global__ void build_b_image_bf16_kernel(const float* __restrict__ w, uint8_t* __restrict__ image) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk (8 consecutive k) each
-  if (idx >= kTileN * kK / 8) return;
-  const int n = idx / (kK / 8), k8 = idx % (kK / 8);
-  const int kb = k8 / 8, chunk = k8 % 8;
-  const float4 a = *reinterpret_cast<const float4*>(w + n * kK + k8 * 8);
-  const float4 b = *reinterpret_cast<const float4*>(w + n * kK + k8 * 8 + 4);
-  *reinterpret_cast<uint4*>(image + kb * (kTileN * 128) + sw128(n, chunk)) = pack8_bf16(a, b);
-}
-
-struct HParams {
-  const float* a;          // x [n_rows, 128] fp32
-  const uint8_t* b_images; // [heads][kHBImageBytes]
-  __nv_bfloat16* out;      // h [n_rows, heads*128] bf16
-  int64_t n_rows;
-  const float* att_src;
-  const float* att_dst;
-  float* s;
-  int heads;
-};
-
-__global__ void __launch_bounds__(kFwdThreads, 1) proj_bf16_kernel(HParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sB = base;
-  const uint32_t sA = sB + kHBImageBytes;
-  float* att = reinterpret_cast<float*>(sm + kHBImageBytes + kHStages * kHAStageBytes);
-  const uint32_t sBar = sA + kHStages * kHAStageBytes + 2 * kTileN * 4;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 32, bar_tfull = sBar + 64, bar_tempty = sBar + 80, bar_b = sBar + 96;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + (sBar - base) + 112);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t n_tiles = (p.n_rows + kTileM - 1) / kTileM;
-  const int64_t ldo = (int64_t)p.heads * kTileN;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kHStages; ++i) {
-      mbar_init(bar_full + 8 * i, kFwdProducerWarps * 32);
-      mbar_init(bar_empty + 8 * i, 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, kFwdEpiWarps * 32);
-    }
-    mbar_init(bar_b, 1);
-    fence_barrier_init();
-  }
-  if (warp == kFwdProducerWarps + kFwdEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
-  for (int i = threadIdx.x; i < 2 * kTileN; i += kFwdThreads)
-    att[i] = i < kTileN ? p.att_src[head * kTileN + i] : p.att_dst[head * kTileN + i - kTileN];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp < kFwdProducerWarps) {
-    const int t = threadIdx.x;
-    const int chunk = t & 7, r0 = t >> 3;
-    constexpr int KB = kK / kHKB;
-    constexpr int R = kProdRows;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_it = my_tiles * KB;
-    struct Ld { float4 v[R][2]; };
-    auto load = [&](int64_t it, Ld& L) {
-      const int64_t row0 = (blockIdx.x + (it / KB) * gridDim.x) * kTileM;
-      const int kb = (int)(it % KB);
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int64_t row = row0 + r0 + kProdStride * i;
-        if (row < p.n_rows) {
-          L.v[i][0] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8);
-          L.v[i][1] = ld_stream4(p.a + row * kK + kb * kHKB + chunk * 8 + 4);
-        } else {
-          L.v[i][0] = L.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    auto store = [&](int64_t it, Ld& L) {
-      const uint32_t stage = (uint32_t)(it % kHStages), phase = (uint32_t)((it / kHStages) & 1);
-      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-      uint8_t* dst = sm + kHBImageBytes + stage * kHAStageBytes;
-#pragma unroll
-      for (int i = 0; i < R; ++i) *reinterpret_cast<uint4*>(dst + sw128(r0 + kProdStride * i, chunk)) = pack8_bf16(L.v[i][0], L.v[i][1]);
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * stage);
-    };
-    Ld l0, l1;   // two k-blocks (64 KB per SM) of loads in flight
-    if (0 < n_it) load(0, l0);
-    for (int64_t it = 0; it < n_it; it += 2) {
-      if (it + 1 < n_it) load(it + 1, l1);
-      store(it, l0);
-      if (it + 1 < n_it) { if (it + 2 < n_it) load(it + 2, l0); store(it + 1, l1); }
-    }
-  } else if (warp == kFwdProducerWarps + kFwdEpiWarps) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_b, kHBImageBytes);
-      bulk_g2s(sB, p.b_images + (size_t)head * kHBImageBytes, kHBImageBytes, bar_b);
-      mbar_wait(bar_b, 0);
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, kTileN);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * kTileN;
-        for (int kb = 0; kb < kK / kHKB; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t a0 = sA + stage * kHAStageBytes, b0 = sB + kb * kTileN * 128;
-#pragma unroll
-          for (int k = 0; k < kHKB / 16; ++k)
-            umma_bf16(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc, (kb | k) != 0);
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == kHStages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(bar_tfull + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row = tile * kTileM + q * 32 + lane;
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
-      float ps = 0.f, pd = 0.f;
-      for (int c = 0; c < kTileN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          ps = fmaf(v[j], att[c * 32 + j], ps);
-          pd = fmaf(v[j], att[kTileN + c * 32 + j], pd);
-        }
-        if (row < p.n_rows) {   // 64 contiguous bytes of this thread's row
-          uint4* o = reinterpret_cast<uint4*>(p.out + row * ldo + head * kTileN + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = pack8_bf16(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-                              make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
-      if (row < p.n_rows) {
-        p.s[row * (2 * p.heads) + head] = ps;
-        p.s[row * (2 * p.heads) + p.heads + head] = pd;
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == kFwdProducerWarps + kFwdEpiWarps) tmem_dealloc(tmem_base, 256);
-}
-
-// ------------------------------------------------------------------------------------------------
 // proj_dw : dW[c, f] = sum_n dh_full[n, c] * x[n, f]   (+ v[q, f] = sum_n ds[n, q] x[n, f])
 // ------------------------------------------------------------------------------------------------
 constexpr int kDwProducerWarps = 8, kDwEpiWarps = 4;
@@ -787,7 +616,6 @@ static int ensure_attrs() {
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem));
-  B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kHSmem));
   B200GAT_CUDA(cudaFuncSetAttribute(tc::proj_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDwSmem));
   once.done();
   return kOk;

@@ -10,8 +10,9 @@
 //   2. candidates: bf16 tcgen05 GEMM of the image against itself.  A CTA keeps a 256-row block of A resident (128 rows
 //                  for 384-d) and streams every 128-row block of B, one 128-wide K chunk at a time, through a 3-deep
 //                  ring of bulk copies; accumulators live in TMEM (2 row blocks x 2 stages x 128 columns = all 512
-//                  columns); 8 epilogue warps read them back (tcgen05.ld) and keep, per row, the 48 best APPROXIMATE
-//                  similarities seen so far in a register-resident list.
+//                  columns); the epilogue warps read them back (tcgen05.ld) and produce, per row, the 48 best APPROXIMATE
+//                  similarities: below 8,192 items as a register-resident running list, above as a pipeline of three sweeps
+//                  (group maxima -> sampled appends -> full-sweep appends against a per-row threshold, see the modes below).
 //   3. re-rank   : exact fp32 dot products for the 48 candidates of every row (warp per row), top-k selection in
 //                  descending order, min_similarity filter.  The final similarities are plain fp32 like the reference's;
 //                  the bf16 pass only decides WHICH 48 columns get the exact treatment, and a per-row guard lists the
@@ -37,6 +38,15 @@ constexpr int kCand = 48;                  // approximate candidates kept per ro
 constexpr int kBStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA warp + producer warp
+// The append sweep runs TWO epilogue warps per (row block, TMEM lane quarter): one takes chunks 0-1 of a tile, the other chunks 2-3,
+// each with its own half of the row's list.  Its epilogue is bound by instruction issue (two warps per scheduler could not keep
+// up with the tensor pipe: 90 ms), not by latency or bytes.
+#ifndef KNN_EPI16
+#define KNN_EPI16 1    // 0: A/B builds with one epilogue warp per (row block, lane quarter) in the append sweep as well
+#endif
+constexpr int kAppendHalves = KNN_EPI16 ? 2 : 1;
+constexpr int kEpiWarpsAppend = 8 * kAppendHalves;
+constexpr int kThreadsAppend = (kEpiWarpsAppend + 2) * 32;
 constexpr int kStage = 32;                 // staged (similarity, column) pairs per row between two merges into the register list
 constexpr int kStageBytesPerWarp = kStage * 32 * 8;   // [entry][lane] uint2: 8 KB
 template <int KC> struct Cfg {
@@ -129,31 +139,90 @@ struct TopList {
   }
 };
 
-// Sampled admission threshold (opt-in, see knn_run).  With a running threshold alone a row accepts ~kCand * ln(n / kCand) columns over a sweep
-// (444 at 498 k items), and every acceptance of any of a warp's 32 rows costs the whole warp one insertion pass: the
-// epilogue, not the tensor pipe, bounded the kernel (tensor pipe 24 % active).  A first sweep over every kSampleStride-th
-// column block keeps only the kSampleKeep best per row; the kSampleKeep-th best of that SUBSET is a valid lower bound of the
-// row's kSampleKeep-th best overall, and in expectation its rank among all columns is kSampleKeep * kSampleStride = 192.
-// The full sweep starts from that threshold: ~48 * (1 + ln 4) = 115 acceptances instead of 444.  Correctness does not rest
-// on the estimate: columns outside the final list have approximate similarity <= max(threshold, 48th entry), which is the
-// bound the re-rank guard uses; a row whose exact k-th neighbour does not clear it is redone exactly (that needs the
-// threshold to rank above ~30 among all columns: P < 1e-7 for a random sample, certain only for adversarial layouts).
+// Modes of the candidates kernel.
+//   kModeLists   : the running top-48 per row in registers (above).  Complete on its own; used for catalogues below
+//                  kAppendMinBlocks column blocks, and as the fallback of the append pipeline.
+// With a running threshold alone a row accepts ~kCand * ln(n / kCand) columns over a sweep (444 at 498 k items) and the
+// register lists, not the tensor pipe, bound the kernel (113.6 -> 90.4 ms with staged merges against a 45.7 ms scan-only
+// floor).  Larger catalogues therefore go through a pipeline in which the full sweep keeps NO list at all:
+//   kModeGroupMax: sweep every kStrideA-th column block; a row keeps the maxima of 64 disjoint column groups (column position
+//                  inside the 32-wide chunk x chunk parity: 64 statically indexed registers, 32 FMNMX per chunk).  The 48th
+//                  largest of the 64 maxima is attained by 48 different columns, hence a lower bound of the row's 48th best
+//                  similarity: thr_A (expected rank among all columns ~ 86 * kStrideA).
+//   kModeAppend  : sweep every jstep-th block and APPEND every (similarity, column) with similarity >= thr to the row's list
+//                  in global memory (one predicated 8-byte store; a per-lane counter).  First with jstep = kStrideB and
+//                  thr_A (~170 appends per row); select_kernel takes the 48th largest of them -- again 48 different columns --
+//                  as thr_B (expected rank 48 * kStrideB); then the full sweep with thr_B (<= 384 +- 52 appends per row) and
+//                  select_kernel keeps the 48 best as the candidate lists of the re-rank.  Inside an append sweep a row's
+//                  threshold climbs a ladder: a rung becomes the threshold once 48 different appended columns have reached it.
+// Every threshold is a valid bound whatever the layout of the catalogue (the columns that produced it are swept again by
+// the next pass, `>=` re-admits them), so each full-sweep list holds at least 48 entries and the bound handed to the
+// re-rank guard, the 48th best approximate similarity, is the same as the register lists'.  Only speed depends on the
+// estimates: a row that appends more than kCap entries in the full sweep (a clump of > kCap near-duplicates that no sampled block
+// showed) is marked unsafe and redone by the exact path; if more than kMaxOverflowRows rows do, the register-list kernel
+// (launched behind a device-side gate, it exits at once otherwise) redoes the sweep for all rows, starting from thr_B.
+// Measured at 498,196 x 128-d (profiles/r2ah_knn_append.md): 3.1 + 12.7 + 2.2 (select) + 59.0 + 3.3 (select) ms for the three
+// sweeps, 84.7 ms for the whole call against 89.6 ms with the register lists (63,001 items: 3.6 against 4.3 ms); the full sweep
+// runs the tensor pipe 51 % active and is bound by the epilogue's ALU/issue rate (136 warp instructions per 32 x 32 chunk).
 #ifndef KNN_DIAG
 #define KNN_DIAG 0     // diagnostic builds only: 1 the epilogue scans (chunk maximum + vote) but never inserts, 2 it does not read TMEM at all
 #endif
-constexpr int kSampleStride = 16, kSampleKeep = 12, kSampleMinBlocks = 64;
+constexpr int kModeLists = 0, kModeGroupMax = 1, kModeAppend = 2;
+constexpr int kStrideA = 16, kStrideB = 8, kAppendMinBlocks = 64;
+constexpr int kCap = 1024;                  // appended entries kept per row (8 KB), one half per epilogue warp of the pair; mean 2 x 192,
+                                            // sd 2 x 37 in the full sweep
+constexpr int kMaxOverflowRows = 64;
 
-// SAMPLE: sweep the column blocks j0, j0 + kSampleStride, ... and write thr_out[row] = the kSampleKeep-th best similarity seen.
-// otherwise: sweep all column blocks starting from thr_in[row] (may be NULL: -inf), write the candidate lists and
-// bound_out[row] = max(thr_in[row], 48th entry) >= the approximate similarity of every column that is NOT in the list.
-template <int KC, bool SAMPLE>
-__global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks,
+// Order-preserving map float -> uint32 (0 is below every real value: the "empty" key)
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// Eight columns of one row against the row's threshold: every similarity >= thr goes to list[min(cnt, cap - 1)] as (similarity,
+// column) and advances cnt.  One PTX block, so that the compares stay where they are (hoisted out of the per-group switch they
+// were paid by every chunk with a hit anywhere: the epilogue is bound by instruction issue) and the stores are predicated, not
+// branched around.  A full list keeps rewriting its last slot; such rows are recognised by their count.
+// Measured alternatives at 498,196 x 128-d (full sweep): C++ with branches 90 ms, predicated stores from C++ 102-120 ms, this block
+// 60.8 ms, staging the 8 values in shared memory and letting lanes 0-7 test one column each 60.4 ms.
+__device__ __forceinline__ void append8(uint2* list, int& cnt, float thr, int cbase, float x0, float x1, float x2, float x3, float x4,
+                                        float x5, float x6, float x7) {
+#define KNN_A1(X, T)                                            \
+  "setp.ge.f32 p, " X ", %2;\n\t"                               \
+  "min.s32 idx, %0, %4;\n\t"                                    \
+  "mad.wide.s32 a, idx, 8, %1;\n\t"                             \
+  "mov.b32 xb, " X ";\n\t"                                      \
+  "add.s32 col, %3, " T ";\n\t"                                 \
+  "@p st.global.v2.b32 [a], {xb, col};\n\t"                     \
+  "@p add.s32 %0, %0, 1;\n\t"
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .s32 idx;\n\t.reg .b32 xb, col;\n\t.reg .s64 a;\n\t"
+      KNN_A1("%5", "0") KNN_A1("%6", "1") KNN_A1("%7", "2") KNN_A1("%8", "3") KNN_A1("%9", "4") KNN_A1("%10", "5") KNN_A1("%11", "6")
+      KNN_A1("%12", "7") "}"
+      : "+r"(cnt)
+      : "l"(list), "f"(thr), "r"(cbase), "n"(kCap / kAppendHalves - 1), "f"(x0), "f"(x1), "f"(x2), "f"(x3), "f"(x4), "f"(x5), "f"(x6), "f"(x7)
+      : "memory");
+#undef KNN_A1
+}
+
+// kModeLists   : sweep from thr_in[row] (may be NULL: -inf; strict >), write the candidate lists and bound_out[row] =
+//                max(thr_in[row], 48th entry) >= the approximate similarity of every column that is NOT in the list.
+//                gate != NULL: the whole launch is a no-op unless *gate > gate_limit.
+// kModeGroupMax: thr_out[row] = 48th largest of the 64 group maxima.
+// kModeAppend  : lists[row][0 .. min(cnt, kCap)) = the columns with similarity >= thr_in[row], acc_cnt[row] = cnt (may exceed kCap).
+template <int KC, int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? kThreadsAppend : kThreads, 1) candidates_kernel(const uint8_t* __restrict__ image, int64_t n, int n_blocks, int jstep,
                                                                  float* __restrict__ cand_sim, int32_t* __restrict__ cand_idx,
                                                                  const float* __restrict__ thr_in, float* __restrict__ thr_out,
-                                                                 float* __restrict__ bound_out) {
-  constexpr int kJStep = SAMPLE ? kSampleStride : 1;
-  constexpr int kList = SAMPLE ? kSampleKeep : kCand;
+                                                                 float* __restrict__ bound_out, uint2* __restrict__ lists,
+                                                                 int32_t* __restrict__ acc_cnt, float* __restrict__ dlt,
+                                                                 const int32_t* __restrict__ gate, int gate_limit) {
+  if (MODE == kModeLists && gate && *gate <= gate_limit) return;      // fallback launch that is not needed (uniform: before any barrier)
+  constexpr int kList = kCand;
   constexpr int NA = Cfg<KC>::kNA;
+  constexpr int kEpi = MODE == kModeAppend ? kEpiWarpsAppend : kEpiWarps;      // epilogue warps; then the MMA warp, then the producer warp
+  constexpr int kHalves = MODE == kModeAppend ? kAppendHalves : 1;
   constexpr int kBlkBytes = Cfg<KC>::kBlkBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -169,16 +238,16 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
     mbar_init(bar_afull, 1);
     mbar_init(bar_aempty, 1);
     for (int i = 0; i < kBStages; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, NA * 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, NA * 128 * kHalves); }
     fence_barrier_init();
   }
-  if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  if (warp == kEpi) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == kEpiWarps + 1) {
+  if (warp == kEpi + 1) {
     // =============================== producer: bulk copies through the TMA unit ===============================
     if (lane == 0) {
       uint32_t bs = 0, bph = 0, aph = 0;
@@ -192,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
           for (int kc = 0; kc < KC; ++kc)
             bulk_g2s(sA + a * kBlkBytes + kc * kChunkBytes, image + ((size_t)ab * KC + kc) * kChunkBytes, kChunkBytes, bar_afull);
         }
-        for (int j = 0; j < n_blocks; j += kJStep) {
+        for (int j = 0; j < n_blocks; j += jstep) {
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
@@ -204,14 +273,14 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
         aph ^= 1;
       }
     }
-  } else if (warp == kEpiWarps) {
+  } else if (warp == kEpi) {
     // =============================== MMA issuer ===============================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
       uint32_t bs = 0, bph = 0, ts = 0, tph = 0, aph = 0;
       for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
         mbar_wait(bar_afull, aph);
-        for (int j = 0; j < n_blocks; j += kJStep) {
+        for (int j = 0; j < n_blocks; j += jstep) {
           mbar_wait(bar_tempty + 8 * ts, tph ^ 1);
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) {
@@ -239,97 +308,197 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
       }
     }
     __syncwarp();
-  } else if ((warp >> 2) < NA) {
-    // =============================== epilogue: running top-48 per row ==========================================
-    const int a = warp >> 2, q = warp & 3;        // A block of the super block, TMEM lane quarter
-    TopList<kList> top;
-    const uint32_t stage0 = sStage + warp * kStageBytesPerWarp + lane * 8;     // entry k of this row: stage0 + k * 256
+  } else if ((warp >> 2) < NA * kHalves) {
+    // =============================== epilogue =====================================================================
+    const int half = warp / (4 * NA);             // append sweep: which two chunks of a tile (and which half of the list) this warp owns
+    const int a = (warp >> 2) % NA, q = warp & 3; // A block of the super block, TMEM lane quarter
+    const int ni = (int)n;                        // n < 2^31 (checked by the entry point)
     uint32_t ts = 0, tph = 0;
-    for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
-      const int row = (NA * sb + a) * kBlk + q * 32 + lane;          // n < 2^31 (checked by the entry point)
-      const int ni = (int)n;
-      const bool live = (NA * sb + a) < n_blocks && row < ni;
-      top.reset();
-      const float thr0 = live ? ((!SAMPLE && thr_in) ? thr_in[row] : -INFINITY) : INFINITY;      // padding rows never append
-      float thr = thr0;
-      int cnt = 0;                                  // staged entries of this row
-      // merge the staged entries of all 32 rows into their lists: pass k serves entry k of every row that has one
-      auto flush = [&]() {
-        const int most = __reduce_max_sync(kFull, cnt);
-        for (int k = 0; k < most; ++k) {
-          float sv = -INFINITY;
-          int sc = -1;
-          if (k < cnt) {
-            const uint2 e = ld_shared_u2(stage0 + k * 256);
-            sv = __uint_as_float(e.x);
-            sc = (int)e.y;
-          }
-          if (!__any_sync(kFull, sv > top.s[kList - 1])) continue;     // stale threshold: nothing of this pass still qualifies
-          top.insert(sv, sc);
-        }
-        cnt = 0;
-        if (live) thr = fmaxf(thr0, top.s[kList - 1]);
-      };
-      for (int j = 0; j < n_blocks; j += kJStep) {
-        mbar_wait(bar_tfull + 8 * ts, tph);
-        tc_fence_after();
-        // the diagonal and the columns past the last item must never be appended: only the row block's own column block and
-        // the last block can contain them (warp-uniform test)
-        const bool edge = j == NA * sb + a || (j + 1) * kBlk > ni;
+    // one 32-column chunk of this row's similarities; the diagonal and the columns past the last item become -inf (only the row
+    // block's own column block and the last block can contain them: warp-uniform test)
+    auto load_chunk = [&](float(&v)[32], int j, int c, int row, bool edge) {
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (ts * 2 + a) * 128 + c * 32, v);
+      if (edge) {
+        const int col0 = j * kBlk + c * 32;
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if (col0 + t == row || col0 + t >= ni) v[t] = -INFINITY;
+      }
+    };
+    // maxima of the four 8-column groups of a chunk
+    auto group_max = [](const float(&v)[32], float(&g)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        g[u] = fmaxf(fmaxf(fmaxf(v[8 * u], v[8 * u + 1]), fmaxf(v[8 * u + 2], v[8 * u + 3])),
+                     fmaxf(fmaxf(v[8 * u + 4], v[8 * u + 5]), fmaxf(v[8 * u + 6], v[8 * u + 7])));
+      }
+    };
+
+    if constexpr (MODE == kModeGroupMax) {
+      // ---------- maxima of 64 disjoint column groups per row; thr_out = the 48th largest of them
+      for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+        const int row = (NA * sb + a) * kBlk + q * 32 + lane;
+        const bool live = (NA * sb + a) < n_blocks && row < ni;
+        float gA[32], gB[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) { gA[t] = -INFINITY; gB[t] = -INFINITY; }
+        for (int j = 0; j < n_blocks; j += jstep) {
+          mbar_wait(bar_tfull + 8 * ts, tph);
+          tc_fence_after();
+          const bool edge = j == NA * sb + a || (j + 1) * kBlk > ni;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (KNN_DIAG & 2) continue;
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (ts * 2 + a) * 128 + c * 32, v);
-          const int col0 = j * kBlk + c * 32;
-          if (edge) {
+          for (int c2 = 0; c2 < 2; ++c2) {
+            float v[32];
+            load_chunk(v, j, 2 * c2, row, edge);
 #pragma unroll
-            for (int t = 0; t < 32; ++t)
-              if (col0 + t == row || col0 + t >= ni) v[t] = -INFINITY;
-          }
-          // maxima of the four 8-column groups, then of the chunk
-          float g[4];
+            for (int t = 0; t < 32; ++t) gA[t] = fmaxf(gA[t], v[t]);
+            load_chunk(v, j, 2 * c2 + 1, row, edge);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            g[u] = fmaxf(fmaxf(fmaxf(v[8 * u], v[8 * u + 1]), fmaxf(v[8 * u + 2], v[8 * u + 3])),
-                         fmaxf(fmaxf(v[8 * u + 4], v[8 * u + 5]), fmaxf(v[8 * u + 6], v[8 * u + 7])));
+            for (int t = 0; t < 32; ++t) gB[t] = fmaxf(gB[t], v[t]);
           }
-          const float vmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-          if (!__any_sync(kFull, vmax > thr)) continue;          // nothing in this chunk beats any row's threshold
-          if (KNN_DIAG & 1) { if (vmax == 12345.f) thr = 0.f; continue; }
-          // groups in which some row has a hit (warp-uniform mask); a group appends at most 8 entries per row
-          unsigned gmask = __reduce_or_sync(kFull, (g[0] > thr ? 1u : 0u) | (g[1] > thr ? 2u : 0u) | (g[2] > thr ? 4u : 0u) | (g[3] > thr ? 8u : 0u));
-          while (gmask) {
-            const int u = __ffs(gmask) - 1;
-            gmask &= gmask - 1;
-            if (__any_sync(kFull, cnt > kStage - 8)) flush();     // single call site: the merge is ~1.5 KB of code
-            const int cbase = col0 + 8 * u;
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * ts);
+          if (++ts == 2) { ts = 0; tph ^= 1; }
+        }
+        TopList<kCand> top;
+        top.reset();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) top.insert(half ? gB[t] : gA[t], t);
+        }
+        if (live) {
+          thr_out[row] = top.s[kCand - 1];
+          dlt[row] = fmaxf(top.s[kCand / 2 - 1] - top.s[kCand - 1], 1e-6f);   // ladder step of the next sweep: ~ a factor 2 in rank
+        }
+      }
+    } else if constexpr (MODE == kModeAppend) {
+      // ---------- no list: every column with similarity >= thr is appended to the row's list in global memory
+      for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+        const int row = (NA * sb + a) * kBlk + q * 32 + lane;
+        const bool live = (NA * sb + a) < n_blocks && row < ni;
+        float thr = live ? thr_in[row] : INFINITY;                     // padding rows never append
+        // Ladder: thr2 < thr3 are the next two rungs; cnt2 / cnt3 count the (chunk, 8-column group) cells of this row seen so far
+        // whose maximum reached them -- that many DIFFERENT columns, all of them appended.  48 of them make the rung a valid
+        // threshold for the rest of the sweep (~48 (1 + ln 8) appends per row instead of 384).
+        const float dl = live ? dlt[row] : 0.f;
+        float thr2 = thr + dl, thr3 = thr2 + dl;
+        int cnt2 = 0, cnt3 = 0;
+        uint2* lp = lists + (size_t)(live ? row : 0) * kCap + half * (kCap / kAppendHalves);
+        int cnt = 0;
+        for (int j = 0; j < n_blocks; j += jstep) {
+          mbar_wait(bar_tfull + 8 * ts, tph);
+          tc_fence_after();
+          const bool edge = j == NA * sb + a || (j + 1) * kBlk > ni;
+#pragma unroll 1
+          for (int c = (4 / kHalves) * half; c < (4 / kHalves) * (half + 1); ++c) {
+            float v[32];
+            load_chunk(v, j, c, row, edge);
+            float g[4];
+            group_max(v, g);
+            const float vmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+            if (!__any_sync(kFull, vmax >= thr)) continue;          // nothing in this chunk reaches any row's threshold
+            unsigned gmask = __reduce_or_sync(kFull, (g[0] >= thr ? 1u : 0u) | (g[1] >= thr ? 2u : 0u) | (g[2] >= thr ? 4u : 0u) | (g[3] >= thr ? 8u : 0u));
+            const int col0 = j * kBlk + c * 32;
+            while (gmask) {
+              const int u = __ffs(gmask) - 1;
+              gmask &= gmask - 1;
+              const int cbase = col0 + 8 * u;
+#define KNN_APPEND8(U) append8(lp, cnt, thr, cbase, v[8 * (U)], v[8 * (U) + 1], v[8 * (U) + 2], v[8 * (U) + 3], v[8 * (U) + 4], \
+                               v[8 * (U) + 5], v[8 * (U) + 6], v[8 * (U) + 7]);
+              switch (u) {
+                case 0: KNN_APPEND8(0) break;
+                case 1: KNN_APPEND8(1) break;
+                case 2: KNN_APPEND8(2) break;
+                default: KNN_APPEND8(3) break;
+              }
+#undef KNN_APPEND8
+            }
+            cnt2 += (g[0] >= thr2 ? 1 : 0) + (g[1] >= thr2 ? 1 : 0) + (g[2] >= thr2 ? 1 : 0) + (g[3] >= thr2 ? 1 : 0);
+            cnt3 += (g[0] >= thr3 ? 1 : 0) + (g[1] >= thr3 ? 1 : 0) + (g[2] >= thr3 ? 1 : 0) + (g[3] >= thr3 ? 1 : 0);
+            if (cnt2 >= kCand) { thr = thr2; thr2 = thr3; cnt2 = cnt3; thr3 += dl; cnt3 = 0; }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * ts);
+          if (++ts == 2) { ts = 0; tph ^= 1; }
+        }
+        if (live) {
+          acc_cnt[2 * row + half] = cnt;
+          if (kHalves == 1) acc_cnt[2 * row + 1] = 0;
+        }
+      }
+    } else {
+      // ---------- running top-48 per row in registers
+      TopList<kList> top;
+      const uint32_t stage0 = sStage + warp * kStageBytesPerWarp + lane * 8;     // entry k of this row: stage0 + k * 256
+      for (int sb = blockIdx.x; sb < n_super; sb += gridDim.x) {
+        const int row = (NA * sb + a) * kBlk + q * 32 + lane;
+        const bool live = (NA * sb + a) < n_blocks && row < ni;
+        top.reset();
+        const float thr0 = live ? (thr_in ? thr_in[row] : -INFINITY) : INFINITY;      // padding rows never append
+        float thr = thr0;
+        int cnt = 0;                                  // staged entries of this row
+        // merge the staged entries of all 32 rows into their lists: pass k serves entry k of every row that has one
+        auto flush = [&]() {
+          const int most = __reduce_max_sync(kFull, cnt);
+          for (int k = 0; k < most; ++k) {
+            float sv = -INFINITY;
+            int sc = -1;
+            if (k < cnt) {
+              const uint2 e = ld_shared_u2(stage0 + k * 256);
+              sv = __uint_as_float(e.x);
+              sc = (int)e.y;
+            }
+            if (!__any_sync(kFull, sv > top.s[kList - 1])) continue;     // stale threshold: nothing of this pass still qualifies
+            top.insert(sv, sc);
+          }
+          cnt = 0;
+          if (live) thr = fmaxf(thr0, top.s[kList - 1]);
+        };
+        for (int j = 0; j < n_blocks; j += jstep) {
+          mbar_wait(bar_tfull + 8 * ts, tph);
+          tc_fence_after();
+          const bool edge = j == NA * sb + a || (j + 1) * kBlk > ni;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            if (KNN_DIAG & 2) continue;
+            float v[32];
+            load_chunk(v, j, c, row, edge);
+            const int col0 = j * kBlk + c * 32;
+            float g[4];
+            group_max(v, g);
+            const float vmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+            if (!__any_sync(kFull, vmax > thr)) continue;          // nothing in this chunk beats any row's threshold
+            if (KNN_DIAG & 1) { if (vmax == 12345.f) thr = 0.f; continue; }
+            // groups in which some row has a hit (warp-uniform mask); a group appends at most 8 entries per row
+            unsigned gmask = __reduce_or_sync(kFull, (g[0] > thr ? 1u : 0u) | (g[1] > thr ? 2u : 0u) | (g[2] > thr ? 4u : 0u) | (g[3] > thr ? 8u : 0u));
+            while (gmask) {
+              const int u = __ffs(gmask) - 1;
+              gmask &= gmask - 1;
+              if (__any_sync(kFull, cnt > kStage - 8)) flush();     // single call site: the merge is ~1.5 KB of code
+              const int cbase = col0 + 8 * u;
 #define KNN_APPEND8(U)                                                                                     \
   _Pragma("unroll") for (int t = 0; t < 8; ++t) {                                                          \
     const float x = v[8 * (U) + t];                                                                        \
-    if (x > thr) {                                                                                         \
-      st_shared_u2(stage0 + cnt * 256, __float_as_uint(x), (uint32_t)(cbase + t));                        \
-      ++cnt;                                                                                               \
-    }                                                                                                      \
+    const int hit = x > thr ? 1 : 0;                                                                       \
+    st_shared_u2_if(hit, stage0 + cnt * 256, __float_as_uint(x), (uint32_t)(cbase + t));                  \
+    cnt += hit;                                                                                            \
   }
-            switch (u) {
-              case 0: KNN_APPEND8(0) break;
-              case 1: KNN_APPEND8(1) break;
-              case 2: KNN_APPEND8(2) break;
-              default: KNN_APPEND8(3) break;
-            }
+              switch (u) {
+                case 0: KNN_APPEND8(0) break;
+                case 1: KNN_APPEND8(1) break;
+                case 2: KNN_APPEND8(2) break;
+                default: KNN_APPEND8(3) break;
+              }
 #undef KNN_APPEND8
+            }
           }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * ts);
+          if (++ts == 2) { ts = 0; tph ^= 1; }
         }
-        tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * ts);
-        if (++ts == 2) { ts = 0; tph ^= 1; }
-      }
-      flush();
-      if (live) {
-        if (SAMPLE) {
-          thr_out[row] = top.s[kList - 1];
-        } else {
+        flush();
+        if (live) {
 #pragma unroll
           for (int k = 0; k < kList; ++k) {
             cand_sim[(int64_t)row * kCand + k] = top.s[k];
@@ -343,7 +512,98 @@ __global__ void __launch_bounds__(kThreads, 1) candidates_kernel(const uint8_t* 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == kEpiWarps) tmem_dealloc(tmem_base, 512);
+  if (warp == kEpi) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- 2b. selection over the appended lists ----------------------------------------------------------------------------
+// Warp per row.  The (at most kCap) appended entries sit in registers, 32 per lane, as order-preserving integer keys; the
+// 48th largest key is found bit by bit (the largest T with |{key >= T}| >= 48: 32 counting rounds).
+//   FINAL = false: thr[row] = that value (the admission threshold of the next sweep).  Fewer than 48 entries: thr stays.
+//   FINAL = true : the 48 best entries become the row's candidate list (unordered: the re-rank does not care), bound[row] =
+//                  the 48th best (no column outside the list has a larger approximate similarity), or thr[row] if the row
+//                  appended fewer than 48, or +inf if it appended more than kCap (entries were dropped: the guard then
+//                  sends the row to the exact path); n_over counts those rows.
+template <bool FINAL>
+__global__ void __launch_bounds__(128) select_kernel(const uint2* __restrict__ lists, const int32_t* __restrict__ acc_cnt, int64_t n,
+                                                     float* __restrict__ thr, float* __restrict__ dlt, float* __restrict__ cand_sim,
+                                                     int32_t* __restrict__ cand_idx, float* __restrict__ bound,
+                                                     int32_t* __restrict__ n_over) {
+  constexpr int kSlots = kCap / 32;
+  static_assert(kCap % 32 == 0 && kCand > 32 && kCand <= 64, "select_kernel lane mapping");
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  // the two halves of the list (one per epilogue warp of the pair) sit in slots [0, kSlots/2) and [kSlots/2, kSlots)
+  constexpr int kHalfCap = kCap / kAppendHalves, kHalfSlots = kSlots / kAppendHalves;
+  const int c_raw0 = acc_cnt[2 * r], c_raw1 = acc_cnt[2 * r + 1];
+  const bool over = c_raw0 > kHalfCap || c_raw1 > kHalfCap;
+  const int c0 = min(c_raw0, kHalfCap), c1 = min(c_raw1, kHalfCap);
+  uint32_t key[kSlots];
+  int col[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    key[s] = 0u;
+    col[s] = -1;
+    const int e = (s % kHalfSlots) * 32 + lane;
+    if (e < (s < kHalfSlots ? c0 : c1)) {
+      const uint2 x = lists[r * kCap + (s < kHalfSlots ? 0 : kHalfCap) + e];
+      key[s] = fkey(__uint_as_float(x.x));
+      col[s] = (int)x.y;
+    }
+  }
+  const int c = c0 + c1;
+  // warp-uniform: does slot s hold any entry
+  auto slot_live = [&](int s) { return (s % kHalfSlots) * 32 < (s < kHalfSlots ? c0 : c1); };
+  uint32_t T = 0u;         // fewer than 48 entries (cannot happen after a sweep that re-admits the 48 columns behind its threshold): keep all
+  if (c >= kCand) {
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t tr = T | (1u << bit);
+      int local = 0;
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s)
+        if (slot_live(s)) local += key[s] >= tr ? 1 : 0;
+      if (__reduce_add_sync(kFull, local) >= kCand) T = tr;
+    }
+  }
+  if (!FINAL) {
+    if (lane == 0 && c >= kCand) {
+      const float t_new = fkey_inv(T), t_old = thr[r];
+      thr[r] = t_new;
+      dlt[r] = fmaxf(0.5f * (t_new - t_old), 1e-6f);      // the two thresholds are a factor ~3.6 apart in rank: ~1.9 per rung
+    }
+    return;
+  }
+  // keys above T (fewer than 48 of them), then keys equal to T until the list is full, then padding
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    if (slot_live(s)) {
+      const bool p = key[s] > T;
+      const unsigned m = __ballot_sync(kFull, p);
+      const int pos = base + __popc(m & lt);
+      if (p) { cand_sim[r * kCand + pos] = fkey_inv(key[s]); cand_idx[r * kCand + pos] = col[s]; }
+      base += __popc(m);
+    }
+  }
+  if (T != 0u) {
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      if (slot_live(s) && base < kCand) {
+        const bool p = key[s] == T;
+        const unsigned m = __ballot_sync(kFull, p);
+        const int pos = base + __popc(m & lt);
+        if (p && pos < kCand) { cand_sim[r * kCand + pos] = fkey_inv(key[s]); cand_idx[r * kCand + pos] = col[s]; }
+        base += __popc(m);
+      }
+    }
+  }
+  for (int pos = min(base, kCand) + lane; pos < kCand; pos += 32) { cand_sim[r * kCand + pos] = -INFINITY; cand_idx[r * kCand + pos] = -1; }
+  if (lane == 0) {
+    bound[r] = over ? INFINITY : (c >= kCand ? fkey_inv(T) : thr[r]);
+    if (over) atomicAdd(n_over, 1);
+  }
 }
 
 // ---- 3. exact re-rank ------------------------------------------------------------------------------------------------
@@ -533,8 +793,9 @@ static int knn_run(const float* emb, int64_t n_items, int k, float min_similarit
   using C = knn::Cfg<KC>;
   static DeviceOnce once;        // one per KC instantiation
   if (once.pending()) {
-    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, knn::kModeLists>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, knn::kModeGroupMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    B200GAT_CUDA(cudaFuncSetAttribute(knn::candidates_kernel<KC, knn::kModeAppend>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     once.done();
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
@@ -546,20 +807,41 @@ static int knn_run(const float* emb, int64_t n_items, int k, float min_similarit
   int32_t* cand_idx = (int32_t*)p;                      p += (size_t)n_pad * knn::kCand * 4;
   int32_t* unsafe_rows = (int32_t*)p;                   p += (size_t)n_pad * 4;
   float* thr = (float*)p;                               p += (size_t)n_pad * 4;
-  float* bound = (float*)p;
-  // Opt-in (B200GAT_KNN_SAMPLE=1, read per call).  Measured at 498,196 x 128-d items: 113.7 ms without, 100.6 ms with.  Off by
-  // default because a catalogue stored cluster by cluster defeats the estimate: rows whose own cluster falls into a sampled
-  // block get a threshold above their k-th neighbour and are redone by the exact path (255 MB of reads per row at that size).
-  const char* env = getenv("B200GAT_KNN_SAMPLE");
-  const bool sample = n_blocks >= knn::kSampleMinBlocks && env && atoi(env) != 0;
+  float* bound = (float*)p;                             p += (size_t)n_pad * 4;
+  int32_t* acc_cnt = (int32_t*)p;                       p += (size_t)n_pad * 8;      // one counter per half list
+  int32_t* n_over = (int32_t*)p;                        p += 256;
+  float* dlt = (float*)p;                               p += (size_t)n_pad * 4;
+  uint2* lists = (uint2*)p;                             // [n_pad][kCap], only laid out for >= kAppendMinBlocks column blocks
+  // B200GAT_KNN_MODE=lists (read per call) forces the register-list kernel at every size (A/B measurements, tests)
+  const char* env = getenv("B200GAT_KNN_MODE");
+  const bool append = n_blocks >= knn::kAppendMinBlocks && !(env && env[0] == 'l');
+  // B200GAT_KNN_MAX_OVERFLOW (tests): how many overflowed rows the exact path may take before the register-list kernel redoes the sweep
+  const char* env_o = getenv("B200GAT_KNN_MAX_OVERFLOW");
+  const int max_over = env_o ? atoi(env_o) : knn::kMaxOverflowRows;
   count_launch(), knn::prepare_kernel<KC><<<ceil_div(n_pad * 32, 128), 128, 0, st>>>(emb, n_items, n_pad, en, image);
   const int n_super = (n_blocks + C::kNA - 1) / C::kNA;
   const int grid = n_super < kNumSMs ? n_super : kNumSMs;
-  if (sample)
-    count_launch(), knn::candidates_kernel<KC, true><<<grid, knn::kThreads, C::kSmem, st>>>(image, n_items, n_blocks, nullptr, nullptr,
-                                                                                           nullptr, thr, nullptr);
-  count_launch(), knn::candidates_kernel<KC, false><<<grid, knn::kThreads, C::kSmem, st>>>(image, n_items, n_blocks, cand_sim, cand_idx,
-                                                                                          sample ? thr : nullptr, nullptr, bound);
+  const int sel_grid = ceil_div(n_items * 32, 128);
+  if (append) {
+    B200GAT_CUDA(cudaMemsetAsync(n_over, 0, sizeof(int32_t), st));
+    // thr_A: 48th largest of 64 group maxima over every 16th column block
+    count_launch(), knn::candidates_kernel<KC, knn::kModeGroupMax><<<grid, knn::kThreads, C::kSmem, st>>>(
+        image, n_items, n_blocks, knn::kStrideA, nullptr, nullptr, nullptr, thr, nullptr, nullptr, nullptr, dlt, nullptr, 0);
+    // thr_B: 48th largest of the columns >= thr_A among every 8th block
+    count_launch(), knn::candidates_kernel<KC, knn::kModeAppend><<<grid, knn::kThreadsAppend, C::kSmem, st>>>(
+        image, n_items, n_blocks, knn::kStrideB, nullptr, nullptr, thr, nullptr, nullptr, lists, acc_cnt, dlt, nullptr, 0);
+    count_launch(), knn::select_kernel<false><<<sel_grid, 128, 0, st>>>(lists, acc_cnt, n_items, thr, dlt, nullptr, nullptr, nullptr, nullptr);
+    // the full sweep: every column >= thr_B, then the 48 best of them
+    count_launch(), knn::candidates_kernel<KC, knn::kModeAppend><<<grid, knn::kThreadsAppend, C::kSmem, st>>>(
+        image, n_items, n_blocks, 1, nullptr, nullptr, thr, nullptr, nullptr, lists, acc_cnt, dlt, nullptr, 0);
+    count_launch(), knn::select_kernel<true><<<sel_grid, 128, 0, st>>>(lists, acc_cnt, n_items, thr, dlt, cand_sim, cand_idx, bound, n_over);
+    // fallback behind a device-side gate: too many rows overflowed their lists -> register lists for all rows, from thr_B
+    count_launch(), knn::candidates_kernel<KC, knn::kModeLists><<<grid, knn::kThreads, C::kSmem, st>>>(
+        image, n_items, n_blocks, 1, cand_sim, cand_idx, thr, nullptr, bound, nullptr, nullptr, nullptr, n_over, max_over);
+  } else {
+    count_launch(), knn::candidates_kernel<KC, knn::kModeLists><<<grid, knn::kThreads, C::kSmem, st>>>(
+        image, n_items, n_blocks, 1, cand_sim, cand_idx, nullptr, nullptr, bound, nullptr, nullptr, nullptr, nullptr, 0);
+  }
 #if KNN_DIAG == 0
   count_launch(), knn::rerank_kernel<KC><<<ceil_div(n_items * 32, 128), 128, 0, st>>>(en, n_items, cand_sim, cand_idx, k, min_similarity,
                                                                                       nbr_idx, nbr_sim, counts, n_unsafe, unsafe_rows,
@@ -580,7 +862,8 @@ extern "C" int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* byt
   }
   const int64_t n_pad = (n_items + knn::kBlk - 1) / knn::kBlk * knn::kBlk;
   *bytes = (size_t)n_pad * dim * 4 /*en*/ + (size_t)n_pad * dim * 2 /*image*/ + (size_t)n_pad * knn::kCand * 8 /*cands*/ +
-           (size_t)n_pad * 12 /*unsafe row list, sampled thresholds, bounds*/ + 1024;
+           (size_t)n_pad * 24 /*unsafe row list, thresholds, ladder steps, bounds, append counters (2)*/ + 256 /*overflow counter*/ + 1024;
+  if (n_pad / knn::kBlk >= knn::kAppendMinBlocks) *bytes += (size_t)n_pad * knn::kCap * 8;   // appended (similarity, column) lists
   return kOk;
 }
 

@@ -109,6 +109,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void st_shared_u2(uint32_t addr, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
+// predicated forms (no branch: a divergent region per appended element is what the epilogues cannot afford)
+__device__ __forceinline__ void st_shared_u2_if(int pred, uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p st.shared.v2.u32 [%1], {%2, %3};\n\t}" ::"r"(pred), "r"(addr), "r"(x), "r"(y)
+               : "memory");
+}
 __device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
   uint2 r;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");

@@ -21,15 +21,14 @@ def _data(n, seed, clustered, d=128):
 @pytest.mark.parametrize("n,clustered,k,min_sim,d", [(50, False, 20, -1.0, 128), (129, True, 20, 0.3, 128),
                                                      (3000, True, 20, 0.3, 128), (2049, False, 5, -1.0, 128),
                                                      (5000, True, 20, 0.5, 128),
-                                                     # >= 64 column blocks, run with the sampled admission threshold switched on
+                                                     # >= 64 column blocks: the append pipeline (group maxima -> sampled appends -> full sweep)
                                                      (9000, True, 20, 0.3, 128), (12345, False, 20, -1.0, 128),
+                                                     (20000, True, 32, 0.3, 128),
                                                      # the 384-d text embeddings (embeddings/embed_text.py -> build_ii_knn.py)
                                                      (130, False, 20, -1.0, 384), (3000, True, 20, 0.3, 384),
                                                      (4100, True, 10, 0.5, 384), (8300, True, 20, 0.3, 384)])
 def test_knn_matches_oracle(n, clustered, k, min_sim, d, monkeypatch):
     import b200gat
-    if n >= 8192:
-        monkeypatch.setenv("B200GAT_KNN_SAMPLE", "1")        # the opt-in sampled admission threshold (>= 64 column blocks)
     emb = _data(n, n, clustered, d)
     rows, cols, sims = O.build_ii_knn(emb, k=min(k, n - 1), min_similarity=min_sim, batch_size=1000)
     r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=min(k, n - 1), min_similarity=min_sim)
@@ -124,20 +123,8 @@ def test_knn_matches_reference_script_output(golden_dir, name):
     np.testing.assert_array_equal(key(r, c), key(g["rows"], g["cols"]))
 
 
-def test_knn_sampled_threshold_survives_index_sorted_clusters(monkeypatch):
-    """Adversarial layout for the sampled admission threshold: items are stored cluster by cluster, one cluster per 128-row
-    column block, so the sampled blocks (every 16th) show each row a threshold taken from OTHER clusters only or -- for rows of a
-    sampled block -- from its own cluster only.  The result must still be the exact top-k (rows the guard cannot prove go
-    through the exact path)."""
-    import b200gat
-    monkeypatch.setenv("B200GAT_KNN_SAMPLE", "1")
-    rng = np.random.default_rng(5)
-    n_clusters, per = 72, 128
-    centers = rng.standard_normal((n_clusters, 128))
-    emb = (np.repeat(centers, per, axis=0) + 0.25 * rng.standard_normal((n_clusters * per, 128))).astype(np.float32)
-    n, k = emb.shape[0], 20
-    r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=k, min_similarity=-1.0)
-    r, c, s = r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
+def _assert_exact_topk(emb, r, c, s, k):
+    n = emb.shape[0]
     en = emb.astype(np.float64)
     en /= np.linalg.norm(en, axis=1, keepdims=True)
     full = en @ en.T
@@ -146,3 +133,43 @@ def test_knn_sampled_threshold_survives_index_sorted_clusters(monkeypatch):
     np.testing.assert_allclose(s, full[r, c], rtol=0, atol=3e-6)
     kth = -np.sort(-full, axis=1)[:, k - 1]
     assert np.all(full[r, c] >= kth[r] - 5e-6)            # every emitted neighbour is among the row's k best (up to rounding ties)
+
+
+@pytest.mark.parametrize("mode", ["append", "lists"])
+def test_knn_survives_index_sorted_clusters(mode, monkeypatch):
+    """Adversarial layout for sampled admission thresholds: items are stored cluster by cluster, one cluster per 128-row
+    column block, so the sampled blocks (every 16th / every 8th) show each row a threshold taken from OTHER clusters only or --
+    for rows of a sampled block -- from its own cluster only.  The result must still be the exact top-k, in the append
+    pipeline (default at this size) and with the register-list kernel forced."""
+    import b200gat
+    if mode == "lists":
+        monkeypatch.setenv("B200GAT_KNN_MODE", "lists")
+    rng = np.random.default_rng(5)
+    n_clusters, per = 72, 128
+    centers = rng.standard_normal((n_clusters, 128))
+    emb = (np.repeat(centers, per, axis=0) + 0.25 * rng.standard_normal((n_clusters * per, 128))).astype(np.float32)
+    k = 20
+    r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=k, min_similarity=-1.0)
+    _assert_exact_topk(emb, r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy(), k)
+
+
+@pytest.mark.parametrize("max_overflow", [None, 100000])
+def test_knn_append_lists_overflow(max_overflow, monkeypatch):
+    """A clump of 1,000 near-duplicates that no sampled column block shows (it sits in blocks 1..7 and 9): each of its rows
+    appends more entries than its list holds in the full sweep.  Default: more than 64 such rows -> the register-list kernel behind the
+    device-side gate redoes the sweep; with the limit raised the overflowed rows are handed to the exact path instead.  Either way
+    the result is the exact top-k."""
+    import b200gat
+    if max_overflow is not None:
+        monkeypatch.setenv("B200GAT_KNN_MAX_OVERFLOW", str(max_overflow))
+    rng = np.random.default_rng(11)
+    n, d, k = 9000, 128, 20
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    clump = np.r_[128:1024, 1152:1256]                    # 896 + 104 rows, none of them in a block with index % 8 == 0
+    emb[clump] = (rng.standard_normal(d) + 0.3 * rng.standard_normal((len(clump), d))).astype(np.float32)
+    stats = {}
+    idx, sim, counts = b200gat.knn_neighbors(torch.from_numpy(emb).cuda(), k, -1.0, stats=stats)
+    r, c, s = b200gat.build_ii_knn(torch.from_numpy(emb).cuda(), k=k, min_similarity=-1.0)
+    _assert_exact_topk(emb, r.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy(), k)
+    if max_overflow is not None:
+        assert int(stats["exact_rows"].item()) >= len(clump)      # the overflowed rows went through the exact path

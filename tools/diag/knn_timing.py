@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import b200gat
 from b200gat import _lib
 dev = torch.device("cuda:0")
-SIZES = ((63001, 128),) if os.environ.get("KNN_SIZES") == "one" else ((63001, 128), (498196, 128)) if os.environ.get("KNN_SIZES") == "small" else ((63001, 128), (498196, 128), (63001, 384), (498196, 384))
+SIZES = ((63001, 128),) if os.environ.get("KNN_SIZES") == "one" else ((498196, 128),) if os.environ.get("KNN_SIZES") == "big" else ((63001, 128), (498196, 128)) if os.environ.get("KNN_SIZES") == "small" else ((63001, 128), (498196, 128), (63001, 384), (498196, 384))
 for n, d in SIZES:
     g = torch.Generator(device="cpu").manual_seed(n)
     centers = torch.randn(n // 50, d, generator=g)

@@ -791,14 +791,43 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 #define EDGE_NB16_BWD 1
 #endif
 #ifndef EDGE_MINB16_FWD
-#define EDGE_MINB16_FWD 8
+#define EDGE_MINB16_FWD 12     // 8 with register buffers (EDGE_FWD_RING 0)
 #endif
 #ifndef EDGE_MINB16_FWD_BF16
-#define EDGE_MINB16_FWD_BF16 9
+#define EDGE_MINB16_FWD_BF16 12   // 9 with register buffers
 #endif
 #ifndef EDGE_MINB16_BWD
 #define EDGE_MINB16_BWD 10
 #endif
+// > 0 = the gathered rows (h in the forward, dout in the backward) go through a per-thread ring of that many load groups in
+// shared memory, filled by cp.async (LDGSTS): every lane reads back exactly the bytes it copied, so no barrier is involved,
+// and the gathers in flight no longer cost registers -- which is what capped the register-buffered versions (backward: one
+// group, NB 1 beat NB 2 only through occupancy; forward: 64 registers, 8 blocks per SM).  0 = the register buffers above.
+// Measured on config 2, ms for both layers (profiles/r2ak_edge_ring_ab.md):
+//   fp32 backward  ring 0: 2.61 | 2: 2.05 | 4: 1.94 | 6: 2.12       bf16 backward  0: 1.90 | 2 (x2 rows): 1.56 | 4: 1.62 | 6: 2.29
+//   fp32 forward   ring 0 / 8 blocks: 1.80 | 4 / 8: 1.73 | 4 / 10: 1.71 | 6 / 9: 1.74 | 3 / 12: 1.70
+//   bf16 forward   ring 0 / 9 blocks: 1.68 | 2 / 9: 1.15 | 2 / 10: 1.16 | 3 / 9: 1.16 | 2 / 12: 1.10
+#ifndef EDGE_BWD_RING
+#define EDGE_BWD_RING 4
+#endif
+#ifndef EDGE_BWD_RING_BF16
+#define EDGE_BWD_RING_BF16 2
+#endif
+#ifndef EDGE_FWD_RING
+#define EDGE_FWD_RING 3
+#endif
+#ifndef EDGE_FWD_RING_BF16
+#define EDGE_FWD_RING_BF16 2
+#endif
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_row(uint32_t dst_smem, const void* src) {
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float half_sum(float v) {
 #pragma unroll
@@ -864,6 +893,25 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
     const float sv = valid ? __ldg(s + (size_t)c * 2) : 0.f;
     const int cnt = min(16, end - base);                                  // <= 0 once this half is done
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));           // warp-uniform trip count
+#if EDGE_FWD_RING > 0
+    constexpr int NB = sizeof(T) == 2 ? EDGE_FWD_RING_BF16 : EDGE_FWD_RING;
+    using Raw = typename Raw4<T>::type;
+    __shared__ Raw ring[NB][U][2][kEdgeThreads];          // see edge_bwd16_kernel
+    auto ring_load = [&](int b, int k, bool on) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ck = __shfl_sync(kFull, c, (k + u) & 15, 16);
+        if (on && k + u < cnt) {
+          const T* hp = h + (size_t)ck * C;
+          cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][0][threadIdx.x]), hp + ch0);
+          cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][1][threadIdx.x]), hp + ch1);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ring_load(b, b * U, b * U < cmax);
+#else
     constexpr int NB = sizeof(T) == 2 ? EDGE_NB16_FWD_BF16 : EDGE_NB16_FWD;
     HalfRow<T> buf[NB][U];
     load_group(buf[0], c, 0, cnt);                                        // gathers start before the softmax math
@@ -871,6 +919,7 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
     for (int b = 1; b < NB; ++b)
       if (b * U < cmax) load_group(buf[b], c, b * U, cnt);
 
+#endif
     float z = -INFINITY, p;
     if (valid) z = activate<POLICY>(sv + sd, neg_slope);
     if (POLICY == kPyG) {
@@ -889,6 +938,26 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
     l += p;   // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
     if (DROPOUT && valid) p *= dropout_scale(seed, (uint32_t)__ldg(perm + e), 0, p_drop, inv_keep);
 
+#if EDGE_FWD_RING > 0
+    for (int k = 0; k < cmax; k += NB * U) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (k + b * U < cmax) {                                           // warp-uniform
+          cp_async_wait<NB - 1>();
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float pk = __shfl_sync(kFull, p, (k + b * U + u) & 15, 16);
+            if (k + b * U + u < cnt) {
+              acc0 = fma4(pk, to_f4(ring[b][u][0][threadIdx.x]), acc0);
+              acc1 = fma4(pk, to_f4(ring[b][u][1][threadIdx.x]), acc1);
+            }
+          }
+          ring_load(b, k + (b + NB) * U, k + (b + NB) * U < cmax);
+        }
+      }
+    }
+    cp_async_wait<0>();
+#else
     auto consume = [&](HalfRow<T>(&buf)[U], int k) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -910,6 +979,7 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
         }
       }
     }
+#endif
   }
   const float lt = half_sum(l);
   if (!live) return;
@@ -1001,6 +1071,27 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
     if (ch + 1 < nch) i_next = (q + 16 < end) ? ld_once(row + q + 16) : 0;   // next chunk's ids: one load latency off the chain
     const int cnt = min(16, end - base);
     const int cmax = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
+#if EDGE_BWD_RING > 0
+    constexpr int NB = sizeof(T) == 2 ? EDGE_BWD_RING_BF16 : EDGE_BWD_RING;
+    using Raw = typename Raw4<T>::type;
+    __shared__ Raw ring[NB][U][2][kEdgeThreads];          // [group slot][row of the group][piece][thread]: conflict-free, private per thread
+    // group b <- rows k .. k + U - 1 of this chunk (or nothing); ALWAYS one commit, so that "all but the newest NB - 1 groups have
+    // landed" means the same thing at every point of the chunk
+    auto ring_load = [&](int b, int k, bool on) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ik = __shfl_sync(kFull, i, (k + u) & 15, 16);
+        if (on && k + u < cnt) {
+          const T* gp = dout + (size_t)ik * C;
+          cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][0][threadIdx.x]), gp + ch0);
+          cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][1][threadIdx.x]), gp + ch1);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ring_load(b, b * U, b * U < cmax);
+#else
     constexpr int NB = EDGE_NB16_BWD;
     HalfRow<T> buf[NB][U];
     load_group(buf[0], i, 0, cnt);                    // dout gathers start before the per-edge scalar math
@@ -1008,6 +1099,7 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
     for (int b = 1; b < NB; ++b)
       if (b * U < cmax) load_group(buf[b], i, b * U, cnt);
 
+#endif
     // per lane (= per edge of this chunk): agg = alpha' (weight of dout_i in dh_j), and the two coefficients of
     // de = alpha * (dalpha * keep - t) * slope  written as  de = gA * <dout_i, h_j> - cB
     float agg = 0.f, gA = 0.f, cB = 0.f, my_de = 0.f;
@@ -1028,6 +1120,38 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
       gA = agg * gsc;
       cB = alpha * st.w * gsc;
     }
+#if EDGE_BWD_RING > 0
+    auto consume_ring = [&](int b, int k) {
+      float dsum[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float a = __shfl_sync(kFull, agg, (k + u) & 15, 16);
+        dsum[u] = 0.f;
+        if (k + u < cnt) {
+          const float4 g0 = to_f4(ring[b][u][0][threadIdx.x]), g1 = to_f4(ring[b][u][1][threadIdx.x]);
+          acc0 = fma4(a, g0, acc0);
+          acc1 = fma4(a, g1, acc1);
+          dsum[u] = dot4(hj0, g0) + dot4(hj1, g1);
+        }
+      }
+      const int mine = (sl - k) & 15;                    // which edge of the group this lane owns (if < U)
+      const bool owner = mine < U && k + mine < cnt;
+      const float tot = MultiReduce<U, 8>::run(dsum, lane);
+      const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (4 - Log2<U>::value), 16);
+      if (owner) my_de = gA * dot - cB;
+    };
+    for (int k = 0; k < cmax; k += NB * U) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (k + b * U < cmax) {                         // warp-uniform
+          cp_async_wait<NB - 1>();
+          consume_ring(b, k + b * U);
+          ring_load(b, k + (b + NB) * U, k + (b + NB) * U < cmax);
+        }
+      }
+    }
+    cp_async_wait<0>();                                 // nothing of this chunk is left in flight when the next one reuses the slots
+#else
     auto consume = [&](HalfRow<T>(&buf)[U], int k) {
       float dsum[U];
 #pragma unroll
@@ -1058,6 +1182,7 @@ __global__ void __launch_bounds__(kEdgeThreads, EDGE_MINB16_BWD) edge_bwd16_kern
         }
       }
     }
+#endif
     if (valid) {
       de[q] = my_de;          // read again by ds_dst right after this kernel: left to the default policy
       dss += my_de;

@@ -131,6 +131,26 @@ constexpr int kEdgeThreads = 128;
 #define EDGE_MINB_H4_BWD 4
 #endif
 
+// > 0: the warp-per-row kernels (heads > 1 or 256 channels) stage their gathered rows in per-thread cp.async rings of that many load
+// groups as well (see EDGE_FWD_RING below); 0 = two register-buffered groups.  Config 3 (heads 4, bf16 rows), ms for both layers
+// (profiles/r2am_cfg3_ring_ab.txt): forward 6.29 -> 5.14 (ring 3, 5 blocks) | 4.99 (ring 3, 6 blocks) | 5.04 (ring 2, 6 blocks);
+// backward 6.25 -> 4.59 (ring 4, 4 blocks) | 4.93 (ring 4, 5 blocks: spills) | 4.66 (ring 2, 5 blocks); step 19.0 -> 16.2 ms.
+#ifndef EDGE_GEN_FWD_RING
+#define EDGE_GEN_FWD_RING 3
+#endif
+#ifndef EDGE_GEN_BWD_RING
+#define EDGE_GEN_BWD_RING 4
+#endif
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_row(uint32_t dst_smem, const void* src) {
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T, int H, int CV>
 struct RowBuf {
   typename Raw4<T>::type v[H][CV];
@@ -236,9 +256,32 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
       const int c0 = __shfl_sync(kFull, c, 0);
       if (!valid) c = c0;
       const int cnt = min(32, end - base);
+#if EDGE_GEN_FWD_RING > 0
+      constexpr int NB = EDGE_GEN_FWD_RING;
+      using Raw = typename Raw4<T>::type;
+      __shared__ Raw ring[NB][U][H][CV][kEdgeThreads];     // private per thread; one commit per call whether or not anything is copied
+      auto ring_load = [&](int b, int k, bool on) {
+        if (on) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int ck = __shfl_sync(kFull, c, (k + u) & 31);
+            const T* hp = h + (size_t)ck * HC + lane * 4;
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh)
+#pragma unroll
+              for (int cv = 0; cv < CV; ++cv)
+                cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][hh][cv][threadIdx.x]), hp + hh * C + cv * 128);
+          }
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int b = 0; b < NB; ++b) ring_load(b, b * U, b * U < cnt);
+#else
       RowBuf<T, H, CV> bufA[U], bufB[U];
       load_group(bufA, c, 0);                              // gathers start before the softmax math
       if (U < cnt) load_group(bufB, c, U);
+#endif
 
       float p[H];
 #pragma unroll
@@ -263,6 +306,26 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
         l[hh] += p[hh];  // the denominator sees every edge; dropout acts on alpha afterwards (:88-89)
         if (DROPOUT && valid) p[hh] *= dropout_scale(seed, (uint32_t)__ldg(perm + e), hh, p_drop, inv_keep);
       }
+#if EDGE_GEN_FWD_RING > 0
+      for (int k = 0; k < cnt; k += NB * U) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          if (k + b * U < cnt) {                           // warp-uniform
+            cp_async_wait<NB - 1>();
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int hh = 0; hh < H; ++hh) {
+                const float pk = __shfl_sync(kFull, p[hh], (k + b * U + u) & 31);
+#pragma unroll
+                for (int cv = 0; cv < CV; ++cv) acc[hh][cv] = fma4(pk, to_f4(ring[b][u][hh][cv][threadIdx.x]), acc[hh][cv]);
+              }
+            ring_load(b, k + (b + NB) * U, k + (b + NB) * U < cnt);
+          }
+        }
+      }
+      cp_async_wait<0>();
+#else
       auto consume = [&](RowBuf<T, H, CV>(&buf)[U], int k) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -281,6 +344,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
           if (k + 3 * U < cnt) load_group(bufB, c, k + 3 * U);
         }
       }
+#endif
     }
     float lt[H];
 #pragma unroll
@@ -498,9 +562,29 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
       const int i0 = __shfl_sync(kFull, i, 0);
       if (!valid) i = i0;
       const int cnt = min(32, end - base);
+#if EDGE_GEN_BWD_RING > 0
+      constexpr int NB = EDGE_GEN_BWD_RING;
+      using Raw = typename Raw4<T>::type;
+      __shared__ Raw ring[NB][U][CV][kEdgeThreads];
+      auto ring_load = [&](int b, int k, bool on) {
+        if (on) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int ik = __shfl_sync(kFull, i, (k + u) & 31);
+#pragma unroll
+            for (int cv = 0; cv < CV; ++cv)
+              cp_async_row<sizeof(Raw)>((uint32_t)__cvta_generic_to_shared(&ring[b][u][cv][threadIdx.x]), dout + (size_t)ik * C + cv * 128 + lane * 4);
+          }
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int b = 0; b < NB; ++b) ring_load(b, b * U, b * U < cnt);
+#else
       GBuf bufA[U], bufB[U];
       load_group(bufA, i, 0);                      // dout gathers start before the per-edge scalar math
       if (U < cnt) load_group(bufB, i, U);
+#endif
 
       // per lane (= per edge of this chunk): agg = alpha' / H (weight of dout_i in dh_j), and the two coefficients of
       // de = alpha * (dalpha * keep - t) * slope  written as  de = gA * <dout_i, h_j> - cB
@@ -526,6 +610,48 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
           cB[hh] = alpha * st.w * gsc;
         }
       }
+#if EDGE_GEN_BWD_RING > 0
+      auto consume = [&](int b, int k) {
+        // dalpha of the U edges of this group: per-lane partial dots first, then ONE multi-value warp reduction per head
+        // (7 shuffles for 4 edges instead of 20), then each edge's owner lane fetches its total.
+        float dsum[H][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int kk = (k + u) & 31;
+#pragma unroll
+          for (int hh = 0; hh < H; ++hh) {
+            const float a = __shfl_sync(kFull, agg[hh], kk);
+            float dp = 0.f;
+#pragma unroll
+            for (int cv = 0; cv < CV; ++cv) {
+              const float4 gv = to_f4(ring[b][u][cv][threadIdx.x]);
+              acc[hh][cv] = fma4(a, gv, acc[hh][cv]);
+              dp += dot4(hj[hh][cv], gv);
+            }
+            dsum[hh][u] = dp;
+          }
+        }
+        const int mine = (lane - k) & 31;                   // which edge of the group this lane owns (if < U)
+        const bool owner = mine < U && k + mine < cnt;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+          const float tot = warp_multi_sum<U>(dsum[hh], lane);
+          const float dot = __shfl_sync(kFull, tot, (mine & (U - 1)) << (5 - Log2<U>::value));   // <dout_i, h_j> of my edge
+          if (owner) my_de[hh] = TP ? agg[hh] * dot : gA[hh] * dot - cB[hh];
+        }
+      };
+      for (int k = 0; k < cnt; k += NB * U) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          if (k + b * U < cnt) {                       // warp-uniform
+            cp_async_wait<NB - 1>();
+            consume(b, k + b * U);
+            ring_load(b, k + (b + NB) * U, k + (b + NB) * U < cnt);
+          }
+        }
+      }
+      cp_async_wait<0>();
+#else
       auto consume = [&](GBuf(&buf)[U], int k) {
         // dalpha of the U edges of this group: per-lane partial dots first, then ONE multi-value warp reduction per head
         // (7 shuffles for 4 edges instead of 20), then each edge's owner lane fetches its total.
@@ -563,6 +689,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
           if (k + 3 * U < cnt) load_group(bufB, i, k + 3 * U);
         }
       }
+#endif
       if (valid) {
 #pragma unroll
         for (int hh = 0; hh < H; ++hh) {
@@ -820,14 +947,6 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 #define EDGE_FWD_RING_BF16 2
 #endif
 
-template <int BYTES>
-__device__ __forceinline__ void cp_async_row(uint32_t dst_smem, const void* src) {
-  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float half_sum(float v) {
 #pragma unroll

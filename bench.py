@@ -268,6 +268,9 @@ def roofline_from_timing(per_call, n, e, cfg, dropout):
     if roof["traffic"]:
         roof["dram_gbs"] = round(roof["traffic"] / (per_call[dom]["avg_ms"] * 1e-3) / 1e9, 1)
         roof["dram_frac"] = round(roof["dram_gbs"] / pk["hbm_gbs"], 4)
+    if roof["frac"] > 1.0:
+        roof["frac_note"] = ("frac > 1: the gather model charges every gathered row to HBM, but ~23 % of the gathered sectors hit in L2 "
+                             "(ncu lts__t_sector_hit_rate); dram_frac is the same launch time against the bytes DRAM really moved")
     return roof
 
 

@@ -313,7 +313,9 @@ int b200gat_eval_ranks_f32(const float* z, int64_t n_users, int64_t n_items, int
  * [n_items, k] descending (self excluded; unused slots -1 / 0), counts[n_items] = how many pass >= min_similarity
  * (a prefix of the row).  n_unsafe: device int32, rows whose bf16 candidate margin could not prove the selection exact
  * and were therefore recomputed with exact fp32 dots against all columns (informational).
- * The COO triple of the reference (:103-111) is (row = item, col = nbr_idx[item, :counts[item]], sim). */
+ * The COO triple of the reference (:103-111) is (row = item, col = nbr_idx[item, :counts[item]], sim).
+ * Workspace: ~1.2 KB per item (128-d), plus 8 KB per item from 8,192 items on (the appended candidate lists of the three-sweep
+ * pipeline, csrc/knn.cu); environment: B200GAT_KNN_MODE=lists forces the register-list kernel at every size (A/B, tests). */
 int b200gat_knn_workspace_bytes(int64_t n_items, int dim, size_t* bytes /*host*/);
 int b200gat_knn_cosine_f32(const float* emb, int64_t n_items, int dim, int k, float min_similarity, int32_t* nbr_idx,
                            float* nbr_sim, int32_t* counts, int32_t* n_unsafe, void* workspace, size_t workspace_bytes,

@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
                                                                 float p_drop, uint64_t seed, OutMode om) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  // rows per load group; two groups in flight.  bf16 rows are half the registers, so twice the rows are kept in flight
+  // rows per load group (EDGE_GEN_FWD_RING groups in flight through the cp.async ring, or two in registers).  bf16 rows are half
+  // the bytes, so twice the rows make a group
   constexpr int U = ((H * CV >= 4) ? 1 : (H * CV >= 2 ? 2 : EDGE_U_FWD)) * (sizeof(T) == 2 ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(kEdgeThreads, (H * CV == 1) ? EDGE_MINB : (H *
                                                                 uint64_t seed) {
   constexpr int C = CV * 128;
   constexpr int HC = H * C;
-  constexpr int U = (CV >= 2 ? 2 : EDGE_U_BWD) * (sizeof(T) == 2 ? 2 : 1);   // dout rows per load group; two groups in flight
+  constexpr int U = (CV >= 2 ? 2 : EDGE_U_BWD) * (sizeof(T) == 2 ? 2 : 1);   // dout rows per load group; EDGE_GEN_BWD_RING groups in flight (ring) or two (registers)
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
   if (idx >= n_rows) return;
@@ -975,7 +976,7 @@ __global__ void __launch_bounds__(kEdgeThreads, sizeof(T) == 2 ? EDGE_MINB16_FWD
                                                                             float2* __restrict__ rowstat, float* __restrict__ partial,
                                                                             float p_drop, uint64_t seed, OutMode om) {
   constexpr int C = 128;
-  constexpr int U = EDGE_U16_FWD * (sizeof(T) == 2 ? 2 : 1);   // rows per load group and half; two groups in flight
+  constexpr int U = EDGE_U16_FWD * (sizeof(T) == 2 ? 2 : 1);   // rows per load group and half; EDGE_FWD_RING groups in flight (ring) or EDGE_NB16_FWD (registers)
   const int lane = threadIdx.x & 31, sl = lane & 15;
   const int idx = (blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
   if ((idx & ~1) >= n_rows) return;     // both halves past the end

@@ -118,3 +118,34 @@ def test_ladder_reduces_appends_without_losing_candidates():
     assert len(cols_c) < static
     top = np.argsort(-s, kind="stable")[:K_CAND]
     assert np.isin(top[s[top] > _kth_largest(s, K_CAND)], cols_c).all()
+
+
+def _fkey(f):
+    """csrc/knn.cu:fkey -- order-preserving float32 -> uint32 (0 is below every real value)."""
+    b = np.asarray(f, np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def _fkey_inv(k):
+    k = np.asarray(k, np.uint32)
+    return np.where(k & np.uint32(0x80000000), k & np.uint32(0x7FFFFFFF), ~k).astype(np.uint32).view(np.float32)
+
+
+def test_select_kernel_bit_search_is_the_kth_largest():
+    """select_kernel finds the 48th largest key bit by bit: the largest T with |{key >= T}| >= 48."""
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        n = int(rng.integers(48, 1025))
+        v = (rng.standard_normal(n) * rng.choice([1e-3, 0.1, 1.0])).astype(np.float32)
+        if trial % 4 == 0:
+            v = np.round(v * 8) / 8                               # ties, +0.0 and -0.0 among them
+        keys = _fkey(v)
+        assert np.array_equal(np.argsort(keys, kind="stable"), np.argsort(v + 0.0, kind="stable")) or np.all(np.diff(v[np.argsort(keys)]) >= 0)
+        assert np.array_equal(_fkey_inv(keys).view(np.uint32), v.view(np.uint32))
+        t = np.uint32(0)
+        for bit in range(31, -1, -1):
+            tr = t | np.uint32(1 << bit)
+            if int((keys >= tr).sum()) >= K_CAND:
+                t = tr
+        assert _fkey_inv(t) == np.sort(v)[-K_CAND]
+        assert int((keys > t).sum()) < K_CAND <= int((keys >= t).sum())
